@@ -1,0 +1,126 @@
+// Shared device/host helpers for the como_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/como_b200.h"
+
+namespace como {
+
+void set_last_error(const char* fmt, ...);
+int check_launch(const char* what);
+int sm_count();
+
+#define COMO_REQUIRE(cond, ...)          \
+  do {                                   \
+    if (!(cond)) {                       \
+      como::set_last_error(__VA_ARGS__); \
+      return COMO_B200_EINVAL;           \
+    }                                    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Grid-wide barrier for cooperative (co-resident) launches.  `counter` is a monotonically
+// increasing arrival count in global memory; the caller tracks `epoch` (number of barriers passed).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void red_release_add_u32(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void group_barrier(unsigned* counter, unsigned& epoch, unsigned group_size) {
+  __syncthreads();
+  epoch += 1;
+  if (threadIdx.x == 0) {
+    red_release_add_u32(counter, 1u);
+    const unsigned target = epoch * group_size;
+    while (ld_acquire_u32(counter) < target) {
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SE(3) exponential with lietorch's tangent convention [tau, phi] (translation first), restated
+// from its published algorithm (the dependency is not vendored in the reference):
+// R = I + A W + B W^2, t = (I + B W + C W^2) tau.  Row-major 4x4 out.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline void se3_exp_tau_phi(const double tau[3], const double phi[3], double T[16]) {
+  const double th2 = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+  double A, B, C;
+  if (th2 < 1e-12) {
+    A = 1.0 - th2 / 6.0;
+    B = 0.5 - th2 / 24.0;
+    C = 1.0 / 6.0 - th2 / 120.0;
+  } else {
+    const double th = sqrt(th2);
+    A = sin(th) / th;
+    B = (1.0 - cos(th)) / th2;
+    C = (th - sin(th)) / (th2 * th);
+  }
+  const double W[9] = {0, -phi[2], phi[1], phi[2], 0, -phi[0], -phi[1], phi[0], 0};
+  double WW[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += W[i * 3 + k] * W[k * 3 + j];
+      WW[i * 3 + j] = s;
+    }
+  for (int i = 0; i < 3; ++i) {
+    double t = 0;
+    for (int j = 0; j < 3; ++j) {
+      const double I = (i == j) ? 1.0 : 0.0;
+      T[i * 4 + j] = I + A * W[i * 3 + j] + B * WW[i * 3 + j];
+      t += (I + B * W[i * 3 + j] + C * WW[i * 3 + j]) * tau[j];
+    }
+    T[i * 4 + 3] = t;
+  }
+  T[12] = T[13] = T[14] = 0.0;
+  T[15] = 1.0;
+}
+
+// In-place lower Cholesky + solve of an n x n SPD system stored row-major in A (n<=16), rhs b -> x.
+// Non-PD input yields NaN (the reference never raises: cholesky_ex(check_errors=False)).
+template <int N>
+__host__ __device__ inline void chol_solve_small(double* A, double* b) {
+  for (int j = 0; j < N; ++j) {
+    double d = A[j * N + j];
+    for (int k = 0; k < j; ++k) d -= A[j * N + k] * A[j * N + k];
+    d = sqrt(d);
+    A[j * N + j] = d;
+    for (int i = j + 1; i < N; ++i) {
+      double s = A[i * N + j];
+      for (int k = 0; k < j; ++k) s -= A[i * N + k] * A[j * N + k];
+      A[i * N + j] = s / d;
+    }
+  }
+  for (int i = 0; i < N; ++i) {
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= A[i * N + k] * b[k];
+    b[i] = s / A[i * N + i];
+  }
+  for (int i = N - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int k = i + 1; k < N; ++k) s -= A[k * N + i] * b[k];
+    b[i] = s / A[i * N + i];
+  }
+}
+
+}  // namespace como

@@ -1,0 +1,100 @@
+"""Drop-in replacements for the reference's tracking operators
+(como/odom/frontend/photo_tracking.py:10-42 `photo_tracking_pyr`, :46-74 `precalc_jacobians`):
+same names, argument order and meaning, same return values -- computed by the sm_100a kernels in
+csrc/track.cu through the C ABI.  Tensors must live on a CUDA device; there is no CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from como_b200 import _lib
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, keep):
+    num_levels = len(vals_i)
+    arr = (_lib.TrackLevel * num_levels)()
+    max_n = 0
+    for l in range(num_levels):
+        v = vals_i[l]
+        if v.shape[-1] != 1:
+            raise NotImplementedError("como_b200 tracking supports tracking.color: gray (C=1) only")
+        v = v.reshape(-1).contiguous().float()
+        P = Pi[l].reshape(-1, 3).contiguous().float()
+        J = dI_dT[l].reshape(-1, 8).contiguous().float()
+        m = masks[l].reshape(-1).contiguous()
+        if m.dtype != torch.uint8:
+            m = m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
+        img = img_j[l]
+        if img.shape[0] != 1 or img.shape[1] != 1:
+            raise NotImplementedError("como_b200 tracking expects img_j[l] of shape (1,1,h,w)")
+        img = img.contiguous().float()
+        Kl = intrinsics[l].detach().to("cpu", torch.float32).reshape(-1).tolist()
+        keep += [v, P, J, m, img]
+        n = v.shape[0]
+        max_n = max(max_n, n)
+        a = arr[l]
+        a.vals, a.P, a.J, a.mask, a.img = v.data_ptr(), P.data_ptr(), J.data_ptr(), m.data_ptr(), img.data_ptr()
+        a.n, a.w, a.h = n, img.shape[-1], img.shape[-2]
+        for k in range(9):
+            a.K[k] = Kl[k]
+    return arr, max_n
+
+
+def photo_tracking_pyr(Tji_init, aff_init, vals_i, Pi, dI_dT, masks, intrinsics, img_j, photo_sigma,
+                       term_criteria, return_stats=False):
+    """Coarse-to-fine inverse-compositional tracking; inputs are per-level lists (coarsest first).
+
+    Like the reference, `photo_sigma` is accepted and ignored (the scale is 1.4826 * median |r|,
+    photo_tracking.py:132-138).  Returns (Tji (1,4,4), aff (1,2,1)) [, stats (iters, 8)].
+    """
+    dev = _lib.require_cuda(Tji_init, aff_init, *vals_i, *Pi, *dI_dT, *masks, *img_j)
+    num_levels = len(vals_i)
+    keep = []
+    with torch.cuda.device(dev):
+        arr, max_n = _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, keep)
+        T = Tji_init.detach().reshape(1, 4, 4).float().clone().contiguous()
+        aff = aff_init.detach().reshape(1, 2).float().clone().contiguous()
+        term = _lib.TrackTerm(int(term_criteria["max_iter"]), float(term_criteria["delta_norm"]),
+                              float(term_criteria["rel_tol"]), float(term_criteria["grad_norm"]))
+        cap = num_levels * term.max_iter
+        stats = torch.zeros(cap, _lib.TRACK_STAT_STRIDE, dtype=torch.float32, device=dev) if return_stats else None
+        nit = torch.zeros(1, dtype=torch.int32, device=dev) if return_stats else None
+        nbytes = _lib.track_workspace_bytes(max_n, 1)
+        ws = _workspace(nbytes, dev)
+        st = _lib.track_pyr(arr, num_levels, 1, C.byref(term), _lib.ptr(T), _lib.ptr(aff), _lib.ptr(stats),
+                            _lib.ptr(nit), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(st, "como_b200_track_pyr")
+    Tji = T.to(Tji_init.dtype)
+    aff_out = aff.reshape(1, 2, 1).to(aff_init.dtype)
+    if return_stats:
+        n = int(nit.item())
+        return Tji, aff_out, stats[:n]
+    return Tji, aff_out
+
+
+def precalc_jacobians(dI_dw, P, vals, intrinsics):
+    """dI_dw (B,N,C,2), P (B,N,3), vals (B,N,C), intrinsics (3,3) -> (B,N,C,8); C must be 1."""
+    dev = _lib.require_cuda(dI_dw, P, vals)
+    if vals.shape[2] != 1:
+        raise NotImplementedError("como_b200 precalc_jacobians supports C=1 only")
+    b, n, _ = P.shape
+    g = dI_dw.reshape(-1, 2).contiguous().float()
+    Pf = P.reshape(-1, 3).contiguous().float()
+    v = vals.reshape(-1).contiguous().float()
+    J = torch.empty(b * n, 8, dtype=torch.float32, device=dev)
+    K = (C.c_float * 9)(*intrinsics.detach().to("cpu", torch.float32).reshape(-1).tolist())
+    with torch.cuda.device(dev):
+        st = _lib.precalc_jacobians(_lib.ptr(g), _lib.ptr(Pf), _lib.ptr(v), K, b * n, _lib.ptr(J), _lib.stream_ptr(dev))
+    _lib.check(st, "como_b200_precalc_jacobians")
+    return J.reshape(b, n, 1, 8).to(dI_dw.dtype)

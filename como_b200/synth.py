@@ -49,3 +49,90 @@ def se3_exp_wv(xi):
 
 
 TRACK_PERTURB = (0.01, -0.008, 0.005, 0.02, -0.01, 0.015)  # [omega, v], SURVEY 8d
+
+
+# ---------------------------------------------------------------------------------------------
+# Synthetic tracking case in the reference's operand layout (what Tracking.update_kf_reference
+# hands to photo_tracking_pyr), built with plain torch ops.  Input generation only.
+# ---------------------------------------------------------------------------------------------
+def _gray(rgb):
+    return (0.2989 * rgb[:, 0:1] + 0.587 * rgb[:, 1:2] + 0.114 * rgb[:, 2:3]).to(rgb.dtype)
+
+
+def _blur_down(x):
+    k = torch.tensor([[1.0, 2.0, 1.0], [2.0, 4.0, 2.0], [1.0, 2.0, 1.0]], dtype=x.dtype, device=x.device) / 16.0
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1), mode="reflect")
+    return torch.nn.functional.conv2d(xp, k.view(1, 1, 3, 3))[:, :, 0::2, 0::2]
+
+
+def _scharr(x):
+    kx = torch.tensor([[-3.0, 0.0, 3.0], [-10.0, 0.0, 10.0], [-3.0, 0.0, 3.0]], dtype=x.dtype, device=x.device) / 32.0
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1), mode="reflect")
+    gx = torch.nn.functional.conv2d(xp, kx.view(1, 1, 3, 3))
+    gy = torch.nn.functional.conv2d(xp, kx.t().contiguous().view(1, 1, 3, 3))
+    return gx, gy
+
+
+def image_pyramid(gray, num_levels):
+    """Coarsest first (the reference's convention)."""
+    pyr = [gray]
+    for _ in range(num_levels - 1):
+        pyr.insert(0, _blur_down(pyr[0]))
+    return pyr
+
+
+def intrinsics_pyramid(K, num_levels):
+    """The reference's resize_intrinsics quirk: the scale is ADDED to the principal point."""
+    out = []
+    for i in range(num_levels):
+        s = 2.0 ** (-i)
+        Tm = torch.tensor([[s, 0, s], [0, s, s], [0, 0, 1.0]], dtype=K.dtype, device=K.device)
+        out.insert(0, Tm @ K)
+    return out
+
+
+def make_tracking_case(H, W, num_levels, seed=0, cell=16, device="cpu", noise2=0.03):
+    """Returns dict with per-level lists vals (1,N,1), P (1,N,3), dI_dT (1,N,1,8), mask (1,N) bool,
+    K (3,3), img2 (1,1,h,w) plus T_init (1,4,4), aff_init (1,2,1)."""
+    rgb = make_rgb(H, W, seed=seed, cell=cell)
+    depth = make_depth(H, W)
+    K = make_intrinsics(H, W)
+    g = torch.Generator().manual_seed(1000 + seed)
+    rgb2 = (rgb * 1.05 + 0.02 + noise2 * (torch.rand(rgb.shape, generator=g) - 0.5)).clamp(0, 1)
+    rgb, depth, K, rgb2 = rgb.to(device), depth.to(device), K.to(device), rgb2.to(device)
+    pyr1 = image_pyramid(_gray(rgb), num_levels)
+    pyr2 = image_pyramid(_gray(rgb2), num_levels)
+    Kp = intrinsics_pyramid(K, num_levels)
+    dpyr = [depth]
+    for _ in range(num_levels - 1):
+        dpyr.insert(0, dpyr[0][:, :, 0::2, 0::2])
+    out = dict(vals=[], P=[], dI_dT=[], mask=[], K=Kp, img=pyr2, rgb=rgb, rgb2=rgb2, depth=depth, K0=K)
+    for l in range(num_levels):
+        img = pyr1[l]
+        h, w = img.shape[-2:]
+        gx, gy = _scharr(img)
+        ys, xs = torch.meshgrid(torch.arange(h, device=device), torch.arange(w, device=device), indexing="ij")
+        xs = xs.reshape(-1).float()
+        ys = ys.reshape(-1).float()
+        z = dpyr[l].reshape(-1)
+        Kl = Kp[l]
+        X = (xs - Kl[0, 2]) / Kl[0, 0] * z
+        Y = (ys - Kl[1, 2]) / Kl[1, 1] * z
+        P = torch.stack((X, Y, z), dim=1)
+        fx, fy = Kl[0, 0], Kl[1, 1]
+        gxv, gyv = gx.reshape(-1), gy.reshape(-1)
+        a = gxv * fx / z
+        b = gyv * fy / z
+        c = -(gxv * fx * X / z + gyv * fy * Y / z) / z
+        J = torch.stack((b * (-z) + c * Y, a * z - c * X, -a * Y + b * X, a, b, c, img.reshape(-1),
+                         torch.ones_like(z)), dim=1)
+        px = fx * X / z + Kl[0, 2]
+        py = fy * Y / z + Kl[1, 2]
+        mask = (px >= -50) & (px <= w - 1 + 50) & (py >= -50) & (py <= h - 1 + 50) & (z > 1e-4)
+        out["vals"].append(img.reshape(1, -1, 1).contiguous())
+        out["P"].append(P.reshape(1, -1, 3).contiguous())
+        out["dI_dT"].append(J.reshape(1, -1, 1, 8).contiguous())
+        out["mask"].append(mask.reshape(1, -1))
+    out["T_init"] = se3_exp_wv(TRACK_PERTURB).float()[None].to(device)
+    out["aff_init"] = torch.zeros(1, 2, 1, device=device)
+    return out

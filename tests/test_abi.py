@@ -1,0 +1,37 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/como_b200.h declares."""
+import ctypes
+import os
+import re
+
+from como_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "como_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(como_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert syms, "no symbols parsed from the header"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/como_b200.h but not exported"
+    assert sorted(_lib.DECLARED_SYMBOLS) == syms
+
+
+def test_abi_version_and_error_string():
+    assert _lib.abi_version() == 1
+    assert isinstance(_lib.last_error(), bytes)
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    # null pointers are rejected before any CUDA call
+    term = _lib.TrackTerm(1, 1e-3, 1e-3, 1.0)
+    st = _lib.track_pyr(None, 1, 1, ctypes.byref(term), None, None, None, None, None, 0, None)
+    assert st == -1
+    assert b"null" in _lib.last_error()
+    assert _lib.track_workspace_bytes(1000, 1) > 1000 * 4
