@@ -123,6 +123,180 @@ def gen_track(name, H, W, end_level, max_iter, cell):
           "final t", out["T_final"][0, :3, 3], "aff", out["aff_final"].ravel())
 
 
+MAP_STATE_TENSORS = [
+    "kf_poses", "kf_aff_params", "recent_poses", "recent_aff_params", "kf_img_and_grads", "recent_img_and_grads",
+    "cov_params_img", "pm_first_obs", "pm", "logzm", "L_mm", "Kmm_inv", "Knm_Kmminv", "correspondence_mask", "P_m",
+    "obs_ref_mask", "pose_anchor", "aff_anchor", "median_depths", "depth_imgs",
+]
+
+
+def snapshot_mapping(m, prefix, out):
+    for k in MAP_STATE_TENSORS:
+        out[prefix + k] = _np(getattr(m, k))
+    out[prefix + "kf_timestamps"] = np.array(m.kf_timestamps, dtype=np.float64)
+    out[prefix + "recent_timestamps"] = np.array(m.recent_timestamps, dtype=np.float64)
+    out[prefix + "window_full"] = bool(m.window_full)
+    out[prefix + "init_scale_anchor"] = _np(m.init_scale_anchor)
+    out[prefix + "intrinsics"] = _np(m.intrinsics)
+    if hasattr(m, "P_m_anchors"):
+        out[prefix + "P_m_anchors"] = _np(m.P_m_anchors)
+
+
+def build_reference_window(H, W, NKF, NOW, M, cfg_num_kf, step=3.0):
+    """Drives the reference's own init_keyframe/add_keyframe/add_one_way_frame (real DepthCov UNet,
+    sampler and correspondence code) on the synthetic translating-plane scene of SURVEY 8d."""
+    ref_harness.load_reference()
+    import como.odom.Mapping as MP
+    from como.depth_cov.core.samplers import sample_sparse_coords
+
+    MP.init_gpu = lambda d: None
+    cfg = copy.deepcopy(ref_cfg()["mapping"])
+    cfg["device"] = "cpu"
+    cfg["model_path"] = os.path.join(ref_harness.REF, "models", "scannet.ckpt")
+    cfg["graph"]["num_keyframes"] = cfg_num_kf
+    cfg["sampling"]["max_num_coords"] = M
+    f = 525.0 * W / 640
+    Z = 2.0
+    K = torch.tensor([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]])
+    tex = synth.make_rgb(H, W, seed=0, cell=8, extra_w=int(step * (NKF + 2)) + 8).double()
+
+    def frame(k):
+        dx = k * step
+        x0 = int(dx)
+        rgb = tex[..., x0:x0 + W].clone()
+        T = torch.eye(4, dtype=torch.double)[None]
+        T[0, 0, 3] = dx * Z / f
+        return rgb, T
+
+    torch.manual_seed(0)
+    m = MP.Mapping(cfg, K)
+    m.setup()
+    rgb0, T0 = frame(0)
+    cov0 = m.run_model(rgb0)
+    with torch.no_grad():
+        coords_m, _ = sample_sparse_coords(
+            cov0, M, mode="greedy_conditional_entropy", max_stdev_thresh=1e-2, border=3, dist_thresh=0.1,
+            signal_var=m.model.get_scale(-1), fixed_var=0.0)
+    coords_m = coords_m.double()
+    assert coords_m.shape[1] == M, coords_m.shape
+    logz = torch.log(torch.full((1, M, 1), Z, dtype=torch.double))
+    m.init_keyframe(rgb0, cov0, coords_m, T0, logz, torch.zeros(1, 2, 1, dtype=torch.double), 1.0)
+    m.init_scale_anchor = torch.log(torch.tensor(Z, dtype=torch.double)).view(1, 1, 1)
+    m.is_init = True
+    for k in range(1, NKF):
+        rgb, T = frame(k)
+        # perturbed initial pose/affine so the optimiser has something to do
+        T = T.clone()
+        T[0, 0, 3] += 0.002 * ((-1) ** k)
+        T[0, 1, 3] += 0.001
+        m.add_keyframe(rgb, T, torch.tensor([[[0.01 * k], [-0.005 * k]]], dtype=torch.double), 1.0 + k)
+    nwin = m.kf_poses.shape[0]
+    t0 = m.kf_timestamps[0]
+    for j in range(NOW):
+        kk = (j % (nwin - 1)) + 0.5 + (t0 - 1.0)
+        rgb, T = frame(kk)
+        m.add_one_way_frame(rgb, T, torch.zeros(1, 2, 1, dtype=torch.double), 1.0 + kk + 0.001 * j)
+    # the reference keeps recent frames time ordered; emulate arrival order by sorting all recent state
+    order = sorted(range(len(m.recent_timestamps)), key=lambda i: m.recent_timestamps[i])
+    m.recent_timestamps = [m.recent_timestamps[i] for i in order]
+    m.recent_img_and_grads = m.recent_img_and_grads[order]
+    m.recent_poses = m.recent_poses[order]
+    m.recent_aff_params = m.recent_aff_params[order]
+    return m, cfg
+
+
+def gen_ba(name, H, W, NKF, NOW, M, cfg_num_kf, iters=3):
+    """Full Mapping.iterate golden: state in, (H, g, delta, pairs, coords_n, errors) of the first
+    iteration, state after every iteration."""
+    ref_harness.load_reference()
+    import como.odom.backend.linear_system as LS
+    import como.odom.backend.photo as PH
+    import como.odom.backend.sparse_map as SM
+    import como.odom.Mapping as MP
+
+    m, cfg = build_reference_window(H, W, NKF, NOW, M, cfg_num_kf)
+    out = {"H": H, "W": W, "M": M, "cfg_num_kf": cfg_num_kf, "iters": iters}
+    out["photo_cfg_batch"] = cfg["photo_construction"]["pairwise_batch_size"]
+    out["sigma_mean_depth_prior"] = cfg["sigmas"]["mean_depth_prior"]
+    out["sigma_scale_prior"] = cfg["sigmas"]["scale_prior"]
+    out["sigma_pose_prior"] = cfg["sigmas"]["pose_prior"]
+    snapshot_mapping(m, "in_", out)
+    cap = {}
+    orig_solve = LS.solve_system
+
+    def solve_hook(Hm, g):
+        d = orig_solve(Hm, g)
+        cap.setdefault("H", []).append(_np(Hm).copy())
+        cap.setdefault("g", []).append(_np(g).copy())
+        cap.setdefault("delta", []).append(_np(d).copy())
+        return d
+
+    orig_cps = MP.create_photo_system
+
+    def cps_hook(*a, **k):
+        r = orig_cps(*a, **k)
+        Hm, g = a[15], a[16]
+        cap.setdefault("photo_err", []).append(float(r[0]))
+        cap.setdefault("H_photo", []).append(_np(Hm).copy())
+        cap.setdefault("g_photo", []).append(_np(g).copy())
+        cap.setdefault("pairs", []).append((list(r[1][0]), list(r[1][1]), list(r[2][0]), list(r[2][1])))
+        cap.setdefault("Pwn", []).append(_np(a[4]).copy())
+        cap.setdefault("vals_n", []).append(_np(a[9]).copy())
+        cap.setdefault("median_depths_n", []).append(_np(a[8]).copy())
+        return r
+
+    orig_sub = MP.subselect_pixels
+
+    def sub_hook(*a, **k):
+        r = orig_sub(*a, **k)
+        cap.setdefault("coords_n", []).append(_np(r[0]).copy())
+        return r
+
+    LS.solve_system = solve_hook
+    MP.lin_sys.solve_system = solve_hook
+    MP.create_photo_system = cps_hook
+    MP.subselect_pixels = sub_hook
+    try:
+        for it in range(iters):
+            m.iterate()
+            out[f"it{it}_total_err"] = float(m.total_err_prev)
+            out[f"it{it}_depth_imgs"] = _np(m.depth_imgs)
+            out[f"it{it}_kf_poses"] = _np(m.kf_poses)
+            out[f"it{it}_kf_aff_params"] = _np(m.kf_aff_params)
+            out[f"it{it}_recent_poses"] = _np(m.recent_poses)
+            out[f"it{it}_recent_aff_params"] = _np(m.recent_aff_params)
+            out[f"it{it}_P_m"] = _np(m.P_m)
+            out[f"it{it}_median_depths"] = _np(m.median_depths)
+    finally:
+        LS.solve_system = orig_solve
+        MP.lin_sys.solve_system = orig_solve
+        MP.create_photo_system = orig_cps
+        MP.subselect_pixels = orig_sub
+    out["H0"] = cap["H"][0]
+    out["g0"] = cap["g"][0]
+    out["delta0"] = cap["delta"][0]
+    out["H0_photo"] = cap["H_photo"][0]
+    out["g0_photo"] = cap["g_photo"][0]
+    for it in range(iters):
+        out[f"it{it}_photo_err"] = cap["photo_err"][it]
+    pr = cap["pairs"][0]
+    out["kf_ref_ids"], out["kf_target_ids"] = np.array(pr[0]), np.array(pr[1])
+    out["one_way_kf_ids"], out["one_way_target_ids"] = np.array(pr[2]), np.array(pr[3])
+    out["coords_n"] = cap["coords_n"][0]
+    out["Pwn0"] = cap["Pwn"][0]
+    out["vals_n0"] = cap["vals_n"][0]
+    out["median_depths_n0"] = cap["median_depths_n"][0]
+    # drop bulky fields the tests do not need
+    for k in list(out.keys()):
+        if k.endswith("_rgb") or k.endswith("depth_imgs") and not k.startswith("it"):
+            pass
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    sz = os.path.getsize(os.path.join(GOLD, name + ".npz"))
+    print(name, "K", m.kf_poses.shape[0], "R", m.recent_poses.shape[0], "L", m.P_m.shape[0], "dim", out["H0"].shape,
+          "pairs", len(pr[0]), len(pr[2]), "full", m.window_full, "errs", [out[f"it{i}_total_err"] for i in range(iters)],
+          "size %.1f MB" % (sz / 1e6))
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(GOLD, exist_ok=True)
@@ -130,6 +304,9 @@ def main():
         gen_track("track_80x60_l3", 60, 80, 3, 50, 4)
         gen_track("track_80x60_l3_it1", 60, 80, 3, 1, 4)  # BASELINE config 1 shape (max_iter 1), shrunk
         gen_track("track_160x120_l4", 120, 160, 4, 50, 8)
+    if what in ("ba", "all"):
+        gen_ba("ba_k4_notfull", 48, 64, 4, 3, 16, 5)
+        gen_ba("ba_k4_full", 48, 64, 5, 3, 16, 4)
 
 
 if __name__ == "__main__":

