@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py -- measures the COMO photometric Gauss-Newton hot path on B200.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`, launched under
+torchrun for N>1 (one rank per GPU).  Prints ONE JSON line on rank 0.
+
+Workloads (config.workload):
+  track640  B independent 640x480 / 4-level frame-to-keyframe tracking problems per GPU, one cooperative
+            launch per step; metric = Gauss-Newton iterations per second (sum over problems).
+A "step" is one pass of the hot path over one batch of synthetic input.  The batch (B x 21 MB of
+reference operands + B target pyramids) is larger than the 126 MB L2, so no L2 flush is needed.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+TERM = dict(max_iter=50, delta_norm=1e-3, rel_tol=1e-3, grad_norm=1.0)  # config/como.yml:12-17
+TRACK_BYTES_PER_PX_ITER = 52  # P 12 + I_ref 4 + J 32 + target 4
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mxv = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = mxv
+            if t0 <= ts <= t1 + 0.2:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: take everything we saw
+            for ts, ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                except Exception:
+                    pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------- workloads
+def build_track_problems(B, device, seed0=0):
+    from como_b200 import synth
+
+    probs, cases = [], []
+    for b in range(B):
+        case = synth.make_tracking_case(480, 640, 4, seed=seed0 + b, device=device)
+        probs.append((case["vals"], case["P"], case["dI_dT"], case["mask"], case["K"], case["img"]))
+        cases.append(case)
+    T0 = torch.cat([c["T_init"] for c in cases], 0)
+    a0 = torch.cat([c["aff_init"] for c in cases], 0)
+    return probs, T0, a0, cases
+
+
+def run_track_ours(args, rank, world, device):
+    from como_b200 import synth
+    from como_b200.odom.frontend.photo_tracking import photo_tracking_pyr_batch
+
+    B = args.batch
+    probs, T0, a0, cases = build_track_problems(B, device, seed0=rank * B)
+    npx = [int(m.sum()) for m in cases[0]["mask"]]
+
+    def step():
+        return photo_tracking_pyr_batch(T0, a0, probs, TERM)
+
+    for _ in range(args.warmup):
+        T, aff, nit = step()
+    torch.cuda.synchronize()
+    barrier(world)
+    clk = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else 0)
+    if rank == 0:
+        clk.start()
+        time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters_total = torch.zeros((), dtype=torch.int64, device=device)
+    t_wall0 = time.time()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        T, aff, nit = step()
+        iters_total += nit.sum()
+    ev1.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    barrier(world)
+    ms = ev0.elapsed_time(ev1)
+    ms_max = allreduce_max(ms, world, device)
+    its = int(allreduce_sum(int(iters_total.item()), world, device))
+    clocks = clk.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    # algorithmic bytes of the timed region on this rank: per problem, sum over iterations of n_level*52
+    # (stats give the level of each iteration) -- measured once outside the timed loop
+    Ts, affs, stats, nit = photo_tracking_pyr_batch(T0, a0, probs, TERM, return_stats=True)
+    torch.cuda.synchronize()
+    stc = stats.cpu()
+    alg_bytes = 0
+    for b in range(B):
+        nb = int(nit[b])
+        lv = stc[b, :nb, 0].long().tolist()
+        msk = [int(m.sum()) for m in cases[b]["mask"]]
+        alg_bytes += sum(msk[l] * TRACK_BYTES_PER_PX_ITER for l in lv)
+    kernel_ms = ms / args.steps  # the step IS one kernel launch (+ a 4 KB descriptor memcpy)
+    peak, peak_src = measured_peaks()
+    ach = alg_bytes / (kernel_ms * 1e-3) / 1e9
+
+    # e2e: per step, pinned host RGB frames -> device -> gray + pyramid -> track -> pose back on the host
+    rgb_host = torch.stack([c["rgb2"][0].cpu() for c in cases]).pin_memory()  # (B,3,480,640) fp32
+    out_host = torch.empty(B, 18, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        rgb = rgb_host.to(device, non_blocking=True)
+        pr = []
+        for b in range(B):
+            pyr = synth.image_pyramid(synth._gray(rgb[b:b + 1]), 4)
+            pr.append((probs[b][0], probs[b][1], probs[b][2], probs[b][3], probs[b][4], pyr))
+        T, aff, nit = photo_tracking_pyr_batch(T0, a0, pr, TERM)
+        out_host[:, :16].copy_(T.reshape(B, 16), non_blocking=True)
+        out_host[:, 16:].copy_(aff.reshape(B, 2), non_blocking=True)
+        return nit
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    torch.cuda.synchronize()
+    barrier(world)
+    e_it = torch.zeros((), dtype=torch.int64, device=device)
+    ev0.record()
+    for _ in range(args.steps):
+        e_it += e2e_step().sum()
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    e_ms = allreduce_max(ev0.elapsed_time(ev1), world, device)
+    e_its = int(allreduce_sum(int(e_it.item()), world, device))
+
+    res = {
+        "metric": "GN-iterations/sec at 640x480 (tracking, 4-level pyramid)", "value": its / (ms_max * 1e-3),
+        "unit": "GN-it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "track640", "resolution": "640x480", "pyramid_levels": 4, "problems_per_gpu": B,
+                   "px_per_level": npx, "l2": "inputs (B x 21 MB operands) exceed the 126 MB L2; no flush",
+                   "parallelism": f"replicas x{world} (independent sequences, no collective)"},
+        "e2e": {"value": e_its / (e_ms * 1e-3), "unit": "GN-it/s",
+                "h2d_bytes_per_step": int(rgb_host.numel() * 4), "d2h_bytes_per_step": int(out_host.numel() * 4)},
+        "gpu_launches": args.steps * 1,
+        "roofline": {"kernel": "track_pyr_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "alg_bytes_per_launch": alg_bytes, "launch_ms": kernel_ms},
+        "clocks": clocks,
+    }
+    return res, cases
+
+
+def cpu_track_baseline(cases, budget_s=15.0):
+    """Oracle port of the reference tracker on the host cores (torch intra-op threads)."""
+    from oracle import track_oracle as TO
+
+    t0 = time.time()
+    its = 0
+    n = 0
+    for c in cases:
+        cc = {k: ([v.cpu() for v in val] if isinstance(val, list) else val) for k, val in c.items()}
+        _, _, trace = TO.track_pyr(c["T_init"].cpu(), c["aff_init"].cpu(), cc["vals"], cc["P"], cc["dI_dT"],
+                                   cc["mask"], cc["K"], cc["img"], TERM)
+        its += len(trace)
+        n += 1
+        if time.time() - t0 > budget_s:
+            break
+    dt = time.time() - t0
+    return {"value": its / dt, "unit": "GN-it/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} of the same 640x480 4-level tracking problems ({its} GN iterations, {dt:.1f} s)"}
+
+
+# --------------------------------------------------------------------------------------------- dist helpers
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+
+
+def allreduce_max(v, world, device):
+    if world == 1:
+        return v
+    t = torch.tensor([v], dtype=torch.float64, device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def allreduce_sum(v, world, device):
+    if world == 1:
+        return v
+    t = torch.tensor([v], dtype=torch.float64, device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+    return float(t.item())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="track640")
+    ap.add_argument("--batch", type=int, default=16)
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation of the path (oracle port; the Python reference cannot travel)
+        if rank != 0:
+            return
+        from como_b200 import synth
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        cases = [synth.make_tracking_case(480, 640, 4, seed=b) for b in range(2)]
+        vals = []
+        for _ in range(args.warmup):
+            cpu_track_baseline(cases[:1], budget_s=0.0)
+        t0 = time.time()
+        its = 0
+        for _ in range(args.steps):
+            r = cpu_track_baseline(cases[:1], budget_s=0.0)
+            its += int(r["sample"].split("(")[1].split(" ")[0])
+        dt = time.time() - t0
+        v = its / dt
+        print(json.dumps({
+            "impl": "reference", "metric": "GN-iterations/sec at 640x480 (tracking, 4-level pyramid)", "value": v,
+            "unit": "GN-it/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "track640", "resolution": "640x480", "pyramid_levels": 4},
+            "cpu_baseline": {"value": v, "unit": "GN-it/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "one 640x480 4-level tracking problem per step"},
+            "e2e": {"value": v, "unit": "GN-it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    res, cases = run_track_ours(args, rank, world, device)
+    if rank == 0:
+        res["cpu_baseline"] = cpu_track_baseline(cases) if world == 1 else None
+        print(json.dumps(res))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -14,6 +14,7 @@
 //      8x8 system (Cholesky), applies T <- T Exp(-d), a -= d6, b -= d7 and evaluates termination.
 // HBM traffic per pixel-iteration: P 12 B + I_ref 4 B + J 32 B + target 4 B (the 52 B of BASELINE.md).
 #include <cooperative_groups.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -459,26 +460,37 @@ extern "C" int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_
     return COMO_B200_EWORKSPACE;
   }
   uint8_t* ws = (uint8_t*)workspace;
-  // level descriptors -> device (padded to MAX_LEVELS per problem)
+  // level descriptors -> device (padded to MAX_LEVELS per problem) through a small ring of pinned
+  // staging slots, each guarded by an event so the host never blocks on the stream
   {
-    static thread_local como_b200_track_level_t* staging = nullptr;
-    static thread_local size_t staging_cap = 0;
+    constexpr int SLOTS = 8;
+    struct Slot {
+      como_b200_track_level_t* buf = nullptr;
+      size_t cap = 0;
+      cudaEvent_t ev = nullptr;
+    };
+    static thread_local Slot ring[SLOTS];
+    static thread_local int next = 0;
+    Slot& sl = ring[next];
+    next = (next + 1) % SLOTS;
     const size_t cnt = (size_t)num_problems * COMO_B200_MAX_LEVELS;
-    if (staging_cap < cnt) {
-      if (staging) cudaFreeHost(staging);
-      if (cudaMallocHost((void**)&staging, cnt * sizeof(como_b200_track_level_t)) != cudaSuccess) {
-        staging = nullptr;
-        staging_cap = 0;
+    if (sl.ev == nullptr) cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming);
+    else cudaEventSynchronize(sl.ev);
+    if (sl.cap < cnt) {
+      if (sl.buf) cudaFreeHost(sl.buf);
+      if (cudaMallocHost((void**)&sl.buf, cnt * sizeof(como_b200_track_level_t)) != cudaSuccess) {
+        sl.buf = nullptr;
+        sl.cap = 0;
         set_last_error("track_pyr: pinned staging allocation failed");
         return COMO_B200_ELAUNCH;
       }
-      staging_cap = cnt;
+      sl.cap = cnt;
     }
-    // the previous launch that read `staging` must have consumed it before we overwrite it
-    cudaStreamSynchronize(stream);
+    memset(sl.buf, 0, cnt * sizeof(como_b200_track_level_t));
     for (int p = 0; p < num_problems; ++p)
-      for (int l = 0; l < num_levels; ++l) staging[p * COMO_B200_MAX_LEVELS + l] = levels[p * num_levels + l];
-    cudaMemcpyAsync(ws, staging, cnt * sizeof(como_b200_track_level_t), cudaMemcpyHostToDevice, stream);
+      for (int l = 0; l < num_levels; ++l) sl.buf[p * COMO_B200_MAX_LEVELS + l] = levels[p * num_levels + l];
+    cudaMemcpyAsync(ws, sl.buf, cnt * sizeof(como_b200_track_level_t), cudaMemcpyHostToDevice, stream);
+    cudaEventRecord(sl.ev, stream);
   }
   for (int p = 0; p < num_problems; ++p)
     cudaMemsetAsync(ws + L.levels_bytes + (size_t)p * L.per_problem, 0, sizeof(TrackCtl), stream);

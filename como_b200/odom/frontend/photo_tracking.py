@@ -83,6 +83,41 @@ def photo_tracking_pyr(Tji_init, aff_init, vals_i, Pi, dI_dT, masks, intrinsics,
     return Tji, aff_out
 
 
+def photo_tracking_pyr_batch(Tji_init, aff_init, problems, term_criteria, return_stats=False):
+    """B independent frame-to-keyframe problems in ONE cooperative launch (BASELINE config 5:
+    independent sequences batched per GPU; no reference counterpart -- the reference loops in Python).
+
+    Tji_init (B,4,4), aff_init (B,2,1); problems: list of B tuples
+    (vals_i, Pi, dI_dT, masks, intrinsics, img_j), each as for photo_tracking_pyr (same num_levels).
+    Returns Tji (B,4,4), aff (B,2,1) [, stats (B, L*max_iter, 8), num_iters (B,)]."""
+    B = len(problems)
+    num_levels = len(problems[0][0])
+    dev = _lib.require_cuda(Tji_init, aff_init)
+    keep = []
+    with torch.cuda.device(dev):
+        arr = (_lib.TrackLevel * (B * num_levels))()
+        max_n = 0
+        for p, (vals_i, Pi, dI_dT, masks, intrinsics, img_j) in enumerate(problems):
+            a, mn = _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, keep)
+            max_n = max(max_n, mn)
+            for l in range(num_levels):
+                arr[p * num_levels + l] = a[l]
+        T = Tji_init.detach().reshape(B, 4, 4).float().clone().contiguous()
+        aff = aff_init.detach().reshape(B, 2).float().clone().contiguous()
+        term = _lib.TrackTerm(int(term_criteria["max_iter"]), float(term_criteria["delta_norm"]),
+                              float(term_criteria["rel_tol"]), float(term_criteria["grad_norm"]))
+        cap = num_levels * term.max_iter
+        stats = torch.zeros(B, cap, _lib.TRACK_STAT_STRIDE, dtype=torch.float32, device=dev) if return_stats else None
+        nit = torch.zeros(B, dtype=torch.int32, device=dev)
+        ws = _workspace(_lib.track_workspace_bytes(max_n, B), dev)
+        st = _lib.track_pyr(arr, num_levels, B, C.byref(term), _lib.ptr(T), _lib.ptr(aff), _lib.ptr(stats),
+                            _lib.ptr(nit), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(st, "como_b200_track_pyr")
+    if return_stats:
+        return T, aff.reshape(B, 2, 1), stats, nit
+    return T, aff.reshape(B, 2, 1), nit
+
+
 def precalc_jacobians(dI_dw, P, vals, intrinsics):
     """dI_dw (B,N,C,2), P (B,N,3), vals (B,N,C), intrinsics (3,3) -> (B,N,C,8); C must be 1."""
     dev = _lib.require_cuda(dI_dw, P, vals)
