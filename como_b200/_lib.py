@@ -51,10 +51,31 @@ precalc_jacobians = _sig(
     "como_b200_precalc_jacobians", C.c_int,
     [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.c_void_p, C.c_void_p])
 
+VP, I32, I64, F64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+median_workspace_bytes = _sig("como_b200_median_workspace_bytes", C.c_size_t, [I32, I32])
+median_f64 = _sig("como_b200_median_f64", C.c_int, [VP, VP, I32, I64, F64, VP, VP, VP, C.c_size_t, VP])
+median_f32 = _sig("como_b200_median_f32", C.c_int, [VP, VP, I32, I64, C.c_float, VP, VP, VP, C.c_size_t, VP])
+subselect_pixels = _sig("como_b200_subselect_pixels", C.c_int, [VP, I32, I32, I32, I32, VP, VP, VP])
+ba_scaffold = _sig("como_b200_ba_scaffold", C.c_int,
+                   [VP, VP, VP, VP, VP, VP, I32, I32, I32, C.POINTER(F64), VP, VP, VP])
+predictor_apply = _sig("como_b200_predictor_apply", C.c_int, [VP, VP, I32, I64, I32, VP, VP])
+predictor_colsum = _sig("como_b200_predictor_colsum", C.c_int, [VP, I64, I32, VP, VP])
+ba_photo_workspace_bytes = _sig("como_b200_ba_photo_workspace_bytes", C.c_size_t, [I32] * 6)
+ba_unit_ints = _sig("como_b200_ba_unit_ints", I32, [])
+ba_target_group = _sig("como_b200_ba_target_group", I32, [])
+ba_photo = _sig("como_b200_ba_photo", C.c_int,
+                [VP] * 20 + [I32] * 10 + [C.POINTER(F64), I32, VP, VP, VP, VP, VP, C.c_size_t, VP])
+ba_priors = _sig("como_b200_ba_priors", C.c_int,
+                 [VP] * 15 + [I32, I32, C.POINTER(F64), F64, I32, I32, I32, I32, C.POINTER(F64), I32, VP, VP, VP, VP])
+ba_update = _sig("como_b200_ba_update", C.c_int, [VP, I32, I32, I32, VP, VP, VP, VP, VP, VP])
+
 # every symbol include/como_b200.h declares (checked by tests/test_abi.py without a GPU)
 DECLARED_SYMBOLS = [
     "como_b200_abi_version", "como_b200_last_error", "como_b200_track_workspace_bytes", "como_b200_track_pyr",
-    "como_b200_precalc_jacobians",
+    "como_b200_precalc_jacobians", "como_b200_median_workspace_bytes", "como_b200_median_f64", "como_b200_median_f32",
+    "como_b200_subselect_pixels", "como_b200_ba_scaffold", "como_b200_predictor_apply", "como_b200_predictor_colsum",
+    "como_b200_ba_photo_workspace_bytes", "como_b200_ba_unit_ints", "como_b200_ba_target_group", "como_b200_ba_photo",
+    "como_b200_ba_priors", "como_b200_ba_update",
 ]
 
 

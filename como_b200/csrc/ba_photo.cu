@@ -1,0 +1,680 @@
+// Window BA photometric factors (fp64): residual pass, exact robust scale, accumulation pass, scatter.
+// Replaces create_photo_system / batch_photo_cost / interp_img / robustify_system_inplace
+// (como/odom/backend/photo.py:24-353), backproject_cloud / setup_test_points
+// (como/odom/backend/sparse_map.py:184-230) and the einsum/scatter_add_ plumbing of
+// como/odom/backend/linear_system.py:6-38.
+//
+// The reference materialises d Pw_n / d z_m as a (b,N,3,M,1) tensor (29.5 MB per pair).  It is rank one,
+//     d r / d z_m = alpha_n * Kt[n,m] * u_m,   alpha_n = (dI/dPw) . (R_wc,i Pc_n),  u_m = 1/z_m,
+// so every anchor block is a product of per-pixel scalars with the predictor row Kt[n,:]:
+//     H_zz = U (sum_n A_n k_n k_n^T) U,   A_n = sum_targets alpha^2          (per REFERENCE keyframe)
+//     g_z  = -U sum_n B_n k_n,            B_n = sum_targets alpha r
+//     H_iz = (sum_n D_n k_n^T) U,         D_n = sum_targets alpha J_i         (8-vector)
+//     H_jz = (sum_n alpha J_j k_n^T) U                                        (per pair)
+// and the 3M expansion by dz/dPw (constant per keyframe) happens in the scatter.
+//
+// Pass A (ba_residual_kernel): one warp per 32 pixels of a reference keyframe.  Stage 1 streams the 32
+//   predictor rows (512 B each, one coalesced request per row) and forms logz_n and q_n = Kt dlogz/dTwc
+//   with warp shuffles; stage 2 maps lanes to pixels and loops over the keyframe's targets: project,
+//   bilinear gather of [I,gx,gy], residual.  Writes r (contiguous, for the median) and dI/dPc.
+// Pass B (ba_accum_kernel): work unit = (reference keyframe, pixel slice, group of <= 8 targets).
+//   Predictor rows of a 32-pixel tile are staged into shared memory with 1-D bulk async copies
+//   (cp.async.bulk + mbarrier, double buffered); per-(pixel,target) Jacobians are rebuilt from the
+//   stored residual data; the Gram / stack products run as register-tiled FMAs over the tile.
+#include "ba_common.cuh"
+
+namespace como {
+
+int ba_build_frames(const double*, const double*, const double*, const double*, const double*, const double*, int, int,
+                    size_t, BAFrame*, cudaStream_t);
+template <typename T>
+int median_launch(const T*, const long long*, int, long long, T, T*, long long*, void*, size_t, cudaStream_t);
+
+constexpr double HUBER_KD = 1.345;
+
+// ================================================================================================ pass A
+constexpr int RA_THREADS = 256;
+
+__global__ void __launch_bounds__(RA_THREADS)
+ba_residual_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coords, const double* __restrict__ vals_n,
+                   const double* __restrict__ scaf, const BAFrame* __restrict__ frames,
+                   const int32_t* __restrict__ ref_ptr, const int32_t* __restrict__ ref_pairs,
+                   const int32_t* __restrict__ pair_tgt, BADims d, double* __restrict__ refbuf,
+                   double* __restrict__ rbuf, double* __restrict__ pairbuf) {
+  __shared__ double s_vec[7][BA_MAXM];  // logzm and dlogz/dTwc columns of this keyframe, zero padded
+  const int i = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int t = tid; t < 7 * BA_MAXM; t += RA_THREADS) {
+    const int v = t / BA_MAXM, m = t % BA_MAXM;
+    double x = 0.0;
+    if (m < d.M) x = scaf[((size_t)i * d.M + m) * SCAF_STRIDE + (v == 0 ? 0 : 7 + v)];
+    s_vec[v][m] = x;
+  }
+  __syncthreads();
+  const int n0 = (blockIdx.x * (RA_THREADS / 32) + wid) * 32;
+  if (n0 >= d.N) return;
+  const int m0 = 2 * lane;
+  const bool act = m0 < d.M;
+  double lv[7][2];
+#pragma unroll
+  for (int v = 0; v < 7; ++v) {
+    lv[v][0] = s_vec[v][m0 < BA_MAXM ? m0 : 0];
+    lv[v][1] = s_vec[v][m0 + 1 < BA_MAXM ? m0 + 1 : 0];
+  }
+  // ---- stage 1: 32 rows, 7 dot products each
+  double mine[7] = {0, 0, 0, 0, 0, 0, 0};
+  const int32_t* crd = coords + 2 * ((size_t)i * d.N);
+  for (int j0 = 0; j0 < 32; j0 += 4) {
+    double2 row[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int n = n0 + j0 + jj;
+      row[jj] = make_double2(0.0, 0.0);
+      if (n < d.N && act) {
+        const int r = crd[2 * n], c = crd[2 * n + 1];
+        row[jj] = *reinterpret_cast<const double2*>(Knm + (((size_t)i * d.H + r) * d.W + c) * d.M + m0);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      double acc[7];
+#pragma unroll
+      for (int v = 0; v < 7; ++v) acc[v] = row[jj].x * lv[v][0] + row[jj].y * lv[v][1];
+#pragma unroll
+      for (int v = 0; v < 7; ++v) acc[v] = warp_sum(acc[v]);
+      if (lane == j0 + jj) {
+#pragma unroll
+        for (int v = 0; v < 7; ++v) mine[v] = acc[v];
+      }
+    }
+  }
+  // ---- stage 2: lane <-> pixel
+  const int n = n0 + lane;
+  if (n >= d.N) return;
+  const BAFrame Fi = frames[i];
+  const double z = exp(mine[0]);
+  const int r = crd[2 * n], c = crd[2 * n + 1];
+  const double ray[3] = {((double)c - d.cx) / d.fx, ((double)r - d.cy) / d.fy, 1.0};
+  const double Pc[3] = {z * ray[0], z * ray[1], z};
+  double Pw[3];
+  mat3_vec(Fi.Rwc, Pc, Pw);
+  Pw[0] += Fi.twc[0];
+  Pw[1] += Fi.twc[1];
+  Pw[2] += Fi.twc[2];
+  double* rb = refbuf + ((size_t)i * d.N + n) * REF_STRIDE;
+  rb[0] = z;
+#pragma unroll
+  for (int v = 1; v < 7; ++v) rb[v] = mine[v];
+  rb[7] = 0.0;
+  const double vi = vals_n[(size_t)i * d.N + n];
+  const size_t HW = (size_t)d.H * d.W;
+  for (int t = ref_ptr[i]; t < ref_ptr[i + 1]; ++t) {
+    const int p = ref_pairs[t];
+    const BAFrame* Fj = frames + pair_tgt[p];
+    double Pj[3];
+    mat3_vec(Fj->Rcw, Pw, Pj);
+    Pj[0] += Fj->tcw[0];
+    Pj[1] += Fj->tcw[1];
+    Pj[2] += Fj->tcw[2];
+    const double X = Pj[0], Y = Pj[1], Z = Pj[2];
+    const double uu = d.fx * X / Z + d.cx, vv = d.fy * Y / Z + d.cy;
+    const bool valid = (uu >= 1.0) && (uu < (double)(d.W - 1)) && (vv >= 1.0) && (vv < (double)(d.H - 1)) && (Z > 0.0);
+    double res = __longlong_as_double(0x7ff8000000000000LL);
+    double dI[3] = {0.0, 0.0, 0.0};
+    const double vsc = exp(Fj->a - Fi.a) * vi;
+    if (valid) {
+      const double x0f = floor(uu), y0f = floor(vv);
+      const int x0 = (int)x0f, y0 = (int)y0f;
+      const double fx0 = uu - x0f, fy0 = vv - y0f, fx1 = 1.0 - fx0, fy1 = 1.0 - fy0;
+      const double w00 = fx1 * fy1, w01 = fx0 * fy1, w10 = fx1 * fy0, w11 = fx0 * fy0;
+      const double* im = Fj->img + (size_t)y0 * d.W + x0;
+      double s[3];
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const double* q = im + ch * HW;
+        s[ch] = __ldg(q) * w00 + __ldg(q + 1) * w01 + __ldg(q + d.W) * w10 + __ldg(q + d.W + 1) * w11;
+      }
+      dI[0] = s[1] * d.fx / Z;
+      dI[1] = s[2] * d.fy / Z;
+      dI[2] = -(s[1] * d.fx * X / Z + s[2] * d.fy * Y / Z) / Z;
+      res = s[0] - vsc + (Fj->b - Fi.b);
+    }
+    rbuf[(size_t)p * d.N + n] = res;
+    double* pb = pairbuf + ((size_t)p * d.N + n) * PAIR_STRIDE;
+    *reinterpret_cast<double2*>(pb) = make_double2(dI[0], dI[1]);
+    *reinterpret_cast<double2*>(pb + 2) = make_double2(dI[2], vsc);
+  }
+}
+
+// ================================================================================================ pass B
+constexpr int AC_THREADS = 256;
+constexpr int TP = 32;               // pixels per tile
+constexpr int TG = 8;                // targets per group
+constexpr int ZW = 17;               // [J_i(8) | J_j(8) | r]
+constexpr int NSMALL = 153;          // upper triangle of the 17x17 Gram
+constexpr int SMALL_STRIDE = 160;
+constexpr int STACK_ROWS = 80;       // 8 (D) + 1 (B) + 8*TG (E) = 73, padded to 5 x 16
+constexpr int PART_STRIDE = BA_MAXM * BA_MAXM + STACK_ROWS * BA_MAXM + TG * SMALL_STRIDE;  // doubles per unit
+
+struct BAUnit {
+  int ref, pix_begin, pix_end, tgt_begin, tgt_end, primary, pad0, pad1;
+};
+
+struct AccumSmem {
+  double X[2][TP][BA_MAXM];          // predictor rows (bulk-copied), double buffered
+  double Z[TG][TP][ZW + 1];
+  double E[TG][TP][8];
+  double part[TG][TP][10];           // per (target,pixel): alpha^2, alpha r, alpha J_i[8]  (primary units)
+  double coef[TP][10];               // summed over all targets of the reference keyframe
+  double refz[TP][REF_STRIDE];
+  unsigned long long mbar[2];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA unit, SASS UBLKCP), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ int tri_index(int a, int b) {  // a <= b < 17 -> index in the packed upper triangle
+  return a * ZW - (a * (a - 1)) / 2 + (b - a);
+}
+
+__global__ void __launch_bounds__(AC_THREADS, 2)
+ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coords, const double* __restrict__ scaf,
+                const BAFrame* __restrict__ frames, const int32_t* __restrict__ ref_ptr,
+                const int32_t* __restrict__ ref_pairs, const int32_t* __restrict__ pair_tgt,
+                const double* __restrict__ sigma_pair, const BAUnit* __restrict__ units, BADims d,
+                const double* __restrict__ refbuf, const double* __restrict__ rbuf, const double* __restrict__ pairbuf,
+                double* __restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  AccumSmem& S = *reinterpret_cast<AccumSmem*>(smem_raw);
+  const BAUnit un = units[blockIdx.x];
+  const int i = un.ref;
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;   // 16 x 16 register tiling of the 64 x 64 / 80 x 64 outputs
+  const int tt = tid >> 5, pl = tid & 31;   // (target in group, pixel in tile) for the coefficient stage
+  const BAFrame Fi = frames[i];
+  const int T_all = ref_ptr[i + 1] - ref_ptr[i];
+  const int ntgt = un.tgt_end - un.tgt_begin;  // <= TG targets owned by this unit
+  const unsigned row_bytes = (unsigned)(d.M * sizeof(double));
+
+  if (tid == 0) {
+    mbar_init(&S.mbar[0], 1);
+    mbar_init(&S.mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // zero the padding columns of X once (bulk copies only write the first M columns)
+  for (int t = tid; t < 2 * TP * BA_MAXM; t += AC_THREADS) (&S.X[0][0][0])[t] = 0.0;
+  __syncthreads();
+
+  double accG[4][4], accS[5][4], accZ[5];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) accG[a][b] = 0.0;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) accS[a][b] = 0.0;
+    accZ[a] = 0.0;
+  }
+
+  const int ntiles = (un.pix_end - un.pix_begin + TP - 1) / TP;
+  const int32_t* crd = coords + 2 * ((size_t)i * d.N);
+  auto issue_tile = [&](int tile, int buf) {
+    // one elected warp issues the row copies of a tile; lane <-> row
+    if (tid < 32) {
+      const int n = un.pix_begin + tile * TP + tid;
+      const bool ok = n < un.pix_end;
+      const unsigned nrows = (unsigned)min(TP, un.pix_end - (un.pix_begin + tile * TP));
+      if (tid == 0) mbar_expect_tx(&S.mbar[buf], nrows * row_bytes);
+      __syncwarp();
+      if (ok) {
+        const int r = crd[2 * n], c = crd[2 * n + 1];
+        bulk_g2s(&S.X[buf][tid][0], Knm + (((size_t)i * d.H + r) * d.W + c) * d.M, row_bytes, &S.mbar[buf]);
+      }
+    }
+  };
+  if (ntiles > 0) issue_tile(0, 0);
+
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int buf = tile & 1;
+    if (tile + 1 < ntiles) issue_tile(tile + 1, buf ^ 1);
+    const int nb = un.pix_begin + tile * TP;
+    const int npx = min(TP, un.pix_end - nb);
+    // per-pixel reference data
+    for (int t = tid; t < TP * REF_STRIDE; t += AC_THREADS) {
+      const int p = t / REF_STRIDE, q = t % REF_STRIDE;
+      S.refz[p][q] = (p < npx) ? refbuf[((size_t)i * d.N + nb + p) * REF_STRIDE + q] : 0.0;
+    }
+    __syncthreads();
+
+    // ---------------- coefficient stage: (target, pixel) threads
+    // primary units walk ALL targets of the keyframe (A,B,D need the sum); others only their own group
+    const int g_first = un.primary ? 0 : un.tgt_begin;
+    const int g_last = un.primary ? T_all : un.tgt_end;
+    double pa2 = 0.0, par = 0.0, pD[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int g0 = g_first; g0 < g_last; g0 += TG) {
+      const int t = g0 + tt;
+      const bool own_group = (g0 == un.tgt_begin);
+      double Ji[8], Jj[8], rs = 0.0, alpha = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) Ji[q] = Jj[q] = 0.0;
+      if (t < g_last && pl < npx) {
+        const int p = ref_pairs[ref_ptr[i] + t];
+        const int n = nb + pl;
+        const double r = rbuf[(size_t)p * d.N + n];
+        if (r == r) {
+          const double2 q0 = *reinterpret_cast<const double2*>(pairbuf + ((size_t)p * d.N + n) * PAIR_STRIDE);
+          const double2 q1 = *reinterpret_cast<const double2*>(pairbuf + ((size_t)p * d.N + n) * PAIR_STRIDE + 2);
+          const double sigma = sigma_pair[p];
+          const double wr = fabs(r / sigma);
+          const double wgt = (wr < HUBER_KD) ? 1.0 : HUBER_KD / wr;
+          const double sc = sqrt(wgt) / sigma;
+          rs = r * sc;
+          const double dIs[3] = {q0.x * sc, q0.y * sc, q1.x * sc};
+          const double vsc = q1.y;
+          const BAFrame* Fj = frames + pair_tgt[p];
+          // geometry of this pixel
+          const double z = S.refz[pl][0];
+          const int rr = crd[2 * n], cc = crd[2 * n + 1];
+          const double Pc[3] = {z * (((double)cc - d.cx) / d.fx), z * (((double)rr - d.cy) / d.fy), z};
+          double RPc[3], Pw[3], Pj[3];
+          mat3_vec(Fi.Rwc, Pc, RPc);
+          Pw[0] = RPc[0] + Fi.twc[0];
+          Pw[1] = RPc[1] + Fi.twc[1];
+          Pw[2] = RPc[2] + Fi.twc[2];
+          mat3_vec(Fj->Rcw, Pw, Pj);
+          Pj[0] += Fj->tcw[0];
+          Pj[1] += Fj->tcw[1];
+          Pj[2] += Fj->tcw[2];
+          // dI/dPw = dI/dPc R_cw,j   (row vector)
+          double dIw[3];
+          mat3T_vec(Fj->Rcw, dIs, dIw);
+          alpha = dIw[0] * RPc[0] + dIw[1] * RPc[1] + dIw[2] * RPc[2];
+          // reference pose: dI/dPw [-R Pc^ | R] + alpha q^T ;   b = dIw R_wc,i (row vector)
+          double bvec[3], sk[3];
+          mat3T_vec(Fi.Rwc, dIw, bvec);
+          row_times_skew(bvec, Pc, sk);
+          Ji[0] = -sk[0] + alpha * S.refz[pl][1];
+          Ji[1] = -sk[1] + alpha * S.refz[pl][2];
+          Ji[2] = -sk[2] + alpha * S.refz[pl][3];
+          Ji[3] = bvec[0] + alpha * S.refz[pl][4];
+          Ji[4] = bvec[1] + alpha * S.refz[pl][5];
+          Ji[5] = bvec[2] + alpha * S.refz[pl][6];
+          Ji[6] = vsc * sc;
+          Ji[7] = -sc;
+          // target pose: dI/dPc [Pc_j^ | -I]
+          row_times_skew(dIs, Pj, sk);
+          Jj[0] = sk[0];
+          Jj[1] = sk[1];
+          Jj[2] = sk[2];
+          Jj[3] = -dIs[0];
+          Jj[4] = -dIs[1];
+          Jj[5] = -dIs[2];
+          Jj[6] = -Ji[6];
+          Jj[7] = -Ji[7];
+        }
+      }
+      pa2 += alpha * alpha;
+      par += alpha * rs;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pD[q] += alpha * Ji[q];
+      if (own_group) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          S.Z[tt][pl][q] = Ji[q];
+          S.Z[tt][pl][8 + q] = Jj[q];
+          S.E[tt][pl][q] = alpha * Jj[q];
+        }
+        S.Z[tt][pl][16] = rs;
+      }
+    }
+    if (un.primary) {
+      S.part[tt][pl][0] = pa2;
+      S.part[tt][pl][1] = par;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) S.part[tt][pl][2 + q] = pD[q];
+    }
+    __syncthreads();
+    if (un.primary) {
+      for (int t = tid; t < TP * 10; t += AC_THREADS) {
+        const int p = t / 10, q = t % 10;
+        double s = 0.0;
+#pragma unroll
+        for (int g = 0; g < TG; ++g) s += S.part[g][p][q];
+        S.coef[p][q] = s;
+      }
+    }
+    // wait for this tile's predictor rows
+    mbar_wait(&S.mbar[buf], (tile >> 1) & 1);
+    __syncthreads();
+
+    // ---------------- product stage (register tiled)
+    for (int p = 0; p < npx; ++p) {
+      const double4 xb = *reinterpret_cast<const double4*>(&S.X[buf][p][4 * tx]);
+      const double b4[4] = {xb.x, xb.y, xb.z, xb.w};
+      if (un.primary) {
+        const double4 xa = *reinterpret_cast<const double4*>(&S.X[buf][p][4 * ty]);
+        const double A = S.coef[p][0];
+        const double a4[4] = {A * xa.x, A * xa.y, A * xa.z, A * xa.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) accG[a][b] += a4[a] * b4[b];
+      }
+      // stack rows handled by this thread: row = ty + 16*a;  0..7 D, 8 B, 9 + 8*t + q -> E[t][q]
+#pragma unroll
+      for (int a = 0; a < 5; ++a) {
+        const int row = ty + 16 * a;
+        double cf = 0.0;
+        if (row < 9) {
+          if (un.primary) cf = (row < 8) ? S.coef[p][2 + row] : S.coef[p][1];
+        } else if (row < 9 + 8 * ntgt) {
+          cf = S.E[(row - 9) >> 3][p][(row - 9) & 7];
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) accS[a][b] += cf * b4[b];
+      }
+    }
+    // small Grams: output o = tid + 256*a -> (target, packed index)
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      const int o = tid + AC_THREADS * a;
+      const int tg = o / NSMALL, idx = o % NSMALL;
+      if (tg < ntgt) {
+        // unpack idx -> (ra, rb)
+        int ra = 0, rem = idx;
+        while (rem >= ZW - ra) {
+          rem -= ZW - ra;
+          ++ra;
+        }
+        const int rbq = ra + rem;
+        double s = 0.0;
+        for (int p = 0; p < npx; ++p) s += S.Z[tg][p][ra] * S.Z[tg][p][rbq];
+        accZ[a] += s;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---------------- write the unit's partial sums
+  double* out = partial + (size_t)blockIdx.x * PART_STRIDE;
+  if (un.primary) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) out[(4 * ty + a) * BA_MAXM + 4 * tx + b] = accG[a][b];
+  }
+  double* outS = out + BA_MAXM * BA_MAXM;
+#pragma unroll
+  for (int a = 0; a < 5; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) outS[(ty + 16 * a) * BA_MAXM + 4 * tx + b] = accS[a][b];
+  double* outZ = outS + STACK_ROWS * BA_MAXM;
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    const int o = tid + AC_THREADS * a;
+    const int tg = o / NSMALL, idx = o % NSMALL;
+    if (tg < TG) outZ[tg * SMALL_STRIDE + idx] = (tg < ntgt) ? accZ[a] : 0.0;
+  }
+}
+
+// ================================================================================================ scatter
+// One CTA per reference keyframe: sums the primary units, expands M -> 3M with dz/dPw, adds into H, g.
+__global__ void __launch_bounds__(256)
+ba_scatter_ref_kernel(const double* __restrict__ partial, const int32_t* __restrict__ unit_base,
+                      const int32_t* __restrict__ unit_slices, const double* __restrict__ scaf,
+                      const double* __restrict__ dz_dP, const int32_t* __restrict__ lm_ids, BADims d, int dim,
+                      double* __restrict__ H, double* __restrict__ g) {
+  extern __shared__ double sm[];
+  double* G = sm;                          // M*M (stride BA_MAXM)
+  double* St = sm + BA_MAXM * BA_MAXM;     // 9 rows x BA_MAXM
+  __shared__ double s_u[BA_MAXM];
+  __shared__ int s_lm[BA_MAXM];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const int ub = unit_base[i], ns = unit_slices[i];
+  for (int t = tid; t < BA_MAXM * BA_MAXM + 9 * BA_MAXM; t += 256) {
+    double s = 0.0;
+    for (int sl = 0; sl < ns; ++sl) s += partial[(size_t)(ub + sl) * PART_STRIDE + t];
+    sm[t] = s;
+  }
+  if (tid < BA_MAXM) {
+    s_u[tid] = (tid < d.M) ? scaf[((size_t)i * d.M + tid) * SCAF_STRIDE + 1] : 0.0;
+    s_lm[tid] = (tid < d.M) ? lm_ids[i * d.M + tid] : 0;
+  }
+  __syncthreads();
+  const double d3[3] = {dz_dP[3 * i], dz_dP[3 * i + 1], dz_dP[3 * i + 2]};
+  const int lm_start = 8 * (d.K + d.R);
+  const int M3 = 3 * d.M;
+  // H_PP
+  for (int t = tid; t < M3 * M3; t += 256) {
+    const int ra = t / M3, rb = t % M3;
+    const int m = ra / 3, c = ra % 3, m2 = rb / 3, c2 = rb % 3;
+    const double v = d3[c] * s_u[m] * G[m * BA_MAXM + m2] * s_u[m2] * d3[c2];
+    atomicAdd(H + (size_t)(lm_start + 3 * s_lm[m] + c) * dim + (lm_start + 3 * s_lm[m2] + c2), v);
+  }
+  // g_P = -u_m v[m] d_c   (v = stack row 8)
+  for (int t = tid; t < M3; t += 256) {
+    const int m = t / 3, c = t % 3;
+    atomicAdd(g + lm_start + 3 * s_lm[m] + c, -s_u[m] * St[8 * BA_MAXM + m] * d3[c]);
+  }
+  // H_iP (reference pose x anchors), both sides
+  for (int t = tid; t < 8 * M3; t += 256) {
+    const int a = t / M3, rb = t % M3;
+    const int m = rb / 3, c = rb % 3;
+    const double v = St[a * BA_MAXM + m] * s_u[m] * d3[c];
+    const size_t ri = 8 * (size_t)i + a, ci = lm_start + 3 * s_lm[m] + c;
+    atomicAdd(H + ri * dim + ci, v);
+    atomicAdd(H + ci * dim + ri, v);
+  }
+}
+
+// One CTA per pair: pose blocks, gradient, target-pose x anchor block, robust error.
+__global__ void __launch_bounds__(256)
+ba_scatter_pair_kernel(const double* __restrict__ partial, const int32_t* __restrict__ unit_base,
+                       const int32_t* __restrict__ unit_slices, const int32_t* __restrict__ pair_ref,
+                       const int32_t* __restrict__ pair_tgt, const int32_t* __restrict__ pair_slot,
+                       const double* __restrict__ scaf, const double* __restrict__ dz_dP,
+                       const int32_t* __restrict__ lm_ids, BADims d, int dim, double* __restrict__ H,
+                       double* __restrict__ g, double* __restrict__ err) {
+  __shared__ double E[8][BA_MAXM];
+  __shared__ double Zs[SMALL_STRIDE];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const int i = pair_ref[p], f = pair_tgt[p], slot = pair_slot[p];
+  const int grp = slot / TG, tg = slot % TG;
+  const int ns = unit_slices[i];
+  const int ub = unit_base[i] + grp * ns;
+  for (int t = tid; t < 8 * BA_MAXM + SMALL_STRIDE; t += 256) {
+    double s = 0.0;
+    if (t < 8 * BA_MAXM) {
+      const int a = t / BA_MAXM, m = t % BA_MAXM;
+      for (int sl = 0; sl < ns; ++sl)
+        s += partial[(size_t)(ub + sl) * PART_STRIDE + BA_MAXM * BA_MAXM + (9 + 8 * tg + a) * BA_MAXM + m];
+      E[a][m] = s;
+    } else {
+      const int o = t - 8 * BA_MAXM;
+      for (int sl = 0; sl < ns; ++sl)
+        s += partial[(size_t)(ub + sl) * PART_STRIDE + BA_MAXM * BA_MAXM + STACK_ROWS * BA_MAXM + tg * SMALL_STRIDE + o];
+      Zs[o] = s;
+    }
+  }
+  __syncthreads();
+  const double d3[3] = {dz_dP[3 * i], dz_dP[3 * i + 1], dz_dP[3 * i + 2]};
+  const int lm_start = 8 * (d.K + d.R);
+  const size_t bi = 8 * (size_t)i, bj = 8 * (size_t)f;
+  // 17x17 packed Gram: rows 0..7 J_i, 8..15 J_j, 16 r
+  if (tid < 64) {
+    const int a = tid / 8, b = tid % 8;
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    atomicAdd(H + (bi + a) * dim + (bi + b), Zs[tri_index(lo, hi)]);
+    atomicAdd(H + (bj + a) * dim + (bj + b), Zs[tri_index(8 + lo, 8 + hi)]);
+    const double hij = Zs[tri_index(a, 8 + b)];
+    atomicAdd(H + (bi + a) * dim + (bj + b), hij);
+    atomicAdd(H + (bj + b) * dim + (bi + a), hij);
+  } else if (tid < 72) {
+    const int a = tid - 64;
+    atomicAdd(g + bi + a, -Zs[tri_index(a, 16)]);
+    atomicAdd(g + bj + a, -Zs[tri_index(8 + a, 16)]);
+  } else if (tid == 72) {
+    atomicAdd(err, Zs[tri_index(16, 16)]);
+  }
+  const int M3 = 3 * d.M;
+  for (int t = tid; t < 8 * M3; t += 256) {
+    const int a = t / M3, rb = t % M3;
+    const int m = rb / 3, c = rb % 3;
+    const double u = scaf[((size_t)i * d.M + m) * SCAF_STRIDE + 1];
+    const double v = E[a][m] * u * d3[c];
+    const size_t ri = bj + a, ci = lm_start + 3 * (size_t)lm_ids[i * d.M + m] + c;
+    atomicAdd(H + ri * dim + ci, v);
+    atomicAdd(H + ci * dim + ri, v);
+  }
+}
+
+// sigma per pair from sigma per batch
+__global__ void sigma_expand_kernel(const double* __restrict__ sigma_batch, int P, int batch, double* __restrict__ sigma_pair) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P) sigma_pair[p] = sigma_batch[p / batch];
+}
+
+}  // namespace como
+
+using namespace como;
+
+// Workspace layout (bytes), all 256-aligned:
+//   frames | refbuf | rbuf | pairbuf | sigma_batch | sigma_pair | seg_off | median hist | partial
+struct BAPhotoLayout {
+  size_t frames, refbuf, rbuf, pairbuf, sigma_batch, sigma_pair, seg_off, medws, medws_bytes, partial, total;
+};
+static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+static BAPhotoLayout ba_photo_layout(int K, int R, int N, int P, int num_units, int num_batches) {
+  BAPhotoLayout L;
+  size_t o = 0;
+  L.frames = o; o += al256((size_t)(K + R) * sizeof(BAFrame));
+  L.refbuf = o; o += al256((size_t)K * N * REF_STRIDE * 8);
+  L.rbuf = o; o += al256((size_t)P * N * 8);
+  L.pairbuf = o; o += al256((size_t)P * N * PAIR_STRIDE * 8);
+  L.sigma_batch = o; o += al256((size_t)num_batches * 8);
+  L.sigma_pair = o; o += al256((size_t)P * 8);
+  L.seg_off = o; o += al256((size_t)(num_batches + 1) * 8);
+  L.medws_bytes = (size_t)6 * num_batches * 2048 * 4;
+  L.medws = o; o += al256(L.medws_bytes);
+  L.partial = o; o += al256((size_t)num_units * PART_STRIDE * 8);
+  L.total = o;
+  return L;
+}
+
+extern "C" size_t como_b200_ba_photo_workspace_bytes(int32_t K, int32_t R, int32_t N, int32_t P, int32_t num_units,
+                                                     int32_t batch_size) {
+  const int nb = (P + batch_size - 1) / batch_size;
+  return ba_photo_layout(K, R, N, P, num_units, nb).total;
+}
+
+extern "C" int32_t como_b200_ba_unit_ints(void) { return (int32_t)(sizeof(BAUnit) / sizeof(int32_t)); }
+extern "C" int32_t como_b200_ba_target_group(void) { return TG; }
+
+extern "C" int como_b200_ba_photo(
+    const double* kf_poses, const double* kf_aff, const double* rec_poses, const double* rec_aff, const double* kf_img,
+    const double* rec_img, const double* Knm, const int32_t* coords, const double* vals_n, const double* scaffold,
+    const double* dz_dP, const int32_t* lm_ids, const int32_t* pair_ref, const int32_t* pair_tgt,
+    const int32_t* pair_slot, const int32_t* ref_ptr, const int32_t* ref_pairs, const int32_t* units,
+    const int32_t* unit_base, const int32_t* unit_slices, int32_t num_units, int32_t K, int32_t R, int32_t L, int32_t M,
+    int32_t N, int32_t Himg, int32_t Wimg, int32_t P, int32_t batch_size, const double* intr4, int32_t dim, double* H,
+    double* g, double* photo_err, double* sigma_out, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  COMO_REQUIRE(kf_poses && kf_aff && kf_img && Knm && coords && vals_n && scaffold && dz_dP && lm_ids && pair_ref &&
+                   pair_tgt && pair_slot && ref_ptr && ref_pairs && units && unit_base && unit_slices && intr4 && H && g &&
+                   photo_err && workspace,
+               "ba_photo: null pointer argument");
+  COMO_REQUIRE(R == 0 || (rec_poses && rec_aff && rec_img), "ba_photo: null one-way frame pointers");
+  COMO_REQUIRE(M >= 2 && M <= BA_MAXM && (M % 4) == 0, "ba_photo: M must be a multiple of 4 and <= 64 (got %d)", M);
+  COMO_REQUIRE(K >= 1 && N >= 1 && P >= 1 && batch_size >= 1 && num_units >= 1, "ba_photo: bad sizes");
+  COMO_REQUIRE(dim == 8 * (K + R) + 3 * L, "ba_photo: dim %d != 8(K+R)+3L", dim);
+  const int nbatch = (P + batch_size - 1) / batch_size;
+  const BAPhotoLayout Lo = ba_photo_layout(K, R, N, P, num_units, nbatch);
+  if (workspace_bytes < Lo.total) {
+    set_last_error("ba_photo: workspace %zu < required %zu", workspace_bytes, Lo.total);
+    return COMO_B200_EWORKSPACE;
+  }
+  unsigned char* ws = (unsigned char*)workspace;
+  BAFrame* frames = (BAFrame*)(ws + Lo.frames);
+  double* refbuf = (double*)(ws + Lo.refbuf);
+  double* rbuf = (double*)(ws + Lo.rbuf);
+  double* pairbuf = (double*)(ws + Lo.pairbuf);
+  double* sigma_batch = (double*)(ws + Lo.sigma_batch);
+  double* sigma_pair = (double*)(ws + Lo.sigma_pair);
+  long long* seg_off = (long long*)(ws + Lo.seg_off);
+  double* partial = (double*)(ws + Lo.partial);
+
+  BADims d{};
+  d.K = K; d.R = R; d.L = L; d.M = M; d.N = N; d.H = Himg; d.W = Wimg; d.P = P;
+  d.fx = intr4[0]; d.fy = intr4[1]; d.cx = intr4[2]; d.cy = intr4[3];
+
+  int rc = ba_build_frames(kf_poses, kf_aff, rec_poses, rec_aff, kf_img, rec_img, K, R, (size_t)3 * Himg * Wimg, frames, st);
+  if (rc) return rc;
+  // segment offsets of the pair batches inside rbuf (host -> device, tiny)
+  {
+    long long h_off[1026];
+    COMO_REQUIRE(nbatch <= 1024, "ba_photo: too many pair batches");
+    for (int b = 0; b <= nbatch; ++b) h_off[b] = (long long)(b * batch_size < P ? b * batch_size : P) * N;
+    cudaMemcpyAsync(seg_off, h_off, sizeof(long long) * (nbatch + 1), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);  // h_off is a stack buffer
+  }
+  {
+    dim3 grid((N + RA_THREADS - 1) / RA_THREADS, K);
+    ba_residual_kernel<<<grid, RA_THREADS, 0, st>>>(Knm, coords, vals_n, scaffold, frames, ref_ptr, ref_pairs, pair_tgt, d,
+                                                    refbuf, rbuf, pairbuf);
+    rc = check_launch("ba_residual");
+    if (rc) return rc;
+  }
+  rc = median_launch<double>(rbuf, seg_off, nbatch, (long long)batch_size * N, 1.4826, sigma_batch, nullptr,
+                             ws + Lo.medws, Lo.medws_bytes, st);
+  if (rc) return rc;
+  sigma_expand_kernel<<<(P + 127) / 128, 128, 0, st>>>(sigma_batch, P, batch_size, sigma_pair);
+  if (sigma_out) cudaMemcpyAsync(sigma_out, sigma_batch, sizeof(double) * nbatch, cudaMemcpyDeviceToDevice, st);
+  {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(ba_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccumSmem));
+      attr_set = true;
+    }
+    ba_accum_kernel<<<num_units, AC_THREADS, sizeof(AccumSmem), st>>>(
+        Knm, coords, scaffold, frames, ref_ptr, ref_pairs, pair_tgt, sigma_pair, (const BAUnit*)units, d, refbuf, rbuf,
+        pairbuf, partial);
+    rc = check_launch("ba_accum");
+    if (rc) return rc;
+  }
+  {
+    const size_t smem = (size_t)(BA_MAXM * BA_MAXM + 9 * BA_MAXM) * sizeof(double);
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaFuncSetAttribute(ba_scatter_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      attr2 = true;
+    }
+    ba_scatter_ref_kernel<<<K, 256, smem, st>>>(partial, unit_base, unit_slices, scaffold, dz_dP, lm_ids, d, dim, H, g);
+    ba_scatter_pair_kernel<<<P, 256, 0, st>>>(partial, unit_base, unit_slices, pair_ref, pair_tgt, pair_slot, scaffold,
+                                              dz_dP, lm_ids, d, dim, H, g, photo_err);
+    rc = check_launch("ba_scatter");
+  }
+  return rc;
+}

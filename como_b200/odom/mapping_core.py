@@ -1,0 +1,290 @@
+"""One window bundle-adjustment Gauss-Newton iteration on the sm_100a kernels.
+
+`iterate(state, cfg)` is the drop-in for `Mapping.iterate` (como/odom/Mapping.py:760-968): `state` is any
+object carrying the reference's Mapping attribute names (kf_poses, kf_aff_params, recent_poses, ...,
+Knm_Kmminv, L_mm, correspondence_mask, P_m, ...) -- a reference `Mapping` instance (see como_b200.patch)
+or the lightweight `WindowState` used by bench.py and the tests.  All tensors must be CUDA float64.
+There is no CPU path.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from como_b200 import _lib
+from como_b200.odom.backend.graph_pair_construction import setup_photometric_pairs
+
+SCAF = 16
+F64 = torch.float64
+
+
+class WindowState:
+    """Plain attribute bag with the reference Mapping's state names."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _i32(x, dev):
+    return torch.as_tensor(x, dtype=torch.int32).to(dev).contiguous()
+
+
+class _Plan:
+    pass
+
+
+def _structure_key(s):
+    return (tuple(float(t) for t in s.kf_timestamps), s.Knm_Kmminv.data_ptr(), tuple(s.correspondence_mask.shape),
+            s.kf_img_and_grads.data_ptr(), s.L_mm.data_ptr(), bool(s.window_full))
+
+
+def _build_kf_plan(s, cfg, dev):
+    """Everything that only changes when a keyframe is added: integer remaps, sampled pixels,
+    W = L^-T L^-1, predictor column means.  (Host integer logic mirrors sparse_map.py:73-112,
+    linear_system.py:79-89 and Mapping.py:615-623.)"""
+    p = _Plan()
+    corr = s.correspondence_mask.detach().to("cpu")
+    K, L = corr.shape
+    rows = [torch.nonzero(corr[k])[:, 0] for k in range(K)]
+    M = int(rows[0].numel())
+    if any(int(r.numel()) != M for r in rows):
+        raise NotImplementedError("como_b200 BA expects the same number of anchors in every keyframe "
+                                  "(the reference makes the same assumption, Mapping.py:607-608)")
+    lm = torch.stack(rows)  # (K,M)
+    first_kf = torch.argmax(corr.int(), dim=0)
+    first_full = torch.zeros_like(corr)
+    first_full[first_kf, torch.arange(L)] = True
+    first_b = torch.gather(first_full, 1, lm)
+    fo = torch.nonzero(first_b.reshape(-1))[:, 0]  # row-major (k*M+m) of the j-th first observation
+    if int(fo.numel()) != L:
+        raise RuntimeError("correspondence mask inconsistent: every landmark needs exactly one first observation")
+    p.K, p.L, p.M = K, L, M
+    p.lm_ids = _i32(lm, dev)
+    p.fo_slots = _i32(fo, dev)
+    if bool(s.window_full):
+        p.fix_ids = _i32(torch.nonzero(corr[0])[:, 0], dev)
+    else:
+        p.fix_ids = None
+    # sampled pixels (constant per keyframe): 4x4 non-max selection on |grad I|
+    img = s.kf_img_and_grads
+    if img.shape[1] != 3:
+        raise NotImplementedError("como_b200 BA supports mapping.color: gray (C=1) only")
+    H, W = int(img.shape[-2]), int(img.shape[-1])
+    win = int(cfg["photo_construction"]["nonmax_suppression_window"])
+    N = (H // win) * (W // win)
+    p.H, p.W, p.N = H, W, N
+    p.coords = torch.empty(K, N, 2, dtype=torch.int32, device=dev)
+    p.vals_n = torch.empty(K, N, dtype=F64, device=dev)
+    st = _lib.subselect_pixels(_lib.ptr(img.contiguous()), K, H, W, win, _lib.ptr(p.coords), _lib.ptr(p.vals_n),
+                               _lib.stream_ptr(dev))
+    _lib.check(st, "como_b200_subselect_pixels")
+    # W = L^-T L^-1  (gp_ml_cost rebuilds L^-1 every iteration, gp_priors.py:22-23; it only depends on the keyframe)
+    eye = torch.eye(M, dtype=F64, device=dev).expand(K, M, M)
+    Linv = torch.linalg.solve_triangular(s.L_mm, eye, upper=False)
+    p.LtL = (Linv.mT @ Linv).contiguous()
+    # column means of keyframe 0's predictor (mean_log_depth_cost) -- only while the window is not full
+    p.colmean = None
+    if not bool(s.window_full):
+        cs = torch.empty(M, dtype=F64, device=dev)
+        st = _lib.predictor_colsum(_lib.ptr(s.Knm_Kmminv), H * W, M, _lib.ptr(cs), _lib.stream_ptr(dev))
+        _lib.check(st, "como_b200_predictor_colsum")
+        p.colmean = cs / float(H * W)
+    return p
+
+
+def _build_pair_plan(s, cfg, kp, dev, rank=0, world=1):
+    """Pair lists, CSR by reference keyframe, and the work units of the accumulation kernel.
+    With world > 1 only the pairs whose reference keyframe belongs to this rank are kept
+    (keyframe k -> rank k % world), so each predictor slab is streamed by one GPU only."""
+    q = _Plan()
+    K = kp.K
+    R = int(s.recent_poses.shape[0]) if s.recent_poses.numel() > 0 else 0
+    ref, tgt, ow_kf, ow_t = setup_photometric_pairs(K, R, s.kf_timestamps, s.recent_timestamps, None,
+                                                    cfg["photo_construction"])
+    q.pairs_full = (ref, tgt, ow_kf, ow_t)
+    pair_ref = ref + ow_kf
+    pair_tgt = tgt + [K + t for t in ow_t]
+    keep = [i for i in range(len(pair_ref)) if pair_ref[i] % world == rank]
+    pair_ref = [pair_ref[i] for i in keep]
+    pair_tgt = [pair_tgt[i] for i in keep]
+    P = len(pair_ref)
+    q.P, q.R = P, R
+    by_ref = [[] for _ in range(K)]
+    slot = [0] * P
+    for pi, r in enumerate(pair_ref):
+        slot[pi] = len(by_ref[r])
+        by_ref[r].append(pi)
+    ref_ptr = [0]
+    ref_pairs = []
+    for r in range(K):
+        ref_pairs += by_ref[r]
+        ref_ptr.append(len(ref_pairs))
+    TG = int(_lib.ba_target_group())
+    groups = [max(1, math.ceil(len(by_ref[r]) / TG)) if len(by_ref[r]) > 0 else 0 for r in range(K)]
+    total_groups = max(1, sum(groups))
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    S = max(1, min((2 * sms) // total_groups, max(1, kp.N // 64)))
+    units, unit_base, unit_slices = [], [], []
+    for r in range(K):
+        unit_base.append(len(units))
+        unit_slices.append(S if groups[r] > 0 else 0)
+        T = len(by_ref[r])
+        for gi in range(groups[r]):
+            t0, t1 = gi * TG, min(T, (gi + 1) * TG)
+            for sl in range(S):
+                p0 = (kp.N * sl) // S
+                p1 = (kp.N * (sl + 1)) // S
+                units.append([r, p0, p1, t0, t1, 1 if gi == 0 else 0, 0, 0])
+    q.num_units = len(units)
+    q.pair_ref, q.pair_tgt, q.pair_slot = _i32(pair_ref, dev), _i32(pair_tgt, dev), _i32(slot, dev)
+    q.ref_ptr, q.ref_pairs = _i32(ref_ptr, dev), _i32(ref_pairs if ref_pairs else [0], dev)
+    q.units = _i32(units if units else [[0] * 8], dev)
+    q.unit_base, q.unit_slices = _i32(unit_base, dev), _i32(unit_slices, dev)
+    q.batch = int(cfg["photo_construction"]["pairwise_batch_size"])
+    if P > 0:
+        q.ws = torch.empty(int(_lib.ba_photo_workspace_bytes(K, R, kp.N, P, q.num_units, q.batch)), dtype=torch.uint8,
+                           device=dev)
+    else:
+        q.ws = None
+    return q
+
+
+def get_plans(s, cfg, dev, rank=0, world=1):
+    cache = s.__dict__.setdefault("_b200_cache", {})
+    key = _structure_key(s)
+    if cache.get("kf_key") != key:
+        cache["kf_plan"] = _build_kf_plan(s, cfg, dev)
+        cache["kf_key"] = key
+        cache.pop("pair_key", None)
+    pkey = (key, tuple(float(t) for t in s.recent_timestamps), rank, world)
+    if cache.get("pair_key") != pkey:
+        cache["pair_plan"] = _build_pair_plan(s, cfg, cache["kf_plan"], dev, rank, world)
+        cache["pair_key"] = pkey
+    return cache["kf_plan"], cache["pair_plan"]
+
+
+def _buf(cache, name, shape, dtype, dev):
+    t = cache.get(name)
+    if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+        t = torch.empty(shape, dtype=dtype, device=dev)
+        cache[name] = t
+    return t
+
+
+def solve_system(H, g):
+    """Drop-in for lin_sys.solve_system (como/odom/backend/linear_system.py:101-112): dense Cholesky,
+    never raises on a non-PD matrix."""
+    Lc, _ = torch.linalg.cholesky_ex(H, upper=False, check_errors=False)
+    return torch.cholesky_solve(g[:, None], Lc, upper=False)
+
+
+def iterate(s, cfg, allreduce=None, rank=0, world=1, return_debug=False):
+    """One BA Gauss-Newton iteration; mutates `s` like Mapping.iterate.  `allreduce(H, g, err)` (optional)
+    sums the normal equations across ranks when the pair blocks are sharded (NCCL over NVLink)."""
+    dev = _lib.require_cuda(s.kf_poses, s.Knm_Kmminv, s.P_m, s.kf_img_and_grads)
+    for name in ("kf_poses", "kf_aff_params", "P_m", "Knm_Kmminv", "kf_img_and_grads", "L_mm", "pm_first_obs",
+                 "median_depths"):
+        t = getattr(s, name)
+        if t.dtype != F64:
+            raise RuntimeError(f"como_b200 BA runs in float64 (mapping.dtype: double); {name} is {t.dtype}")
+        if not t.is_contiguous():
+            setattr(s, name, t.contiguous())
+    with torch.cuda.device(dev):
+        kp, pp = get_plans(s, cfg, dev, rank, world)
+        cache = s.__dict__["_b200_cache"]
+        K, L, M, N, H, W = kp.K, kp.L, kp.M, kp.N, kp.H, kp.W
+        R = pp.R
+        stream = _lib.stream_ptr(dev)
+        Kmat = s.intrinsics[0].detach().to("cpu", F64)
+        intr4 = (C.c_double * 4)(float(Kmat[0, 0]), float(Kmat[1, 1]), float(Kmat[0, 2]), float(Kmat[1, 2]))
+        if R > 0:
+            if not s.recent_poses.is_contiguous():
+                s.recent_poses = s.recent_poses.contiguous()
+            if not s.recent_aff_params.is_contiguous():
+                s.recent_aff_params = s.recent_aff_params.contiguous()
+            if not s.recent_img_and_grads.is_contiguous():
+                s.recent_img_and_grads = s.recent_img_and_grads.contiguous()
+        rec_poses = s.recent_poses if R > 0 else None
+        rec_aff = s.recent_aff_params if R > 0 else None
+        rec_img = s.recent_img_and_grads if R > 0 else None
+
+        # ---- scaffold (uses the median depths of the previous store_vars) + landmark re-initialisation
+        scaf = _buf(cache, "scaf", (K, M, SCAF), F64, dev)
+        dz_dP = _buf(cache, "dz_dP", (K, 3), F64, dev)
+        st = _lib.ba_scaffold(_lib.ptr(s.kf_poses), _lib.ptr(s.P_m), _lib.ptr(kp.lm_ids), _lib.ptr(kp.fo_slots),
+                              _lib.ptr(s.pm_first_obs), _lib.ptr(s.median_depths), K, L, M, intr4, _lib.ptr(scaf),
+                              _lib.ptr(dz_dP), stream)
+        _lib.check(st, "como_b200_ba_scaffold")
+
+        # ---- store_vars: dense depth of every keyframe + exact per-keyframe median
+        depth = torch.empty(K, 1, H, W, dtype=F64, device=dev)
+        st = _lib.predictor_apply(_lib.ptr(s.Knm_Kmminv), _lib.ptr(scaf), K, H * W, M, _lib.ptr(depth), stream)
+        _lib.check(st, "como_b200_predictor_apply")
+        med_new = torch.empty(K, dtype=F64, device=dev)
+        seg = cache.get("depth_seg")
+        if seg is None or seg.numel() != K + 1:
+            seg = (torch.arange(K + 1, dtype=torch.int64) * (H * W)).to(dev)
+            cache["depth_seg"] = seg
+        mws = _buf(cache, "med_ws", (int(_lib.median_workspace_bytes(K, 8)),), torch.uint8, dev)
+        st = _lib.median_f64(_lib.ptr(depth), _lib.ptr(seg), K, H * W, 1.0, _lib.ptr(med_new), None, _lib.ptr(mws),
+                             mws.numel(), stream)
+        _lib.check(st, "como_b200_median_f64")
+        s.pm = scaf[:, :, 2:4].clone()
+        s.logzm = scaf[:, :, 0:1].clone()
+        s.depth_imgs = depth
+        s.median_depths = med_new
+
+        # ---- normal equations
+        dim = 8 * (K + R) + 3 * L
+        Hm = _buf(cache, "H", (dim, dim), F64, dev)
+        g = _buf(cache, "g", (dim,), F64, dev)
+        err = _buf(cache, "err", (8,), F64, dev)
+        Hm.zero_()
+        g.zero_()
+        err.zero_()
+        nb = max(1, (pp.P + pp.batch - 1) // pp.batch)
+        sig = _buf(cache, "sigma", (nb,), F64, dev)
+        if pp.P > 0:
+            st = _lib.ba_photo(
+                _lib.ptr(s.kf_poses), _lib.ptr(s.kf_aff_params), _lib.ptr(rec_poses), _lib.ptr(rec_aff),
+                _lib.ptr(s.kf_img_and_grads), _lib.ptr(rec_img), _lib.ptr(s.Knm_Kmminv), _lib.ptr(kp.coords),
+                _lib.ptr(kp.vals_n), _lib.ptr(scaf), _lib.ptr(dz_dP), _lib.ptr(kp.lm_ids), _lib.ptr(pp.pair_ref),
+                _lib.ptr(pp.pair_tgt), _lib.ptr(pp.pair_slot), _lib.ptr(pp.ref_ptr), _lib.ptr(pp.ref_pairs),
+                _lib.ptr(pp.units), _lib.ptr(pp.unit_base), _lib.ptr(pp.unit_slices), pp.num_units, K, R, L, M, N, H,
+                W, pp.P, pp.batch, intr4, dim, _lib.ptr(Hm), _lib.ptr(g), _lib.ptr(err), _lib.ptr(sig), _lib.ptr(pp.ws),
+                pp.ws.numel(), stream)
+            _lib.check(st, "como_b200_ba_photo")
+        if allreduce is not None:
+            allreduce(Hm, g, err)
+        dbg = None
+        if return_debug:
+            dbg = dict(H_photo=Hm.clone(), g_photo=g.clone(), sigma=sig.clone(), coords_n=kp.coords.clone(),
+                       pairs=pp.pairs_full, vals_n=kp.vals_n.clone())
+        sg = cfg["sigmas"]
+        sig4 = (C.c_double * 4)(1e-2, float(sg["pose_prior"]), float(sg["scale_prior"]), float(sg["mean_depth_prior"]))
+        full = bool(s.window_full)
+        anchors = s.P_m_anchors.contiguous() if full else None
+        scale_anchor = 0.0 if full else float(torch.as_tensor(s.init_scale_anchor).reshape(-1)[0])
+        obs = s.obs_ref_mask.contiguous().view(torch.uint8)
+        st = _lib.ba_priors(
+            _lib.ptr(scaf), _lib.ptr(dz_dP), _lib.ptr(kp.LtL), _lib.ptr(med_new), _lib.ptr(obs), _lib.ptr(s.pm_first_obs),
+            _lib.ptr(kp.lm_ids), _lib.ptr(s.kf_poses), _lib.ptr(s.pose_anchor.contiguous()), _lib.ptr(s.kf_aff_params),
+            _lib.ptr(s.aff_anchor.contiguous()), _lib.ptr(kp.colmean), _lib.ptr(s.P_m), _lib.ptr(anchors),
+            _lib.ptr(kp.fix_ids), int(kp.fix_ids.numel()) if full else 0, 1 if full else 0, sig4, scale_anchor, K, R, L,
+            M, intr4, dim, _lib.ptr(Hm), _lib.ptr(g), _lib.ptr(err), stream)
+        _lib.check(st, "como_b200_ba_priors")
+
+        # ---- solve + update
+        delta = solve_system(Hm, g)
+        st = _lib.ba_update(_lib.ptr(delta), K, R, L, _lib.ptr(s.kf_poses), _lib.ptr(s.kf_aff_params),
+                            _lib.ptr(rec_poses), _lib.ptr(rec_aff), _lib.ptr(s.P_m), stream)
+        _lib.check(st, "como_b200_ba_update")
+        s.total_err_prev = err.sum()
+        s.kf_pairs = [pp.pairs_full[0], pp.pairs_full[1]]
+        s.one_way_pairs = [pp.pairs_full[2], pp.pairs_full[3]]
+        if "iter" in s.__dict__:
+            s.iter += 1
+    if return_debug:
+        dbg.update(H=Hm.clone(), g=g.clone(), delta=delta.clone(), err=err.clone())
+        return dbg
+    return getattr(s, "converged", False)

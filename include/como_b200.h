@@ -73,6 +73,83 @@ int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_t num_level
 int como_b200_precalc_jacobians(const float* grads, const float* P, const float* vals, const float* K,
                                 int64_t n, float* J, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Exact segmented lower median (torch.median semantics) of non-negative values; NaN entries are
+ * skipped.  out[s] = scale * median(values[seg_offsets[s] : seg_offsets[s+1]]), count[s] = #valid.
+ * Replaces torch.median at como/odom/backend/photo.py:124-128, como/odom/Mapping.py:757-758,
+ * como/odom/Tracking.py:342-345.  Radix select, 11-bit digits (6 passes f64 / 3 passes f32).
+ * ------------------------------------------------------------------------------------------ */
+size_t como_b200_median_workspace_bytes(int32_t num_segments, int32_t elem_bytes);
+int como_b200_median_f64(const double* values, const int64_t* seg_offsets, int32_t num_segments,
+                         int64_t max_segment_len, double scale, double* out, int64_t* count, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int como_b200_median_f32(const float* values, const int64_t* seg_offsets, int32_t num_segments,
+                         int64_t max_segment_len, float scale, float* out, int64_t* count, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Window bundle adjustment (fp64): one Gauss-Newton iteration of como/odom/Mapping.py:760-968.
+ * All arrays are DEVICE pointers unless stated otherwise.  Keyframes K, one-way frames R, landmarks L,
+ * anchors per keyframe M (multiple of 4, <= 64), sampled pixels per keyframe N = (H/win)*(W/win).
+ * Frame index f in [0,K+R): keyframes first.  Unknown layout of H (dim x dim) / g (dim), as the
+ * reference (Mapping.py:701-747): 8 per keyframe, 8 per one-way frame, then 3 per landmark.
+ * ------------------------------------------------------------------------------------------ */
+
+/* subselect_pixels (como/odom/backend/sparse_map.py:116-142): per win x win cell the first strict
+ * maximum of |grad I|; coords (K,N,2) int32 [row,col] (bit-exact), vals (K,N) = I at those pixels. */
+int como_b200_subselect_pixels(const double* img_and_grads /*(K,3,H,W)*/, int32_t K, int32_t H, int32_t W,
+                               int32_t win, int32_t* coords, double* vals, void* stream);
+
+/* prep_geometry_scaffold / project_landmarks (Mapping.py:603-659, sparse_map.py:18-60).
+ * lm_ids (K,M) landmark id per anchor slot; fo_slots (L): flat (k*M+m) slot of the j-th first
+ * observation in row-major order; scaffold out (K,M,16): logz,u,pm(2),Pc(3),zmask,dlogz/dT(6),pad(2);
+ * dz_dP out (K,3).  Also re-initialises landmarks behind their camera in place (P_m). intr4=[fx,fy,cx,cy] HOST. */
+int como_b200_ba_scaffold(const double* kf_poses, double* P_m, const int32_t* lm_ids, const int32_t* fo_slots,
+                          const double* pm_first_obs, const double* median_depths, int32_t K, int32_t L, int32_t M,
+                          const double* intr4, double* scaffold, double* dz_dP, void* stream);
+
+/* store_vars (Mapping.py:749-758): depth (K,HW) = exp(Knm_Kmminv (K,HW,M) . logz_m); logz_m read from scaffold. */
+int como_b200_predictor_apply(const double* Knm, const double* scaffold, int32_t K, int64_t HW, int32_t M,
+                              double* depth, void* stream);
+/* column sums of one keyframe's predictor (mean_log_depth_cost, gp_priors.py:99-106); M must divide 256. */
+int como_b200_predictor_colsum(const double* Knm, int64_t HW, int32_t M, double* colsum, void* stream);
+
+/* create_photo_system (como/odom/backend/photo.py:236-353) without the materialised (b,N,3,M,1)
+ * Jacobian: residual pass, exact median per pair batch, accumulation pass, scatter into H, g.
+ * Pair p: reference keyframe pair_ref[p], target frame pair_tgt[p], pair_slot[p] = position in the
+ * reference keyframe's target list; ref_ptr (K+1) / ref_pairs (P): CSR of pairs by reference keyframe.
+ * units (num_units, como_b200_ba_unit_ints() int32 each): [ref, pix_begin, pix_end, tgt_begin, tgt_end, primary,0,0],
+ * ordered (ref, target group, slice); unit_base[ref] = first unit, unit_slices[ref] = slices per group.
+ * photo_err: += sum w (r/sigma)^2; sigma_out (ceil(P/batch)) optional. */
+size_t como_b200_ba_photo_workspace_bytes(int32_t K, int32_t R, int32_t N, int32_t P, int32_t num_units,
+                                          int32_t batch_size);
+int32_t como_b200_ba_unit_ints(void);
+int32_t como_b200_ba_target_group(void);
+int como_b200_ba_photo(const double* kf_poses, const double* kf_aff, const double* rec_poses, const double* rec_aff,
+                       const double* kf_img, const double* rec_img, const double* Knm, const int32_t* coords,
+                       const double* vals_n, const double* scaffold, const double* dz_dP, const int32_t* lm_ids,
+                       const int32_t* pair_ref, const int32_t* pair_tgt, const int32_t* pair_slot,
+                       const int32_t* ref_ptr, const int32_t* ref_pairs, const int32_t* units,
+                       const int32_t* unit_base, const int32_t* unit_slices, int32_t num_units, int32_t K, int32_t R,
+                       int32_t L, int32_t M, int32_t N, int32_t Himg, int32_t Wimg, int32_t P, int32_t batch_size,
+                       const double* intr4, int32_t dim, double* H, double* g, double* photo_err, double* sigma_out,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Prior factors of Mapping.iterate (Mapping.py:809-917; como/odom/factors/*.py).  LtL (K,M,M) = L_mm^-T L_mm^-1.
+ * sigmas4 HOST = [pixel_sigma_first, pose_prior, scale_prior, mean_depth_prior]; err8 += [_, gp, logdepth, pixel,
+ * pose, affine, scale, fixed]. */
+int como_b200_ba_priors(const double* scaffold, const double* dz_dP, const double* LtL, const double* median_depths,
+                        const uint8_t* obs_ref_mask, const double* pm_first_obs, const int32_t* lm_ids,
+                        const double* kf_poses, const double* pose_anchor, const double* kf_aff,
+                        const double* aff_anchor, const double* colmean, const double* P_m,
+                        const double* P_m_anchors, const int32_t* fix_ids, int32_t nfix, int32_t window_full,
+                        const double* sigmas4, double scale_anchor, int32_t K, int32_t R, int32_t L, int32_t M,
+                        const double* intr4, int32_t dim, double* H, double* g, double* err8, void* stream);
+
+/* update_vars (como/odom/backend/linear_system.py:115-152): T <- T Exp(delta), affine += delta, P_m += delta. */
+int como_b200_ba_update(const double* delta, int32_t K, int32_t R, int32_t L, double* kf_poses, double* kf_aff,
+                        double* rec_poses, double* rec_aff, double* P_m, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,96 @@
+"""GPU parity tests for the window-BA path (CUDA through the C ABI) against the reference-generated
+golden vectors and the oracle.  fp64: blocks of the normal equations to 1e-9 relative (summation order),
+state after each iteration to 1e-7, integer selections bit exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ba_oracle as BO
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def cuda_state(sd):
+    from como_b200.odom.mapping_core import WindowState
+
+    out = {}
+    for k, v in sd.items():
+        out[k] = v.cuda() if isinstance(v, torch.Tensor) else v
+    return WindowState(**out)
+
+
+@pytest.mark.parametrize("name", ["ba_k4_notfull", "ba_k4_full"])
+def test_iterate_vs_reference_golden(golden_dir, name):
+    from como_b200.odom import mapping_core as MC
+
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = BO.cfg_from_golden(g)
+    s = cuda_state(BO.state_from_golden(g))
+    for it in range(int(g["iters"])):
+        dbg = MC.iterate(s, cfg, return_debug=True)
+        if it == 0:
+            np.testing.assert_array_equal(dbg["coords_n"].cpu().numpy().astype(np.int64), g["coords_n"])
+            assert dbg["pairs"][0] == list(g["kf_ref_ids"]) and dbg["pairs"][1] == list(g["kf_target_ids"])
+            assert dbg["pairs"][2] == list(g["one_way_kf_ids"]) and dbg["pairs"][3] == list(g["one_way_target_ids"])
+            assert rel(dbg["H_photo"], g["H0_photo"]) < 1e-9
+            assert rel(dbg["g_photo"], g["g0_photo"]) < 1e-9
+            assert rel(dbg["H"], g["H0"]) < 1e-9
+            assert rel(dbg["g"], g["g0"]) < 1e-9
+            assert rel(dbg["delta"][:, 0], g["delta0"][:, 0]) < 1e-6
+        e = dbg["err"].cpu().numpy()
+        assert abs(e[0] - float(g[f"it{it}_photo_err"])) <= 1e-9 * float(g[f"it{it}_photo_err"])  # residual norm
+        assert abs(e.sum() - float(g[f"it{it}_total_err"])) <= 1e-9 * float(g[f"it{it}_total_err"])
+        assert rel(s.kf_poses, g[f"it{it}_kf_poses"]) < 1e-7
+        assert rel(s.kf_aff_params, g[f"it{it}_kf_aff_params"]) < 1e-6
+        assert rel(s.recent_poses, g[f"it{it}_recent_poses"]) < 1e-7
+        assert rel(s.P_m, g[f"it{it}_P_m"]) < 1e-7
+        assert rel(s.median_depths, g[f"it{it}_median_depths"]) < 1e-12
+        assert rel(s.depth_imgs, g[f"it{it}_depth_imgs"]) < 1e-12
+
+
+def test_segmented_median_matches_torch():
+    from como_b200 import _lib
+
+    torch.manual_seed(0)
+    for dtype, fn, eb in ((torch.float64, _lib.median_f64, 8), (torch.float32, _lib.median_f32, 4)):
+        lens = [1, 2, 7, 1000, 4097, 100001, 3]
+        vals = [torch.rand(n, dtype=dtype).abs() * (10.0 ** (i - 3)) for i, n in enumerate(lens)]
+        vals[3][::3] = float("nan")      # invalid markers are skipped
+        vals[4][:] = 0.25                # all equal
+        flat = torch.cat(vals).cuda()
+        off = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64).cuda()
+        out = torch.empty(len(lens), dtype=dtype, device="cuda")
+        cnt = torch.empty(len(lens), dtype=torch.int64, device="cuda")
+        ws = torch.empty(int(_lib.median_workspace_bytes(len(lens), eb)), dtype=torch.uint8, device="cuda")
+        st = fn(_lib.ptr(flat), _lib.ptr(off), len(lens), max(lens), 1.0, _lib.ptr(out), _lib.ptr(cnt), _lib.ptr(ws),
+                ws.numel(), _lib.stream_ptr())
+        _lib.check(st, "median")
+        for i, v in enumerate(vals):
+            ok = v[~torch.isnan(v)]
+            assert int(cnt[i]) == ok.numel()
+            assert float(out[i]) == float(torch.median(ok)), (dtype, i)   # bit exact order statistic
+
+
+def test_predictor_apply_and_colsum_vs_torch():
+    from como_b200 import _lib
+
+    torch.manual_seed(1)
+    K, HW, M = 3, 5000, 64
+    Knm = torch.randn(K, HW, M, dtype=torch.float64, device="cuda") * 0.1
+    scaf = torch.zeros(K, M, 16, dtype=torch.float64, device="cuda")
+    scaf[:, :, 0] = torch.randn(K, M, dtype=torch.float64, device="cuda")
+    out = torch.empty(K, HW, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.predictor_apply(_lib.ptr(Knm), _lib.ptr(scaf), K, HW, M, _lib.ptr(out), _lib.stream_ptr()), "pa")
+    ref = torch.exp((Knm @ scaf[:, :, 0:1])[..., 0])
+    assert rel(out, ref) < 1e-13
+    cs = torch.empty(M, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.predictor_colsum(_lib.ptr(Knm[0]), HW, M, _lib.ptr(cs), _lib.stream_ptr()), "cs")
+    assert rel(cs, Knm[0].sum(0)) < 1e-11
