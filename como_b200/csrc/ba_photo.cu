@@ -247,7 +247,11 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
       const int n = un.pix_begin + tile * TP + tid;
       const bool ok = n < un.pix_end;
       const unsigned nrows = (unsigned)min(TP, un.pix_end - (un.pix_begin + tile * TP));
-      if (tid == 0) mbar_expect_tx(&S.mbar[buf], nrows * row_bytes);
+      if (tid == 0) {
+        // order the generic-proxy reads of this buffer (previous tile) before the async-proxy writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&S.mbar[buf], nrows * row_bytes);
+      }
       __syncwarp();
       if (ok) {
         const int r = crd[2 * n], c = crd[2 * n + 1];
@@ -551,6 +555,11 @@ ba_scatter_pair_kernel(const double* __restrict__ partial, const int32_t* __rest
   }
 }
 
+__global__ void seg_off_kernel(long long* __restrict__ seg_off, int nbatch, int batch, int P, int N) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= nbatch) seg_off[b] = (long long)min(b * batch, P) * N;
+}
+
 // sigma per pair from sigma per batch
 __global__ void sigma_expand_kernel(const double* __restrict__ sigma_batch, int P, int batch, double* __restrict__ sigma_pair) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -632,14 +641,8 @@ extern "C" int como_b200_ba_photo(
 
   int rc = ba_build_frames(kf_poses, kf_aff, rec_poses, rec_aff, kf_img, rec_img, K, R, (size_t)3 * Himg * Wimg, frames, st);
   if (rc) return rc;
-  // segment offsets of the pair batches inside rbuf (host -> device, tiny)
-  {
-    long long h_off[1026];
-    COMO_REQUIRE(nbatch <= 1024, "ba_photo: too many pair batches");
-    for (int b = 0; b <= nbatch; ++b) h_off[b] = (long long)(b * batch_size < P ? b * batch_size : P) * N;
-    cudaMemcpyAsync(seg_off, h_off, sizeof(long long) * (nbatch + 1), cudaMemcpyHostToDevice, st);
-    cudaStreamSynchronize(st);  // h_off is a stack buffer
-  }
+  // segment offsets of the pair batches inside rbuf
+  seg_off_kernel<<<(nbatch + 128) / 128, 128, 0, st>>>(seg_off, nbatch, batch_size, P, N);
   {
     dim3 grid((N + RA_THREADS - 1) / RA_THREADS, K);
     ba_residual_kernel<<<grid, RA_THREADS, 0, st>>>(Knm, coords, vals_n, scaffold, frames, ref_ptr, ref_pairs, pair_tgt, d,
