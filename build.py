@@ -15,6 +15,10 @@ FLAGS = [
 ]
 
 
+# depthcov.cu holds the bit-exact fp32 anchor-selection path: no FMA contraction there
+PER_FILE = {"depthcov.cu": ["-fmad=false"]}
+
+
 def needs_build(srcs):
     if not os.path.exists(OUT):
         return True
@@ -37,7 +41,7 @@ def build(force=False, verbose=False, ptxas_v=False):
             [os.path.getmtime(s)] + [os.path.getmtime(d) for d in glob.glob(os.path.join(CSRC, "*.cuh"))]
             + [os.path.getmtime(d) for d in glob.glob(os.path.join(ROOT, "include", "*.h"))]):
             continue
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", s, "-o", o]
+        cmd = [NVCC] + FLAGS + PER_FILE.get(os.path.basename(s), []) + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", s, "-o", o]
         if verbose:
             print(" ".join(cmd))
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -69,13 +69,24 @@ ba_priors = _sig("como_b200_ba_priors", C.c_int,
                  [VP] * 15 + [I32, I32, C.POINTER(F64), F64, I32, I32, I32, I32, C.POINTER(F64), I32, VP, VP, VP, VP])
 ba_update = _sig("como_b200_ba_update", C.c_int, [VP, I32, I32, I32, VP, VP, VP, VP, VP, VP])
 
+F32 = C.c_float
+cross_covariance = _sig("como_b200_cross_covariance", C.c_int, [VP, VP, VP, VP, F64, I32, I32, I32, I32, VP, VP])
+chol_append = _sig("como_b200_chol_append", C.c_int, [VP, VP, VP, VP, VP, F32, I32, I32, I32, I32, VP])
+sampler_workspace_bytes = _sig("como_b200_sampler_workspace_bytes", C.c_size_t, [I32, I32])
+sampler_greedy = _sig("como_b200_sampler_greedy", C.c_int,
+                      [VP, VP, I32, I32, I32, I32, VP, VP, VP, VP, VP, VP, VP, F32, F32, I32, F32, F32, I32, VP, VP,
+                       C.c_size_t, VP])
+kmat_kmm = _sig("como_b200_kmat_kmm", C.c_int, [VP, I32, I32, I32, VP, I32, F64, F64, VP, VP, VP])
+kmat_predictor = _sig("como_b200_kmat_predictor", C.c_int, [VP, I32, I32, I32, VP, VP, VP, I32, F64, VP, VP])
+
 # every symbol include/como_b200.h declares (checked by tests/test_abi.py without a GPU)
 DECLARED_SYMBOLS = [
     "como_b200_abi_version", "como_b200_last_error", "como_b200_track_workspace_bytes", "como_b200_track_pyr",
     "como_b200_precalc_jacobians", "como_b200_median_workspace_bytes", "como_b200_median_f64", "como_b200_median_f32",
     "como_b200_subselect_pixels", "como_b200_ba_scaffold", "como_b200_predictor_apply", "como_b200_predictor_colsum",
     "como_b200_ba_photo_workspace_bytes", "como_b200_ba_unit_ints", "como_b200_ba_target_group", "como_b200_ba_photo",
-    "como_b200_ba_priors", "como_b200_ba_update",
+    "como_b200_ba_priors", "como_b200_ba_update", "como_b200_cross_covariance", "como_b200_chol_append",
+    "como_b200_sampler_workspace_bytes", "como_b200_sampler_greedy", "como_b200_kmat_kmm", "como_b200_kmat_predictor",
 ]
 
 

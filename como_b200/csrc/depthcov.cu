@@ -1,0 +1,511 @@
+// DepthCov Gaussian-process kernels (compiled with -fmad=false: the fp32 selection path must not be
+// re-associated; the GEMM part uses explicit fma()).
+//
+//  * cross_covariance / get_new_chol_obs_info : the two operators of the reference's pybind module
+//    `como_backends` (como/backend/src/cov.cpp:5-65, cov_cpu.cpp:17-85, cov_gpu.cu:17-215), same formula:
+//      K12 = scale * 2 (|E1||E2|)^(1/4) sqrt(1/|E1+E2| + 1e-8) * matern32(Q),  Q = d^T (E1+E2)^-1 d / 2
+//  * sampler step: the greedy conditional-entropy loop of como/depth_cov/core/samplers.py:211-302 run on
+//    the device (one small launch + one domain-wide launch per selected anchor, no host round trips).
+//  * K-matrix / predictor: CovarianceModule / CrossCovarianceModule (como/depth_cov/core/covariance.py:10-39,
+//    kernels.py:22-89 -- note the Python formula differs from the native one: 1/sqrt(|E1+E2| + 1e-8), and
+//    the coordinate difference is rounded to float32) fused with the (HW x M) x (M x M) product of
+//    Mapping.prep_predictor (como/odom/Mapping.py:430-468).
+#include "ba_common.cuh"
+
+namespace como {
+
+// ------------------------------------------------------------------------------------------------ native formula
+// fp32 path mirrors cov_cpu.cpp's mixed float/double expression types; pow(x, 0.25f) and exp are
+// evaluated in double and rounded once (glibc's powf/expf are correctly rounded to within ~0.5 ulp).
+__device__ __forceinline__ float cov_native_f32(float x1x, float x1y, float e1_00, float e1_01, float e1_10, float e1_11,
+                                                float x2x, float x2y, float e2_00, float e2_01, float e2_10, float e2_11,
+                                                float scale) {
+  const float dx = x1x - x2x, dy = x1y - x2y;
+  const float E00 = e1_00 + e2_00, E01 = e1_01 + e2_01, E11 = e1_11 + e2_11;
+  const float det = E00 * E11 - E01 * E01;
+  const float det_inv = (float)(1.0 / (double)det);
+  float Q = (E11 * dx * dx) - 2.0f * (E01 * dx * dy) + (E00 * dy * dy);
+  Q = (float)((double)Q * (0.5 * (double)det_inv));
+  const float d1 = e1_00 * e1_11 - e1_01 * e1_10;
+  const float d2 = e2_00 * e2_11 - e2_01 * e2_10;
+  const float pw = (float)sqrt(sqrt((double)(d1 * d2)));
+  const float ssq = (float)sqrt((double)det_inv + 1e-8);
+  const float Cc = (float)(2.0 * (double)pw * (double)ssq);
+  const float sq = (float)sqrt((double)Q + 1e-8);
+  const float tmp = (float)(1.73205080757 * (double)sq);
+  const float mat = (1.0f + tmp) * (float)exp(-(double)tmp);
+  return scale * Cc * mat;
+}
+
+__device__ __forceinline__ double cov_native_f64(double x1x, double x1y, double e1_00, double e1_01, double e1_10,
+                                                 double e1_11, double x2x, double x2y, double e2_00, double e2_01,
+                                                 double e2_10, double e2_11, double scale) {
+  const double dx = x1x - x2x, dy = x1y - x2y;
+  const double E00 = e1_00 + e2_00, E01 = e1_01 + e2_01, E11 = e1_11 + e2_11;
+  const double det_inv = 1.0 / (E00 * E11 - E01 * E01);
+  double Q = (E11 * dx * dx) - 2.0 * (E01 * dx * dy) + (E00 * dy * dy);
+  Q *= 0.5 * det_inv;
+  const double d1 = e1_00 * e1_11 - e1_01 * e1_10, d2 = e2_00 * e2_11 - e2_01 * e2_10;
+  // the reference's safe_sqrt/matern helpers take and return float even in the double kernel
+  const double Cc = 2.0 * pow(d1 * d2, 0.25) * (double)(float)sqrt((double)(float)det_inv + 1e-8);
+  const float sq = (float)sqrt((double)(float)Q + 1e-8);
+  const float tmp = (float)(1.73205080757 * (double)sq);
+  const float mat = (1.0f + tmp) * (float)exp(-(double)tmp);
+  return scale * Cc * (double)mat;
+}
+
+template <typename T>
+__global__ void cross_cov_kernel(const T* __restrict__ x1, const T* __restrict__ E1, const T* __restrict__ x2,
+                                 const T* __restrict__ E2, T scale, int n1, int n2, T* __restrict__ out) {
+  const int b = blockIdx.y;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (long long)n1 * n2) return;
+  const int i = (int)(p / n2), j = (int)(p % n2);
+  const T* a = x1 + ((size_t)b * n1 + i) * 2;
+  const T* A = E1 + ((size_t)b * n1 + i) * 4;
+  const T* c = x2 + ((size_t)b * n2 + j) * 2;
+  const T* Cm = E2 + ((size_t)b * n2 + j) * 4;
+  T v;
+  if constexpr (sizeof(T) == 4)
+    v = cov_native_f32(a[0], a[1], A[0], A[1], A[2], A[3], c[0], c[1], Cm[0], Cm[1], Cm[2], Cm[3], scale);
+  else
+    v = cov_native_f64(a[0], a[1], A[0], A[1], A[2], A[3], c[0], c[1], Cm[0], Cm[1], Cm[2], Cm[3], scale);
+  out[(size_t)b * n1 * n2 + p] = v;
+}
+
+// ------------------------------------------------------------------------------------------------ Cholesky append
+// L (B,n,n) row-major; appends row N:  L[N,:N] = L[:N,:N]^-1 k_ni (forward substitution, ascending order),
+// L[N,N] = sqrt(k_ii - sum L[N,:]^2).  One warp per batch (N <= 64... any N, serial in N like the reference).
+__global__ void chol_append_kernel(float* __restrict__ L, const float* __restrict__ k_ni, float k_ii, int n, int N) {
+  const int b = blockIdx.x;
+  float* Lb = L + (size_t)b * n * n;
+  if (threadIdx.x != 0) return;
+  float ss = 0.0f;
+  for (int r = 0; r < N; ++r) {
+    float s = k_ni[(size_t)b * N + r];
+    for (int c = 0; c < r; ++c) s -= Lb[r * n + c] * Lb[N * n + c];
+    const float v = s / Lb[r * n + r];
+    Lb[N * n + r] = v;
+    ss += v * v;
+  }
+  Lb[N * n + N] = sqrtf(k_ii - ss);
+}
+
+// obs_info (B,n,d): new row N = (k_id - sum_i L[N,i] obs_info[i,:]) / L[N,N];  var -= row^2
+__global__ void obs_info_kernel(const float* __restrict__ L, float* __restrict__ obs_info, float* __restrict__ var,
+                                const float* __restrict__ k_id, int n, int d, int N) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  const float* Lr = L + (size_t)b * n * n + (size_t)N * n;
+  float* ob = obs_info + (size_t)b * n * d;
+  float s = 0.0f;
+  for (int i = 0; i < N; ++i) s += Lr[i] * ob[(size_t)i * d + j];
+  const float v = (k_id[(size_t)b * d + j] - s) / Lr[N];
+  ob[(size_t)N * d + j] = v;
+  var[(size_t)b * d + j] -= v * v;
+}
+
+// ------------------------------------------------------------------------------------------------ sampler (device loop)
+struct SamplerState {   // per batch element, in global memory
+  int count;            // anchors selected so far
+  int next;             // domain index chosen for the next step
+  float next_stdev;     // its stdev (+1e-10)
+  int done;             // early termination flag
+};
+
+// step A (1 CTA per batch): commit `next` as anchor number i=count: coords/E, k_ni against the previous
+// anchors, Cholesky row.  Mirrors greedy_loop lines 252-274 of samplers.py.
+__global__ void sampler_commit_kernel(SamplerState* __restrict__ st, const float* __restrict__ dom_xy,
+                                      const float* __restrict__ dom_E, int d, float* __restrict__ sel_xy,
+                                      float* __restrict__ sel_E, long long* __restrict__ sel_idx, float* __restrict__ L,
+                                      int n, float signal_var, float fixed_var, int has_fixed, float max_stdev_thresh,
+                                      int terminate_early) {
+  const int b = blockIdx.x;
+  SamplerState& s = st[b];
+  __shared__ float k_ni[128];
+  const int i = s.count;
+  if (s.done || i >= n) return;
+  if (terminate_early && s.next_stdev < max_stdev_thresh) {   // batch size 1 in every reference call site
+    if (threadIdx.x == 0) s.done = 1;
+    return;
+  }
+  const int j = s.next;
+  const float* xj = dom_xy + ((size_t)b * d + j) * 2;
+  const float* Ej = dom_E + ((size_t)b * d + j) * 4;
+  float* sx = sel_xy + (size_t)b * n * 2;
+  float* sE = sel_E + (size_t)b * n * 4;
+  for (int r = threadIdx.x; r < i; r += blockDim.x)
+    k_ni[r] = cov_native_f32(sx[2 * r], sx[2 * r + 1], sE[4 * r], sE[4 * r + 1], sE[4 * r + 2], sE[4 * r + 3], xj[0], xj[1],
+                             Ej[0], Ej[1], Ej[2], Ej[3], signal_var);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float* Lb = L + (size_t)b * n * n;
+    float ss = 0.0f;
+    for (int r = 0; r < i; ++r) {
+      float acc = k_ni[r];
+      for (int c = 0; c < r; ++c) acc -= Lb[r * n + c] * Lb[i * n + c];
+      const float v = acc / Lb[r * n + r];
+      Lb[i * n + r] = v;
+      ss += v * v;
+    }
+    float k_ii = signal_var;
+    if (has_fixed) k_ii += fixed_var;
+    Lb[i * n + i] = sqrtf(k_ii - ss);
+    sx[2 * i] = xj[0];
+    sx[2 * i + 1] = xj[1];
+    for (int q = 0; q < 4; ++q) sE[4 * i + q] = Ej[q];
+    sel_idx[(size_t)b * n + i] = j;
+  }
+}
+
+// step B (grid over the domain): k_id against the new anchor, new obs_info row, variance downdate, distance
+// mask update, block-level argmax of stdev*mask (first index wins ties) -> per-block candidates.
+constexpr int SB_THREADS = 256;
+__global__ void __launch_bounds__(SB_THREADS)
+sampler_domain_kernel(const SamplerState* __restrict__ st, const float* __restrict__ dom_xy,
+                      const float* __restrict__ dom_E, int d, const float* __restrict__ sel_xy,
+                      const float* __restrict__ sel_E, const float* __restrict__ L, int n, float* __restrict__ obs_info,
+                      float* __restrict__ var, uint8_t* __restrict__ dist_ok, float signal_var, float dist_thresh_sq,
+                      float* __restrict__ cand_val, int* __restrict__ cand_idx) {
+  const int b = blockIdx.y;
+  const SamplerState s = st[b];
+  const int i = s.count;   // row being appended
+  const bool live = !(s.done || i >= n);
+  const int j = blockIdx.x * SB_THREADS + threadIdx.x;
+  float best = -1.0f;
+  int besti = 0x7fffffff;
+  if (j < d) {
+    const size_t o = (size_t)b * d + j;
+    float v = var[o];
+    uint8_t ok = dist_ok[o];
+    if (live) {
+      const float* sx = sel_xy + ((size_t)b * n + i) * 2;
+      const float* sE = sel_E + ((size_t)b * n + i) * 4;
+      const float* xj = dom_xy + o * 2;
+      const float* Ej = dom_E + o * 4;
+      const float kid = cov_native_f32(sx[0], sx[1], sE[0], sE[1], sE[2], sE[3], xj[0], xj[1], Ej[0], Ej[1], Ej[2], Ej[3],
+                                       signal_var);
+      const float* Lr = L + (size_t)b * n * n + (size_t)i * n;
+      float* ob = obs_info + (size_t)b * n * d;
+      float acc = 0.0f;
+      for (int r = 0; r < i; ++r) acc += Lr[r] * ob[(size_t)r * d + j];
+      const float nv = (kid - acc) / Lr[i];
+      ob[(size_t)i * d + j] = nv;
+      v -= nv * nv;
+      var[o] = v;
+      const float ddx = sx[0] - xj[0], ddy = sx[1] - xj[1];
+      if (!(ddx * ddx + ddy * ddy > dist_thresh_sq)) ok = 0;
+      dist_ok[o] = ok;
+    }
+    float sd = sqrtf(v);
+    if (sd != sd) sd = 0.0f;
+    sd += 1e-10f;
+    best = sd * (ok ? 1.0f : 0.0f);
+    besti = j;
+  }
+  // block argmax, smallest index on ties
+  __shared__ float sv[SB_THREADS];
+  __shared__ int si[SB_THREADS];
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = besti;
+  __syncthreads();
+  for (int o = SB_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const float v2 = sv[threadIdx.x + o];
+      const int i2 = si[threadIdx.x + o];
+      if (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) {
+        sv[threadIdx.x] = v2;
+        si[threadIdx.x] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    cand_val[(size_t)b * gridDim.x + blockIdx.x] = sv[0];
+    cand_idx[(size_t)b * gridDim.x + blockIdx.x] = si[0];
+  }
+}
+
+// step C (1 CTA per batch): final argmax over block candidates -> next index; advance the count.
+__global__ void sampler_pick_kernel(SamplerState* __restrict__ st, const float* __restrict__ cand_val,
+                                    const int* __restrict__ cand_idx, int nblocks, const float* __restrict__ var, int d,
+                                    int n, int advance) {
+  const int b = blockIdx.x;
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  float best = -1.0f;
+  int besti = 0x7fffffff;
+  for (int t = threadIdx.x; t < nblocks; t += blockDim.x) {
+    const float v = cand_val[(size_t)b * nblocks + t];
+    const int ix = cand_idx[(size_t)b * nblocks + t];
+    if (v > best || (v == best && ix < besti)) {
+      best = v;
+      besti = ix;
+    }
+  }
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = besti;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const float v2 = sv[threadIdx.x + o];
+      const int i2 = si[threadIdx.x + o];
+      if (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) {
+        sv[threadIdx.x] = v2;
+        si[threadIdx.x] = i2;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    SamplerState& s = st[b];
+    const bool live = !(s.done || s.count >= n);
+    if (advance && live) s.count += 1;
+    s.next = si[0];
+    // the reference reports gp_stdev at the chosen index (without the distance mask)
+    float sd = sqrtf(var[(size_t)b * d + si[0]]);
+    if (sd != sd) sd = 0.0f;
+    s.next_stdev = sd + 1e-10f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K-matrix (Python formula)
+__device__ __forceinline__ double cov_python_f64(double x1r, double x1c, const double* E1, double x2r, double x2c,
+                                                 const double* E2, double scale) {
+  // kernels.py:22-68: diff rounded to float32, everything else in double
+  const double d0 = (double)(float)(x1r - x2r), d1 = (double)(float)(x1c - x2c);
+  const double s00 = E1[0] + E2[0], s01 = E1[1] + E2[1], s11 = E1[3] + E2[3];
+  double Q = s11 * (d0 * d0);
+  Q += -2.0 * s01 * d0 * d1;
+  Q += s00 * (d1 * d1);
+  const double det = s00 * s11 - s01 * s01;
+  Q /= det;
+  Q *= 0.5;
+  const double r1 = sqrt(sqrt(E1[0] * E1[3] - E1[1] * E1[2]));
+  const double r2 = sqrt(sqrt(E2[0] * E2[3] - E2[1] * E2[2]));
+  const double Cc = 2.0 * r1 * r2 / sqrt(det + 1e-8);
+  const double t = 1.7320508075688772 * sqrt(Q + 1e-8);
+  return ((1.0 + t) * exp(-t)) * Cc * scale;
+}
+
+// bilinear lookup of the 4-channel covariance image with border padding (gaussian_kernel.py:52-79);
+// coords are pixel (row, col); normalisation to [-1,1] and back cancels up to rounding.
+__device__ __forceinline__ void interp_cov(const double* __restrict__ img, int H, int W, double row, double col,
+                                           double* E) {
+  double x = col, y = row;
+  x = fmin(fmax(x, 0.0), (double)(W - 1));
+  y = fmin(fmax(y, 0.0), (double)(H - 1));
+  const double x0f = floor(x), y0f = floor(y);
+  int x0 = (int)x0f, y0 = (int)y0f;
+  const double fx = x - x0f, fy = y - y0f;
+  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+  for (int c = 0; c < 4; ++c) {
+    const double* p = img + (size_t)c * H * W;
+    E[c] = p[(size_t)y0 * W + x0] * (1 - fx) * (1 - fy) + p[(size_t)y0 * W + x1] * fx * (1 - fy) +
+           p[(size_t)y1 * W + x0] * (1 - fx) * fy + p[(size_t)y1 * W + x1] * fx * fy;
+  }
+}
+
+// E_m at the anchors + K_mm (+ jitter on the diagonal).  One CTA per keyframe.
+__global__ void kmm_kernel(const double* __restrict__ cov_img, int H, int W, const double* __restrict__ coords_m, int M,
+                           double scale, double jitter, double* __restrict__ E_m, double* __restrict__ K_mm) {
+  const int b = blockIdx.x;
+  const double* img = cov_img + (size_t)b * 4 * H * W;
+  extern __shared__ double sE[];  // M*4 + M*2
+  double* sx = sE + 4 * M;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    const double r = coords_m[((size_t)b * M + m) * 2], c = coords_m[((size_t)b * M + m) * 2 + 1];
+    double E[4];
+    interp_cov(img, H, W, r, c, E);
+    for (int q = 0; q < 4; ++q) {
+      sE[4 * m + q] = E[q];
+      E_m[((size_t)b * M + m) * 4 + q] = E[q];
+    }
+    // normalised coordinates as the reference feeds them: 2*A*x + A - 1, A = 1/dims
+    sx[2 * m] = 2.0 * (1.0 / H) * r + (1.0 / H) - 1.0;
+    sx[2 * m + 1] = 2.0 * (1.0 / W) * c + (1.0 / W) - 1.0;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < M * M; t += blockDim.x) {
+    const int i = t / M, j = t % M;
+    double v = cov_python_f64(sx[2 * i], sx[2 * i + 1], sE + 4 * i, sx[2 * j], sx[2 * j + 1], sE + 4 * j, scale);
+    if (i == j) v += jitter;
+    K_mm[(size_t)b * M * M + t] = v;
+  }
+}
+
+// Fused K_nm (HW x M, never written) times K_mm^-1 (M x M):  out[p, :] = K_nm[p, :] Kinv.
+// CTA = 256 threads = 64 pixels x 4 column groups; K_nm rows for 64 pixels are built in shared memory,
+// then each thread produces 16 outputs of its pixel with fma() over Kinv held in shared memory.
+constexpr int KP_PIX = 64;
+__global__ void __launch_bounds__(256)
+kmat_predictor_kernel(const double* __restrict__ cov_img, int H, int W, const double* __restrict__ coords_m,
+                      const double* __restrict__ E_m, const double* __restrict__ Kinv, int M, double scale,
+                      double* __restrict__ out) {
+  extern __shared__ double sm[];
+  double* sKinv = sm;                      // M*M
+  double* sEm = sKinv + BA_MAXM * BA_MAXM; // M*4
+  double* sxm = sEm + 4 * BA_MAXM;         // M*2
+  double* sK = sxm + 2 * BA_MAXM;          // KP_PIX * (M+1)
+  const int b = blockIdx.y;
+  const double* img = cov_img + (size_t)b * 4 * H * W;
+  const long long HW = (long long)H * W;
+  for (int t = threadIdx.x; t < M * M; t += 256) sKinv[t] = Kinv[(size_t)b * M * M + t];
+  for (int t = threadIdx.x; t < M; t += 256) {
+    for (int q = 0; q < 4; ++q) sEm[4 * t + q] = E_m[((size_t)b * M + t) * 4 + q];
+    const double r = coords_m[((size_t)b * M + t) * 2], c = coords_m[((size_t)b * M + t) * 2 + 1];
+    sxm[2 * t] = 2.0 * (1.0 / H) * r + (1.0 / H) - 1.0;
+    sxm[2 * t + 1] = 2.0 * (1.0 / W) * c + (1.0 / W) - 1.0;
+  }
+  __syncthreads();
+  const int pitch = M + 1;
+  for (long long p0 = (long long)blockIdx.x * KP_PIX; p0 < HW; p0 += (long long)gridDim.x * KP_PIX) {
+    // build K_nm tile: thread t -> pixel t%64, anchors (t/64)*M/4 ...
+    {
+      const int pl = threadIdx.x & (KP_PIX - 1), grp = threadIdx.x >> 6;
+      const long long p = p0 + pl;
+      if (p < HW) {
+        const int r = (int)(p / W), c = (int)(p % W);
+        double En[4];
+        for (int q = 0; q < 4; ++q) En[q] = img[(size_t)q * HW + p];
+        const double xr = 2.0 * (1.0 / H) * (double)r + (1.0 / H) - 1.0, xc = 2.0 * (1.0 / W) * (double)c + (1.0 / W) - 1.0;
+        for (int m = grp * (M / 4); m < (grp + 1) * (M / 4); ++m)
+          sK[pl * pitch + m] = cov_python_f64(xr, xc, En, sxm[2 * m], sxm[2 * m + 1], sEm + 4 * m, scale);
+      }
+    }
+    __syncthreads();
+    {
+      const int pl = threadIdx.x & (KP_PIX - 1), grp = threadIdx.x >> 6;
+      const long long p = p0 + pl;
+      if (p < HW) {
+        const int c0 = grp * (M / 4);
+        double acc[16];
+        for (int q = 0; q < 16; ++q) acc[q] = 0.0;
+        for (int m = 0; m < M; ++m) {
+          const double a = sK[pl * pitch + m];
+          for (int q = 0; q < M / 4; ++q) acc[q] = fma(a, sKinv[m * M + c0 + q], acc[q]);
+        }
+        double* o = out + ((size_t)b * HW + p) * M + c0;
+        for (int q = 0; q < M / 4; ++q) o[q] = acc[q];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace como
+
+using namespace como;
+
+extern "C" int como_b200_cross_covariance(const void* x1, const void* E1, const void* x2, const void* E2, double scale,
+                                          int32_t B, int32_t n1, int32_t n2, int32_t elem_bytes, void* out, void* stream) {
+  COMO_REQUIRE(x1 && E1 && x2 && E2 && out, "cross_covariance: null pointer argument");
+  COMO_REQUIRE(elem_bytes == 4 || elem_bytes == 8, "cross_covariance: only float32/float64 are supported");
+  COMO_REQUIRE(B >= 1 && n1 >= 0 && n2 >= 0, "cross_covariance: bad shape");
+  if ((long long)n1 * n2 == 0) return COMO_B200_OK;
+  const long long total = (long long)n1 * n2;
+  dim3 grid((unsigned)((total + 255) / 256), B);
+  if (elem_bytes == 4)
+    cross_cov_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x1, (const float*)E1, (const float*)x2,
+                                                                    (const float*)E2, (float)scale, n1, n2, (float*)out);
+  else
+    cross_cov_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)x1, (const double*)E1, (const double*)x2,
+                                                                     (const double*)E2, scale, n1, n2, (double*)out);
+  return check_launch("cross_covariance");
+}
+
+extern "C" int como_b200_chol_append(float* L, float* obs_info, float* var, const float* k_ni, const float* k_id,
+                                     float k_ii, int32_t B, int32_t n, int32_t d, int32_t N, void* stream) {
+  COMO_REQUIRE(L && obs_info && var && k_ni && k_id, "get_new_chol_obs_info: null pointer argument");
+  COMO_REQUIRE(N >= 0 && N < n, "get_new_chol_obs_info: row %d out of range for n=%d", N, n);
+  cudaStream_t st = (cudaStream_t)stream;
+  chol_append_kernel<<<B, 32, 0, st>>>(L, k_ni, k_ii, n, N);
+  obs_info_kernel<<<dim3((d + 255) / 256, B), 256, 0, st>>>(L, obs_info, var, k_id, n, d, N);
+  return check_launch("get_new_chol_obs_info");
+}
+
+extern "C" size_t como_b200_sampler_workspace_bytes(int32_t B, int32_t d) {
+  const size_t nblk = (d + SB_THREADS - 1) / SB_THREADS;
+  return 256 + (size_t)B * sizeof(SamplerState) + (size_t)B * nblk * 8 + 256;
+}
+
+// Runs greedy steps m..n-1 on the device.  Preconditions (built by the host veneer exactly as
+// precalc_entropy_vars does, samplers.py:115-208): sel_xy/sel_E/sel_idx hold the first m anchors,
+// L[:m,:m] their Cholesky factor, obs_info[:m] = L^-1 K_md, var = signal_var - sum obs_info^2,
+// dist_ok = distance mask against the first m anchors.  count_out[b] = anchors selected in total.
+extern "C" int como_b200_sampler_greedy(const float* dom_xy, const float* dom_E, int32_t B, int32_t d, int32_t n, int32_t m,
+                                        float* sel_xy, float* sel_E, int64_t* sel_idx, float* L, float* obs_info,
+                                        float* var, uint8_t* dist_ok, float signal_var, float fixed_var,
+                                        int32_t has_fixed, float dist_thresh, float max_stdev_thresh,
+                                        int32_t terminate_early, int32_t* count_out, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  COMO_REQUIRE(dom_xy && dom_E && sel_xy && sel_E && sel_idx && L && obs_info && var && dist_ok && count_out && workspace,
+               "sampler_greedy: null pointer argument");
+  COMO_REQUIRE(B >= 1 && d >= 1 && n >= 1 && n <= 128 && m >= 1 && m <= n, "sampler_greedy: bad sizes");
+  if (workspace_bytes < como_b200_sampler_workspace_bytes(B, d)) {
+    set_last_error("sampler_greedy: workspace too small");
+    return COMO_B200_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = (d + SB_THREADS - 1) / SB_THREADS;
+  unsigned char* ws = (unsigned char*)workspace;
+  SamplerState* state = (SamplerState*)ws;
+  float* cand_val = (float*)(ws + 256 + (size_t)B * sizeof(SamplerState));
+  int* cand_idx = (int*)(cand_val + (size_t)B * nblk);
+  // state: count = m, not done; the first domain pass below only evaluates the arg max (row m is not live yet)
+  SamplerState h;
+  h.count = n;  // "not live": makes the first domain pass a pure argmax evaluation
+  h.next = 0;
+  h.next_stdev = 0.0f;
+  h.done = 0;
+  for (int b = 0; b < B; ++b) cudaMemcpyAsync(state + b, &h, sizeof(h), cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
+  sampler_domain_kernel<<<dim3(nblk, B), SB_THREADS, 0, st>>>(state, dom_xy, dom_E, d, sel_xy, sel_E, L, n, obs_info, var,
+                                                              dist_ok, signal_var, dist_thresh * dist_thresh, cand_val, cand_idx);
+  sampler_pick_kernel<<<B, 256, 0, st>>>(state, cand_val, cand_idx, nblk, var, d, n, 0);
+  h.count = m;
+  // set count = m without touching `next`: small kernel-free trick -> copy only the first int
+  for (int b = 0; b < B; ++b) cudaMemcpyAsync(&state[b].count, &h.count, sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
+  for (int i = m; i < n; ++i) {
+    sampler_commit_kernel<<<B, 64, 0, st>>>(state, dom_xy, dom_E, d, sel_xy, sel_E, (long long*)sel_idx, L, n, signal_var,
+                                            fixed_var, has_fixed, max_stdev_thresh, terminate_early);
+    sampler_domain_kernel<<<dim3(nblk, B), SB_THREADS, 0, st>>>(state, dom_xy, dom_E, d, sel_xy, sel_E, L, n, obs_info, var,
+                                                                dist_ok, signal_var, dist_thresh * dist_thresh, cand_val,
+                                                                cand_idx);
+    sampler_pick_kernel<<<B, 256, 0, st>>>(state, cand_val, cand_idx, nblk, var, d, n, 1);
+  }
+  for (int b = 0; b < B; ++b)
+    cudaMemcpyAsync(count_out + b, &state[b].count, sizeof(int), cudaMemcpyDeviceToDevice, st);
+  return check_launch("sampler_greedy");
+}
+
+extern "C" int como_b200_kmat_kmm(const double* cov_img, int32_t B, int32_t H, int32_t W, const double* coords_m,
+                                  int32_t M, double scale, double jitter, double* E_m, double* K_mm, void* stream) {
+  COMO_REQUIRE(cov_img && coords_m && E_m && K_mm, "kmat_kmm: null pointer argument");
+  COMO_REQUIRE(M >= 1 && M <= 1024, "kmat_kmm: bad M");
+  kmm_kernel<<<B, 256, (size_t)M * 6 * sizeof(double), (cudaStream_t)stream>>>(cov_img, H, W, coords_m, M, scale, jitter, E_m,
+                                                                               K_mm);
+  return check_launch("kmat_kmm");
+}
+
+extern "C" int como_b200_kmat_predictor(const double* cov_img, int32_t B, int32_t H, int32_t W, const double* coords_m,
+                                        const double* E_m, const double* Kmm_inv, int32_t M, double scale,
+                                        double* Knm_Kmminv, void* stream) {
+  COMO_REQUIRE(cov_img && coords_m && E_m && Kmm_inv && Knm_Kmminv, "kmat_predictor: null pointer argument");
+  COMO_REQUIRE(M >= 4 && M <= BA_MAXM && M % 4 == 0, "kmat_predictor: M must be a multiple of 4, <= 64");
+  const size_t smem = (size_t)(BA_MAXM * BA_MAXM + 6 * BA_MAXM + KP_PIX * (BA_MAXM + 1)) * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(kmat_predictor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr = true;
+  }
+  const long long HW = (long long)H * W;
+  int per = (sm_count() * 3 + B - 1) / B;
+  const long long need = (HW + KP_PIX - 1) / KP_PIX;
+  if (per > need) per = (int)need;
+  kmat_predictor_kernel<<<dim3(per, B), 256, smem, (cudaStream_t)stream>>>(cov_img, H, W, coords_m, E_m, Kmm_inv, M, scale,
+                                                                          Knm_Kmminv);
+  return check_launch("kmat_predictor");
+}

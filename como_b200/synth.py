@@ -48,6 +48,19 @@ def se3_exp_wv(xi):
     return T
 
 
+def make_cov_image(H, W, seed=0, dtype=torch.float32, device="cpu"):
+    """Smooth SPD 2x2 covariance-parameter image (1,4,H,W) [E00,E01,E10,E11], like the DepthCov UNet head's output
+    after gaussian_kernel.kernel_params_to_covariance (x, z > 0, |rho| < 0.99)."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand(1, 3, max(H // 12, 2), max(W // 12, 2), generator=g)
+    f = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False).clamp(0.02, 0.98)
+    x = 2e-3 * torch.exp(3.0 * f[:, 0])
+    z = 2e-3 * torch.exp(3.0 * f[:, 1])
+    rho = 0.9 * (2 * f[:, 2] - 1)
+    off = torch.sqrt(x * z - 1e-8) * rho
+    return torch.stack((x, off, off, z), dim=1).to(dtype=dtype, device=device)
+
+
 TRACK_PERTURB = (0.01, -0.008, 0.005, 0.02, -0.01, 0.015)  # [omega, v], SURVEY 8d
 
 

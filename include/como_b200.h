@@ -150,6 +150,41 @@ int como_b200_ba_priors(const double* scaffold, const double* dz_dP, const doubl
 int como_b200_ba_update(const double* delta, int32_t K, int32_t R, int32_t L, double* kf_poses, double* kf_aff,
                         double* rec_poses, double* rec_aff, double* P_m, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * DepthCov Gaussian process.
+ * ------------------------------------------------------------------------------------------ */
+
+/* como_backends.cross_covariance (como/backend/src/cov.cpp:5-32, cov_cpu.cpp:17-64, cov_gpu.cu:17-84).
+ * x1 (B,n1,2), E1 (B,n1,2,2), x2 (B,n2,2), E2 (B,n2,2,2) contiguous, elem_bytes 4 or 8 -> out (B,n1,n2). */
+int como_b200_cross_covariance(const void* x1, const void* E1, const void* x2, const void* E2, double scale, int32_t B,
+                               int32_t n1, int32_t n2, int32_t elem_bytes, void* out, void* stream);
+
+/* como_backends.get_new_chol_obs_info (cov.cpp:34-65, cov_cpu.cpp:66-85, cov_gpu.cu:132-215), float32:
+ * in place: L (B,n,n) gets row N, obs_info (B,n,d) gets row N, var (B,d) -= row^2. k_ni (B,N,1), k_id (B,1,d). */
+int como_b200_chol_append(float* L, float* obs_info, float* var, const float* k_ni, const float* k_id, float k_ii,
+                          int32_t B, int32_t n, int32_t d, int32_t N, void* stream);
+
+/* Device-resident greedy conditional-entropy loop (como/depth_cov/core/samplers.py:211-302): selects anchors
+ * m..n-1.  dom_xy (B,d,2) normalised coords, dom_E (B,d,4); sel_* / L / obs_info / var / dist_ok pre-filled
+ * for the first m anchors (precalc_entropy_vars, samplers.py:115-208).  sel_idx (B,n) int64 (bit-exact
+ * domain indices), count_out (B) int32 = number of anchors after the loop (early termination). */
+size_t como_b200_sampler_workspace_bytes(int32_t B, int32_t d);
+int como_b200_sampler_greedy(const float* dom_xy, const float* dom_E, int32_t B, int32_t d, int32_t n, int32_t m,
+                             float* sel_xy, float* sel_E, int64_t* sel_idx, float* L, float* obs_info, float* var,
+                             uint8_t* dist_ok, float signal_var, float fixed_var, int32_t has_fixed, float dist_thresh,
+                             float max_stdev_thresh, int32_t terminate_early, int32_t* count_out, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
+/* Mapping.prep_predictor (como/odom/Mapping.py:430-468) with the Python covariance formula
+ * (como/depth_cov/core/covariance.py:10-39, kernels.py:22-89), fp64.
+ * kmat_kmm: E_m (B,M,4) by bilinear lookup of cov_img (B,4,H,W) at coords_m (B,M,2) [row,col]; K_mm (B,M,M) + jitter I.
+ * kmat_predictor: Knm_Kmminv (B,H*W,M) = K_nm(all pixels, anchors) * Kmm_inv, K_nm never materialised. */
+int como_b200_kmat_kmm(const double* cov_img, int32_t B, int32_t H, int32_t W, const double* coords_m, int32_t M,
+                       double scale, double jitter, double* E_m, double* K_mm, void* stream);
+int como_b200_kmat_predictor(const double* cov_img, int32_t B, int32_t H, int32_t W, const double* coords_m,
+                             const double* E_m, const double* Kmm_inv, int32_t M, double scale, double* Knm_Kmminv,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

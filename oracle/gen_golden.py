@@ -221,6 +221,7 @@ def gen_ba(name, H, W, NKF, NOW, M, cfg_num_kf, iters=3):
     out["sigma_scale_prior"] = cfg["sigmas"]["scale_prior"]
     out["sigma_pose_prior"] = cfg["sigmas"]["pose_prior"]
     snapshot_mapping(m, "in_", out)
+    out["gp_scale"] = float(m.model.get_scale(-1))
     cap = {}
     orig_solve = LS.solve_system
 
@@ -297,6 +298,83 @@ def gen_ba(name, H, W, NKF, NOW, M, cfg_num_kf, iters=3):
           "size %.1f MB" % (sz / 1e6))
 
 
+def synth_cov_image(H, W, seed):
+    """Smooth SPD 2x2 covariance-parameter image (1,4,H,W) float32, the shape gaussian_kernel.py produces."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand(1, 3, max(H // 12, 2), max(W // 12, 2), generator=g)
+    f = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False).clamp(0.02, 0.98)
+    x = 2e-3 * torch.exp(3.0 * f[:, 0])
+    z = 2e-3 * torch.exp(3.0 * f[:, 1])
+    rho = 0.9 * (2 * f[:, 2] - 1)
+    off = torch.sqrt(x * z - 1e-8) * rho
+    return torch.stack((x, off, off, z), dim=1).float()
+
+
+def gen_cov(name):
+    """como_backends.cross_covariance / get_new_chol_obs_info (reference CPU build) and the reference
+    sampler's anchor indices on synthetic covariance images."""
+    ref_harness.load_reference()
+    import como_backends
+    from como.depth_cov.core.samplers import sample_sparse_coords
+
+    out = {}
+    g = torch.Generator().manual_seed(7)
+    B, n1, n2 = 2, 37, 53
+    x1 = torch.rand(B, n1, 2, generator=g) * 2 - 1
+    x2 = torch.rand(B, n2, 2, generator=g) * 2 - 1
+
+    def randE(n):
+        a = 1e-3 + 5e-2 * torch.rand(B, n, generator=g)
+        c = 1e-3 + 5e-2 * torch.rand(B, n, generator=g)
+        r = 0.9 * (2 * torch.rand(B, n, generator=g) - 1)
+        o = torch.sqrt(a * c) * r
+        return torch.stack((a, o, o, c), -1).reshape(B, n, 2, 2)
+
+    E1, E2 = randE(n1), randE(n2)
+    out.update(cc_x1=_np(x1), cc_E1=_np(E1), cc_x2=_np(x2), cc_E2=_np(E2), cc_scale=0.83)
+    out["cc_K"] = _np(como_backends.cross_covariance(x1, E1, x2, E2, 0.83))
+    # chol append sequence
+    n, d = 6, 200
+    xd = torch.rand(1, d, 2, generator=g) * 2 - 1
+    a = 1e-2 + 3e-2 * torch.rand(1, d, generator=g)
+    Ed = torch.stack((a, 0 * a, 0 * a, a), -1).reshape(1, d, 2, 2)
+    L = torch.eye(n).unsqueeze(0).clone()
+    obs = torch.zeros(1, n, d)
+    sel = [3, 50, 120, 7, 160, 90]
+    sv = 1.0
+    K00 = como_backends.cross_covariance(xd[:, sel[:1]], Ed[:, sel[:1]], xd[:, sel[:1]].clone(), Ed[:, sel[:1]].clone(), sv)
+    L[:, :1, :1] = torch.linalg.cholesky(K00)
+    Kmd = como_backends.cross_covariance(xd[:, sel[:1]], Ed[:, sel[:1]], xd, Ed, sv)
+    obs[:, :1] = Kmd / L[:, :1, :1]
+    var = sv - torch.sum(obs[:, :1] * obs[:, :1], dim=1)
+    out.update(ca_xd=_np(xd), ca_Ed=_np(Ed), ca_sel=np.array(sel), ca_L0=_np(L), ca_obs0=_np(obs), ca_var0=_np(var))
+    for i in range(1, n):
+        k_ni = como_backends.cross_covariance(xd[:, sel[:i]], Ed[:, sel[:i]], xd[:, sel[i:i + 1]], Ed[:, sel[i:i + 1]], sv)
+        k_id = como_backends.cross_covariance(xd[:, sel[i:i + 1]], Ed[:, sel[i:i + 1]], xd, Ed, sv)
+        como_backends.get_new_chol_obs_info(L, obs, var, k_ni, k_id, torch.tensor(sv).clone(), i)
+    out.update(ca_L=_np(L), ca_obs=_np(obs), ca_var=_np(var))
+    # sampler indices
+    for tag, (H, W, seed, ns) in {"a": (48, 64, 1, 64), "b": (96, 128, 2, 64), "c": (60, 80, 3, 24)}.items():
+        cov = synth_cov_image(H, W, seed)
+        with torch.no_grad():
+            coords, inds = sample_sparse_coords(cov, ns, mode="greedy_conditional_entropy", max_stdev_thresh=1e-2,
+                                                border=3, dist_thresh=0.1, signal_var=torch.tensor(1.0), fixed_var=0.0)
+        out[f"s{tag}_cov"] = _np(cov)
+        out[f"s{tag}_coords"] = _np(coords)
+        out[f"s{tag}_inds"] = _np(inds)
+        out[f"s{tag}_n"] = ns
+        # continuation from existing coordinates (corr.py:202-213 call shape)
+        keep = coords[:, : ns // 2].float()
+        with torch.no_grad():
+            c2, i2 = sample_sparse_coords(cov, ns, mode="greedy_conditional_entropy", max_stdev_thresh=1e-2, border=3,
+                                          dist_thresh=0.1, signal_var=torch.tensor(1.0), fixed_var=0.0, curr_coords=keep)
+        out[f"s{tag}_coords2"] = _np(c2)
+        out[f"s{tag}_inds2"] = _np(i2)
+        print("sampler", tag, tuple(coords.shape), tuple(c2.shape))
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "size %.2f MB" % (os.path.getsize(os.path.join(GOLD, name + ".npz")) / 1e6))
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(GOLD, exist_ok=True)
@@ -304,6 +382,8 @@ def main():
         gen_track("track_80x60_l3", 60, 80, 3, 50, 4)
         gen_track("track_80x60_l3_it1", 60, 80, 3, 1, 4)  # BASELINE config 1 shape (max_iter 1), shrunk
         gen_track("track_160x120_l4", 120, 160, 4, 50, 8)
+    if what in ("cov", "all"):
+        gen_cov("depthcov")
     if what in ("ba", "all"):
         gen_ba("ba_k4_notfull", 48, 64, 4, 3, 16, 5)
         gen_ba("ba_k4_full", 48, 64, 5, 3, 16, 4)

@@ -52,8 +52,8 @@ def test_iterate_vs_reference_golden(golden_dir, name):
         assert rel(s.kf_aff_params, g[f"it{it}_kf_aff_params"]) < 1e-6
         assert rel(s.recent_poses, g[f"it{it}_recent_poses"]) < 1e-7
         assert rel(s.P_m, g[f"it{it}_P_m"]) < 1e-7
-        assert rel(s.median_depths, g[f"it{it}_median_depths"]) < 1e-12
-        assert rel(s.depth_imgs, g[f"it{it}_depth_imgs"]) < 1e-12
+        assert rel(s.median_depths, g[f"it{it}_median_depths"]) < 1e-10
+        assert rel(s.depth_imgs, g[f"it{it}_depth_imgs"]) < 1e-10
 
 
 def test_segmented_median_matches_torch():
