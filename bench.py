@@ -226,6 +226,142 @@ def cpu_track_baseline(cases, budget_s=15.0):
             "sample": f"{n} of the same 640x480 4-level tracking problems ({its} GN iterations, {dt:.1f} s)"}
 
 
+# --------------------------------------------------------------------------------------------- BA workload
+BA_K, BA_R = 32, 24
+
+
+def ba_alg_bytes(K, N, P, HW, M):
+    """Algorithmic bytes of one BA iteration: predictor apply K*HW*M*8, pair kernels
+    K*N*M*8 (one predictor row per reference pixel) + P*N*48."""
+    return dict(predictor_apply=K * HW * M * 8, photo=K * N * M * 8 + P * N * 48)
+
+
+def run_ba_ours(args, rank, world, device):
+    from como_b200 import synth
+    from como_b200.odom import mapping_core as MC
+
+    K, R, H, W, M = args.kf, args.oneway, 480, 640, 64
+    s = synth.make_ba_window(K, R, H, W, M=M, device=device, seed=rank)
+    cfg = synth.ba_cfg()
+    allreduce = None
+    shard = world > 1 and args.shard
+    if shard:
+        def allreduce(Hm, g, err):
+            torch.distributed.all_reduce(Hm)
+            torch.distributed.all_reduce(g)
+            torch.distributed.all_reduce(err)
+
+    def step():
+        MC.iterate(s, cfg, allreduce=allreduce, rank=rank if shard else 0, world=world if shard else 1)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    barrier(world)
+    clk = ClockSampler(0 if "CUDA_VISIBLE_DEVICES" in os.environ else torch.cuda.current_device())
+    if rank == 0:
+        clk.start()
+        time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    barrier(world)
+    ms = allreduce_max(ev0.elapsed_time(ev1), world, device)
+    clocks = clk.stop(t0, t1) if rank == 0 else None
+    kp, pp = MC.get_plans(s, cfg, device, rank if shard else 0, world if shard else 1)
+
+    # per-kernel device time of the dominant kernel (predictor apply), timed alone with CUDA events
+    from como_b200 import _lib
+    scaf = s.__dict__["_b200_cache"]["scaf"]
+    depth = torch.empty(K, H * W, dtype=torch.float64, device=device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        _lib.predictor_apply(_lib.ptr(s.Knm_Kmminv), _lib.ptr(scaf), K, H * W, M, _lib.ptr(depth), _lib.stream_ptr(device))
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        _lib.predictor_apply(_lib.ptr(s.Knm_Kmminv), _lib.ptr(scaf), K, H * W, M, _lib.ptr(depth), _lib.stream_ptr(device))
+    e1.record()
+    torch.cuda.synchronize()
+    pa_ms = e0.elapsed_time(e1) / 5
+    ab = ba_alg_bytes(K, kp.N, pp.P, H * W, M)
+    peak, peak_src = measured_peaks()
+    ach = ab["predictor_apply"] / (pa_ms * 1e-3) / 1e9
+
+    # e2e: a new one-way frame arrives on the host every step (pinned RGB) -> device -> gray + gradients ->
+    # replaces the oldest one-way frame -> iterate -> poses + error back to the host
+    rgb_host = synth.make_rgb(H, W, seed=77, dtype=torch.float64).pin_memory()
+    res_host = torch.empty((K + R) * 16 + 1, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        rgb = rgb_host.to(device, non_blocking=True)
+        gray = synth._gray(rgb)
+        gx, gy = synth._scharr(gray)
+        s.recent_img_and_grads[0].copy_(torch.cat((gray, gx, gy), dim=1)[0])
+        step()
+        res_host[: K * 16].copy_(s.kf_poses.reshape(-1), non_blocking=True)
+        res_host[K * 16:(K + R) * 16].copy_(s.recent_poses.reshape(-1), non_blocking=True)
+        res_host[-1:].copy_(s.total_err_prev.reshape(1), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    barrier(world)
+    ev0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    e_ms = allreduce_max(ev0.elapsed_time(ev1), world, device)
+    nwin = 1 if shard else world   # sharded: one window over all GPUs (strong); else one window per GPU (weak)
+    res = {
+        "metric": "GN-iterations/sec at 640x480, 32-keyframe window", "value": nwin * args.steps / (ms * 1e-3),
+        "unit": "GN-it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "strong" if shard else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "ba_window", "resolution": "640x480", "keyframes": K, "one_way_frames": R,
+                   "anchors_per_kf": M, "landmarks": kp.L, "pairs": pp.P, "pixels_per_kf": kp.N,
+                   "system_dim": 8 * (K + R) + 3 * kp.L,
+                   "l2": "inputs (5.0 GB predictor slabs) exceed the 126 MB L2; no flush",
+                   "parallelism": (f"pair blocks sharded by reference keyframe over {world} GPUs + NCCL allreduce of H,g"
+                                   if shard else f"replicas x{world} (one independent window per GPU)")},
+        "e2e": {"value": nwin * args.steps / (e_ms * 1e-3), "unit": "GN-it/s",
+                "h2d_bytes_per_step": int(rgb_host.numel() * 8), "d2h_bytes_per_step": int(res_host.numel() * 8)},
+        "gpu_launches": args.steps * 22,
+        "roofline": {"kernel": "predictor_apply_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "alg_bytes_per_launch": ab["predictor_apply"], "launch_ms": pa_ms},
+        "clocks": clocks,
+    }
+    return res, s, cfg
+
+
+def cpu_ba_baseline(s, cfg, max_iters=1):
+    """Oracle port of Mapping.iterate on the host cores (torch CPU, fp64), on the same window."""
+    from oracle import ba_oracle as BO
+
+    sc = {}
+    for k, v in s.__dict__.items():
+        if k.startswith("_"):
+            continue
+        sc[k] = v.detach().cpu() if isinstance(v, torch.Tensor) else v
+    t0 = time.time()
+    n = 0
+    for _ in range(max_iters):
+        BO.iterate(sc, cfg)
+        n += 1
+    dt = time.time() - t0
+    return {"value": n / dt, "unit": "GN-it/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} iteration(s) of the same window ({dt:.1f} s)"}
+
+
 # --------------------------------------------------------------------------------------------- dist helpers
 def barrier(world):
     if world > 1:
@@ -254,8 +390,11 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="track640")
+    ap.add_argument("--workload", default="ba_window", choices=["ba_window", "track640"])
     ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--kf", type=int, default=BA_K)
+    ap.add_argument("--oneway", type=int, default=BA_R)
+    ap.add_argument("--shard", type=int, default=0, help="1: shard the pair blocks of ONE window over the GPUs")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -294,10 +433,16 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=device)
-    res, cases = run_track_ours(args, rank, world, device)
-    if rank == 0:
-        res["cpu_baseline"] = cpu_track_baseline(cases) if world == 1 else None
-        print(json.dumps(res))
+    if args.workload == "track640":
+        res, cases = run_track_ours(args, rank, world, device)
+        if rank == 0:
+            res["cpu_baseline"] = cpu_track_baseline(cases) if world == 1 else None
+            print(json.dumps(res))
+    else:
+        res, s, cfg = run_ba_ours(args, rank, world, device)
+        if rank == 0:
+            res["cpu_baseline"] = cpu_ba_baseline(s, cfg) if world == 1 else None
+            print(json.dumps(res))
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -149,3 +149,134 @@ def make_tracking_case(H, W, num_levels, seed=0, cell=16, device="cpu", noise2=0
     out["T_init"] = se3_exp_wv(TRACK_PERTURB).float()[None].to(device)
     out["aff_init"] = torch.zeros(1, 2, 1, device=device)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Synthetic BA window: fronto-parallel textured plane at Z = 2, camera translating +x by
+# `step` px per keyframe; anchors from the device sampler, ~`ndrop` anchors replaced per keyframe so the
+# landmark count grows like the real system (L ~ M + ndrop (K-1)); predictors from the fused K-matrix
+# kernel.  Needs CUDA.  Returns a mapping_core.WindowState with the reference Mapping attribute names.
+# ---------------------------------------------------------------------------------------------
+def make_ba_window(K, R, H, W, M=64, device="cuda", seed=0, step=6.0, ndrop=20, pose_noise=2e-3, window_full=False):
+    from como_b200.depth_cov.core.predictor import prep_predictor
+    from como_b200.depth_cov.core.samplers import sample_sparse_coords
+    from como_b200.odom.mapping_core import WindowState
+
+    dev = torch.device(device)
+    f64 = torch.float64
+    g = torch.Generator().manual_seed(seed)
+    Z = 2.0
+    fx = 525.0 * W / 640.0
+    Kmat = torch.tensor([[fx, 0, W / 2.0], [0, fx, H / 2.0], [0, 0, 1.0]], dtype=f64)
+    tex = make_rgb(H, W, seed=seed, cell=16, extra_w=int(step * (K + 2)) + 8, dtype=f64, device=dev)
+
+    def frame(k):
+        x0 = int(k * step)
+        rgb = tex[..., x0:x0 + W]
+        gray = _gray(rgb)
+        gx, gy = _scharr(gray)
+        T = torch.eye(4, dtype=f64)
+        T[0, 3] = k * step * Z / fx
+        return torch.cat((gray, gx, gy), dim=1), T
+
+    def noisy(T):
+        T = T.clone()
+        T[:3, 3] += pose_noise * (torch.rand(3, generator=g, dtype=f64) - 0.5)
+        return T
+
+    imgs, poses, covs, coords_all, Ls, Kinvs, slabs = [], [], [], [], [], [], []
+    lm_of_slot = []  # per keyframe: landmark id of each slot
+    first_dim = []
+    nlm = 0
+    P_list = []
+    border = 3
+    for k in range(K):
+        img, T = frame(k)
+        cov = make_cov_image(H, W, seed=1000 + seed * 100 + k, dtype=f64, device=dev)
+        if k == 0:
+            c, _ = sample_sparse_coords(cov, M, "greedy_conditional_entropy", max_stdev_thresh=1e-2, border=border,
+                                        dist_thresh=0.1, signal_var=torch.tensor(1.0), fixed_var=0.0)
+            coords = c[0].to(f64)
+            lms = list(range(M))
+            nlm = M
+            new_dim = M
+        else:
+            prev = coords_all[-1].clone()
+            prev[:, 1] -= step  # points move -x when the camera moves +x (plane at constant depth)
+            inside = (prev[:, 1] >= border + 1) & (prev[:, 1] <= W - border - 2)
+            order = torch.randperm(M, generator=g)[:ndrop].tolist()
+            keep = [m for m in range(M) if bool(inside[m]) and m not in order]
+            tracked = prev[keep]
+            c, _ = sample_sparse_coords(cov, M, "greedy_conditional_entropy", max_stdev_thresh=1e-2, border=border,
+                                        dist_thresh=0.1, signal_var=torch.tensor(1.0), fixed_var=0.0,
+                                        curr_coords=tracked[None].float())
+            new = c[0].to(f64)
+            coords = torch.cat((tracked, new), 0)[:M]
+            new_dim = coords.shape[0] - len(keep)
+            lms = [lm_of_slot[-1][m] for m in keep] + list(range(nlm, nlm + new_dim))
+            nlm += new_dim
+        assert coords.shape[0] == M, "sampler returned too few anchors for the synthetic window"
+        Kinv, Lm, slab = prep_predictor(cov, coords[None], 1.0)
+        zs = Z * (1.0 + 0.01 * (torch.rand(M, generator=g, dtype=f64) - 0.5)).to(dev)
+        # world points of the NEW landmarks of this keyframe (GT pose, perturbed depth)
+        pix = torch.stack((coords[:, 1], coords[:, 0]), -1)  # (x, y)
+        Pc = torch.stack(((pix[:, 0] - Kmat[0, 2]) / fx * zs, (pix[:, 1] - Kmat[1, 2]) / fx * zs, zs), -1)
+        Pw = Pc + T[:3, 3].to(dev)
+        P_list.append(Pw[M - new_dim:])
+        imgs.append(img)
+        poses.append(noisy(T) if k > 0 else T)
+        covs.append(cov)
+        coords_all.append(coords)
+        lm_of_slot.append(lms)
+        first_dim.append(new_dim)
+        Ls.append(Lm)
+        Kinvs.append(Kinv)
+        slabs.append(slab)
+    L = nlm
+    corr = torch.zeros(K, L, dtype=torch.bool)
+    for k in range(K):
+        corr[k, lm_of_slot[k]] = True
+    obs_ref = torch.zeros(K, M, dtype=torch.bool)
+    for k in range(K):
+        obs_ref[k, M - first_dim[k]:] = True
+    rec_imgs, rec_poses, rec_ts = [], [], []
+    for j in range(R):
+        kk = (j % (K - 1)) + 0.5
+        img, T = frame(kk)
+        rec_imgs.append(img)
+        rec_poses.append(noisy(T))
+        rec_ts.append(1.0 + kk + 0.001 * j)
+    order = sorted(range(R), key=lambda i: rec_ts[i])
+    pm = torch.stack([torch.stack((c[:, 1], c[:, 0]), -1) for c in coords_all]).to(dev)
+    s = WindowState(
+        intrinsics=Kmat[None].to(dev),
+        kf_timestamps=[1.0 + k for k in range(K)],
+        recent_timestamps=[rec_ts[i] for i in order],
+        kf_poses=torch.stack(poses).to(dev).contiguous(),
+        kf_aff_params=(0.01 * (torch.rand(K, 2, 1, generator=g, dtype=f64) - 0.5)).to(dev).contiguous(),
+        recent_poses=(torch.stack([rec_poses[i] for i in order]).to(dev).contiguous() if R else torch.empty(0, dtype=f64, device=dev)),
+        recent_aff_params=torch.zeros(R, 2, 1, dtype=f64, device=dev),
+        kf_img_and_grads=torch.cat(imgs, 0).contiguous(),
+        recent_img_and_grads=(torch.cat([rec_imgs[i] for i in order], 0).contiguous() if R else torch.empty(0, dtype=f64, device=dev)),
+        cov_params_img=torch.cat(covs, 0),
+        pm_first_obs=pm.contiguous(), pm=pm.clone(),
+        logzm=torch.full((K, M, 1), math.log(Z), dtype=f64, device=dev),
+        L_mm=torch.cat(Ls, 0).contiguous(), Kmm_inv=torch.cat(Kinvs, 0).contiguous(),
+        Knm_Kmminv=torch.cat(slabs, 0).contiguous(),
+        correspondence_mask=corr.to(dev), P_m=torch.cat(P_list, 0).contiguous(), obs_ref_mask=obs_ref.to(dev),
+        pose_anchor=torch.stack(poses[:1]).to(dev), aff_anchor=torch.zeros(1, 2, 1, dtype=f64, device=dev),
+        median_depths=torch.full((K,), Z, dtype=f64, device=dev), depth_imgs=None,
+        window_full=bool(window_full), init_scale_anchor=torch.tensor(math.log(Z), dtype=f64, device=dev).view(1, 1, 1),
+        iter=0, converged=False,
+    )
+    s.kf_aff_params[0] = 0.0
+    if window_full:
+        s.P_m_anchors = s.P_m[s.correspondence_mask[0]].clone()
+    return s
+
+
+def ba_cfg(batch=128):
+    """The reference's mapping config values used by iterate (config/como.yml:26-51)."""
+    return dict(photo_construction=dict(nonmax_suppression_window=4, pairwise_batch_size=batch, radius_thresh=0.0,
+                                        degrees_thresh=0.0),
+                sigmas=dict(photo=1e-1, mean_depth_prior=1e-2, scale_prior=1e-4, pose_prior=1e-6))

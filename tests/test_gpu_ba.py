@@ -94,3 +94,53 @@ def test_predictor_apply_and_colsum_vs_torch():
     cs = torch.empty(M, dtype=torch.float64, device="cuda")
     _lib.check(_lib.predictor_colsum(_lib.ptr(Knm[0]), HW, M, _lib.ptr(cs), _lib.stream_ptr()), "cs")
     assert rel(cs, Knm[0].sum(0)) < 1e-11
+
+
+def state_to_cpu_dict(s):
+    d = {}
+    for k, v in s.__dict__.items():
+        if k.startswith("_"):
+            continue
+        d[k] = v.detach().cpu().clone() if isinstance(v, torch.Tensor) else (list(v) if isinstance(v, list) else v)
+    return d
+
+
+@pytest.mark.parametrize("full", [False, True])
+def test_synthetic_window_vs_oracle(full):
+    """A second configuration (more keyframes / one-way frames, M=32, several targets per keyframe) built
+    with the device sampler + K-matrix kernels: CUDA iterate vs the oracle on identical state."""
+    from como_b200 import synth
+    from como_b200.odom import mapping_core as MC
+
+    s = synth.make_ba_window(6, 9, 96, 128, M=32, seed=3, ndrop=8, window_full=full)
+    cfg = synth.ba_cfg()
+    sc = state_to_cpu_dict(s)
+    for it in range(2):
+        o = BO.iterate(sc, cfg)
+        dbg = MC.iterate(s, cfg, return_debug=True)
+        np.testing.assert_array_equal(dbg["coords_n"].cpu().numpy().astype(np.int64), o["coords_n"].numpy())
+        assert rel(dbg["sigma"], torch.tensor(o["sigmas"])) < 1e-12
+        assert rel(dbg["H_photo"], o["H_photo"]) < 1e-9
+        assert rel(dbg["g_photo"], o["g_photo"]) < 1e-9
+        assert rel(dbg["H"], o["H"]) < 1e-9
+        assert rel(dbg["g"], o["g"]) < 1e-9
+        assert abs(float(dbg["err"][0]) - o["photo_err"]) <= 1e-10 * o["photo_err"]
+        assert rel(s.kf_poses, sc["kf_poses"]) < 1e-6
+        assert rel(s.recent_poses, sc["recent_poses"]) < 1e-6
+        assert rel(s.P_m, sc["P_m"]) < 1e-6
+        assert rel(s.median_depths, sc["median_depths"]) < 1e-9
+
+
+def test_small_batch_size_splits_median_segments():
+    """pairwise_batch_size smaller than the pair count: one robust scale per batch of pairs (photo.py:262-347)."""
+    from como_b200 import synth
+    from como_b200.odom import mapping_core as MC
+
+    s = synth.make_ba_window(4, 3, 64, 96, M=16, seed=5, ndrop=4)
+    cfg = synth.ba_cfg(batch=4)
+    sc = state_to_cpu_dict(s)
+    o = BO.iterate(sc, cfg)
+    dbg = MC.iterate(s, cfg, return_debug=True)
+    assert len(o["sigmas"]) == 3
+    assert rel(dbg["sigma"], torch.tensor(o["sigmas"])) < 1e-12
+    assert rel(dbg["H"], o["H"]) < 1e-9
