@@ -79,6 +79,12 @@ sampler_greedy = _sig("como_b200_sampler_greedy", C.c_int,
 kmat_kmm = _sig("como_b200_kmat_kmm", C.c_int, [VP, I32, I32, I32, VP, I32, F64, F64, VP, VP, VP])
 kmat_predictor = _sig("como_b200_kmat_predictor", C.c_int, [VP, I32, I32, I32, VP, VP, VP, I32, F64, VP, VP])
 
+gray_pyramid = _sig("como_b200_gray_pyramid", C.c_int, [VP, I32, I32, I32, C.POINTER(C.c_void_p), VP])
+image_gradients = _sig("como_b200_image_gradients", C.c_int, [VP, I32, I32, VP, VP, VP])
+kf_reference_level = _sig("como_b200_kf_reference_level", C.c_int,
+                          [VP, VP, VP, VP, I32, I32, I32, I32, I32, C.POINTER(F32), VP, F32, F32, VP, VP, VP, VP, VP, VP])
+reproj_depth = _sig("como_b200_reproj_depth", C.c_int, [VP, I32, VP, C.POINTER(F32), I32, I32, VP, VP, VP])
+
 # every symbol include/como_b200.h declares (checked by tests/test_abi.py without a GPU)
 DECLARED_SYMBOLS = [
     "como_b200_abi_version", "como_b200_last_error", "como_b200_track_workspace_bytes", "como_b200_track_pyr",
@@ -87,6 +93,7 @@ DECLARED_SYMBOLS = [
     "como_b200_ba_photo_workspace_bytes", "como_b200_ba_unit_ints", "como_b200_ba_target_group", "como_b200_ba_photo",
     "como_b200_ba_priors", "como_b200_ba_update", "como_b200_cross_covariance", "como_b200_chol_append",
     "como_b200_sampler_workspace_bytes", "como_b200_sampler_greedy", "como_b200_kmat_kmm", "como_b200_kmat_predictor",
+    "como_b200_gray_pyramid", "como_b200_image_gradients", "como_b200_kf_reference_level", "como_b200_reproj_depth",
 ]
 
 

@@ -185,6 +185,29 @@ int como_b200_kmat_predictor(const double* cov_img, int32_t B, int32_t H, int32_
                              const double* E_m, const double* Kmm_inv, int32_t M, double scale, double* Knm_Kmminv,
                              void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Tracker front-end (fp32).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Tracking.prep_tracking_img (como/odom/Tracking.py:88-94; utils/image_processing.py:48-87): rgb (3,H,W) ->
+ * gray pyramid.  levels: HOST array of num_levels DEVICE pointers, coarsest first (reference order). */
+int como_b200_gray_pyramid(const float* rgb, int32_t H, int32_t W, int32_t num_levels, float* const* levels,
+                           void* stream);
+/* ImageGradientModule (utils/image_processing.py:8-44): Scharr/32, reflect padding. */
+int como_b200_image_gradients(const float* img, int32_t h, int32_t w, float* gx, float* gy, void* stream);
+/* One pyramid level of Tracking.update_kf_reference (Tracking.py:243-314) for one keyframe: nearest depth
+ * (stride `sub` into the full-resolution depth), back-projection, rel (3x4, DEVICE) into the last keyframe,
+ * +-`border` px / depth mask, precalc_jacobians.  Outputs in the reference layout: vals (n), grads (n,2),
+ * P (n,3), J (n,8), mask (n) with n = h*w.  K9 HOST. */
+int como_b200_kf_reference_level(const float* img, const float* gx, const float* gy, const float* depth_full,
+                                 int32_t Hf, int32_t Wf, int32_t sub, int32_t h, int32_t w, const float* K9,
+                                 const float* rel12_dev, float border, float depth_thresh, float* vals, float* grads,
+                                 float* P, float* J, uint8_t* mask, void* stream);
+/* get_reproj_last_kf (Tracking.py:169-188): depth image (h*w, NaN where empty) of the cloud P (n,3) seen
+ * from T (3x4 or 4x4 row-major, DEVICE); duplicates resolved as "largest point index wins". winner_ws: h*w int32. */
+int como_b200_reproj_depth(const float* P, int32_t n, const float* T_dev, const float* K9, int32_t h, int32_t w,
+                           int32_t* winner_ws, float* depth_img, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
