@@ -60,11 +60,17 @@ ba_scaffold = _sig("como_b200_ba_scaffold", C.c_int,
                    [VP, VP, VP, VP, VP, VP, I32, I32, I32, C.POINTER(F64), VP, VP, VP])
 predictor_apply = _sig("como_b200_predictor_apply", C.c_int, [VP, VP, I32, I64, I32, VP, VP])
 predictor_colsum = _sig("como_b200_predictor_colsum", C.c_int, [VP, I64, I32, VP, VP])
-ba_photo_workspace_bytes = _sig("como_b200_ba_photo_workspace_bytes", C.c_size_t, [I32] * 6)
+ba_frames_bytes = _sig("como_b200_ba_frames_bytes", C.c_size_t, [I32])
+ba_partial_doubles = _sig("como_b200_ba_partial_doubles", C.c_size_t, [I32])
 ba_unit_ints = _sig("como_b200_ba_unit_ints", I32, [])
 ba_target_group = _sig("como_b200_ba_target_group", I32, [])
-ba_photo = _sig("como_b200_ba_photo", C.c_int,
-                [VP] * 20 + [I32] * 10 + [C.POINTER(F64), I32, VP, VP, VP, VP, VP, C.c_size_t, VP])
+ba_photo_residual = _sig("como_b200_ba_photo_residual", C.c_int,
+                         [VP] * 13 + [I32] * 7 + [C.POINTER(F64), VP, VP, VP, VP, VP])
+ba_photo_accum = _sig("como_b200_ba_photo_accum", C.c_int,
+                      [VP] * 14 + [I32] * 9 + [C.POINTER(F64), I32] + [VP] * 11)
+median_num_passes = _sig("como_b200_median_num_passes", I32, [I32])
+median_pass_f64 = _sig("como_b200_median_pass_f64", C.c_int, [VP, VP, I32, I64, I32, VP, VP])
+median_finish_f64 = _sig("como_b200_median_finish_f64", C.c_int, [I32, VP, F64, VP, VP, VP])
 ba_priors = _sig("como_b200_ba_priors", C.c_int,
                  [VP] * 15 + [I32, I32, C.POINTER(F64), F64, I32, I32, I32, I32, C.POINTER(F64), I32, VP, VP, VP, VP])
 ba_update = _sig("como_b200_ba_update", C.c_int, [VP, I32, I32, I32, VP, VP, VP, VP, VP, VP])
@@ -90,7 +96,9 @@ DECLARED_SYMBOLS = [
     "como_b200_abi_version", "como_b200_last_error", "como_b200_track_workspace_bytes", "como_b200_track_pyr",
     "como_b200_precalc_jacobians", "como_b200_median_workspace_bytes", "como_b200_median_f64", "como_b200_median_f32",
     "como_b200_subselect_pixels", "como_b200_ba_scaffold", "como_b200_predictor_apply", "como_b200_predictor_colsum",
-    "como_b200_ba_photo_workspace_bytes", "como_b200_ba_unit_ints", "como_b200_ba_target_group", "como_b200_ba_photo",
+    "como_b200_ba_frames_bytes", "como_b200_ba_partial_doubles", "como_b200_ba_unit_ints", "como_b200_ba_target_group",
+    "como_b200_ba_photo_residual", "como_b200_ba_photo_accum", "como_b200_median_num_passes",
+    "como_b200_median_pass_f64", "como_b200_median_finish_f64",
     "como_b200_ba_priors", "como_b200_ba_update", "como_b200_cross_covariance", "como_b200_chol_append",
     "como_b200_sampler_workspace_bytes", "como_b200_sampler_greedy", "como_b200_kmat_kmm", "como_b200_kmat_predictor",
     "como_b200_gray_pyramid", "como_b200_image_gradients", "como_b200_kf_reference_level", "como_b200_reproj_depth",

@@ -458,6 +458,7 @@ ba_scatter_ref_kernel(const double* __restrict__ partial, const int32_t* __restr
   __shared__ int s_lm[BA_MAXM];
   const int i = blockIdx.x, tid = threadIdx.x;
   const int ub = unit_base[i], ns = unit_slices[i];
+  if (ns == 0) return;  // this keyframe is the reference of no pair on this rank
   for (int t = tid; t < BA_MAXM * BA_MAXM + 9 * BA_MAXM; t += 256) {
     double s = 0.0;
     for (int sl = 0; sl < ns; ++sl) s += partial[(size_t)(ub + sl) * PART_STRIDE + t];
@@ -555,129 +556,92 @@ ba_scatter_pair_kernel(const double* __restrict__ partial, const int32_t* __rest
   }
 }
 
-__global__ void seg_off_kernel(long long* __restrict__ seg_off, int nbatch, int batch, int P, int N) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b <= nbatch) seg_off[b] = (long long)min(b * batch, P) * N;
-}
-
 // sigma per pair from sigma per batch
-__global__ void sigma_expand_kernel(const double* __restrict__ sigma_batch, int P, int batch, double* __restrict__ sigma_pair) {
+__global__ void sigma_expand_kernel(const double* __restrict__ sigma_batch, const int32_t* __restrict__ pair_batch, int P,
+                                    double* __restrict__ sigma_pair) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P) sigma_pair[p] = sigma_batch[p / batch];
+  if (p < P) sigma_pair[p] = sigma_batch[pair_batch[p]];
 }
 
 }  // namespace como
 
 using namespace como;
 
-// Workspace layout (bytes), all 256-aligned:
-//   frames | refbuf | rbuf | pairbuf | sigma_batch | sigma_pair | seg_off | median hist | partial
-struct BAPhotoLayout {
-  size_t frames, refbuf, rbuf, pairbuf, sigma_batch, sigma_pair, seg_off, medws, medws_bytes, partial, total;
-};
-static size_t al256(size_t v) { return (v + 255) / 256 * 256; }
-static BAPhotoLayout ba_photo_layout(int K, int R, int N, int P, int num_units, int num_batches) {
-  BAPhotoLayout L;
-  size_t o = 0;
-  L.frames = o; o += al256((size_t)(K + R) * sizeof(BAFrame));
-  L.refbuf = o; o += al256((size_t)K * N * REF_STRIDE * 8);
-  L.rbuf = o; o += al256((size_t)P * N * 8);
-  L.pairbuf = o; o += al256((size_t)P * N * PAIR_STRIDE * 8);
-  L.sigma_batch = o; o += al256((size_t)num_batches * 8);
-  L.sigma_pair = o; o += al256((size_t)P * 8);
-  L.seg_off = o; o += al256((size_t)(num_batches + 1) * 8);
-  L.medws_bytes = (size_t)6 * num_batches * 2048 * 4;
-  L.medws = o; o += al256(L.medws_bytes);
-  L.partial = o; o += al256((size_t)num_units * PART_STRIDE * 8);
-  L.total = o;
-  return L;
-}
-
-extern "C" size_t como_b200_ba_photo_workspace_bytes(int32_t K, int32_t R, int32_t N, int32_t P, int32_t num_units,
-                                                     int32_t batch_size) {
-  const int nb = (P + batch_size - 1) / batch_size;
-  return ba_photo_layout(K, R, N, P, num_units, nb).total;
-}
-
+extern "C" size_t como_b200_ba_frames_bytes(int32_t num_frames) { return (size_t)num_frames * sizeof(BAFrame); }
+extern "C" size_t como_b200_ba_partial_doubles(int32_t num_units) { return (size_t)num_units * PART_STRIDE; }
 extern "C" int32_t como_b200_ba_unit_ints(void) { return (int32_t)(sizeof(BAUnit) / sizeof(int32_t)); }
 extern "C" int32_t como_b200_ba_target_group(void) { return TG; }
 
-extern "C" int como_b200_ba_photo(
+static BADims make_dims(int K, int R, int L, int M, int N, int H, int W, int P, const double* intr4) {
+  BADims d{};
+  d.K = K; d.R = R; d.L = L; d.M = M; d.N = N; d.H = H; d.W = W; d.P = P;
+  d.fx = intr4[0]; d.fy = intr4[1]; d.cx = intr4[2]; d.cy = intr4[3];
+  return d;
+}
+
+// Pass A: frame table + residuals of every (pair, pixel) of this rank.
+extern "C" int como_b200_ba_photo_residual(
     const double* kf_poses, const double* kf_aff, const double* rec_poses, const double* rec_aff, const double* kf_img,
     const double* rec_img, const double* Knm, const int32_t* coords, const double* vals_n, const double* scaffold,
-    const double* dz_dP, const int32_t* lm_ids, const int32_t* pair_ref, const int32_t* pair_tgt,
-    const int32_t* pair_slot, const int32_t* ref_ptr, const int32_t* ref_pairs, const int32_t* units,
-    const int32_t* unit_base, const int32_t* unit_slices, int32_t num_units, int32_t K, int32_t R, int32_t L, int32_t M,
-    int32_t N, int32_t Himg, int32_t Wimg, int32_t P, int32_t batch_size, const double* intr4, int32_t dim, double* H,
-    double* g, double* photo_err, double* sigma_out, void* workspace, size_t workspace_bytes, void* stream_) {
+    const int32_t* pair_tgt, const int32_t* ref_ptr, const int32_t* ref_pairs, int32_t K, int32_t R, int32_t M, int32_t N,
+    int32_t Himg, int32_t Wimg, int32_t P, const double* intr4, void* frames_ws, double* refbuf, double* rbuf,
+    double* pairbuf, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  COMO_REQUIRE(kf_poses && kf_aff && kf_img && Knm && coords && vals_n && scaffold && dz_dP && lm_ids && pair_ref &&
-                   pair_tgt && pair_slot && ref_ptr && ref_pairs && units && unit_base && unit_slices && intr4 && H && g &&
-                   photo_err && workspace,
-               "ba_photo: null pointer argument");
-  COMO_REQUIRE(R == 0 || (rec_poses && rec_aff && rec_img), "ba_photo: null one-way frame pointers");
-  COMO_REQUIRE(M >= 2 && M <= BA_MAXM && (M % 4) == 0, "ba_photo: M must be a multiple of 4 and <= 64 (got %d)", M);
-  COMO_REQUIRE(K >= 1 && N >= 1 && P >= 1 && batch_size >= 1 && num_units >= 1, "ba_photo: bad sizes");
-  COMO_REQUIRE(dim == 8 * (K + R) + 3 * L, "ba_photo: dim %d != 8(K+R)+3L", dim);
-  const int nbatch = (P + batch_size - 1) / batch_size;
-  const BAPhotoLayout Lo = ba_photo_layout(K, R, N, P, num_units, nbatch);
-  if (workspace_bytes < Lo.total) {
-    set_last_error("ba_photo: workspace %zu < required %zu", workspace_bytes, Lo.total);
-    return COMO_B200_EWORKSPACE;
-  }
-  unsigned char* ws = (unsigned char*)workspace;
-  BAFrame* frames = (BAFrame*)(ws + Lo.frames);
-  double* refbuf = (double*)(ws + Lo.refbuf);
-  double* rbuf = (double*)(ws + Lo.rbuf);
-  double* pairbuf = (double*)(ws + Lo.pairbuf);
-  double* sigma_batch = (double*)(ws + Lo.sigma_batch);
-  double* sigma_pair = (double*)(ws + Lo.sigma_pair);
-  long long* seg_off = (long long*)(ws + Lo.seg_off);
-  double* partial = (double*)(ws + Lo.partial);
-
-  BADims d{};
-  d.K = K; d.R = R; d.L = L; d.M = M; d.N = N; d.H = Himg; d.W = Wimg; d.P = P;
-  d.fx = intr4[0]; d.fy = intr4[1]; d.cx = intr4[2]; d.cy = intr4[3];
-
+  COMO_REQUIRE(kf_poses && kf_aff && kf_img && Knm && coords && vals_n && scaffold && pair_tgt && ref_ptr && ref_pairs &&
+                   intr4 && frames_ws && refbuf && rbuf && pairbuf,
+               "ba_photo_residual: null pointer argument");
+  COMO_REQUIRE(R == 0 || (rec_poses && rec_aff && rec_img), "ba_photo_residual: null one-way frame pointers");
+  COMO_REQUIRE(M >= 4 && M <= BA_MAXM && (M % 4) == 0, "ba_photo: M must be a multiple of 4 and <= 64 (got %d)", M);
+  COMO_REQUIRE(K >= 1 && N >= 1 && P >= 1, "ba_photo_residual: bad sizes");
+  const BADims d = make_dims(K, R, 0, M, N, Himg, Wimg, P, intr4);
+  BAFrame* frames = (BAFrame*)frames_ws;
   int rc = ba_build_frames(kf_poses, kf_aff, rec_poses, rec_aff, kf_img, rec_img, K, R, (size_t)3 * Himg * Wimg, frames, st);
   if (rc) return rc;
-  // segment offsets of the pair batches inside rbuf
-  seg_off_kernel<<<(nbatch + 128) / 128, 128, 0, st>>>(seg_off, nbatch, batch_size, P, N);
-  {
-    dim3 grid((N + RA_THREADS - 1) / RA_THREADS, K);
-    ba_residual_kernel<<<grid, RA_THREADS, 0, st>>>(Knm, coords, vals_n, scaffold, frames, ref_ptr, ref_pairs, pair_tgt, d,
-                                                    refbuf, rbuf, pairbuf);
-    rc = check_launch("ba_residual");
-    if (rc) return rc;
+  dim3 grid((N + RA_THREADS - 1) / RA_THREADS, K);
+  ba_residual_kernel<<<grid, RA_THREADS, 0, st>>>(Knm, coords, vals_n, scaffold, frames, ref_ptr, ref_pairs, pair_tgt, d, refbuf,
+                                                  rbuf, pairbuf);
+  return check_launch("ba_photo_residual");
+}
+
+// Pass B + scatter.  sigma_batch (num_batches) = 1.4826 * median |r| per pair batch (global across ranks);
+// pair_batch (P) = batch of each local pair.
+extern "C" int como_b200_ba_photo_accum(
+    const double* Knm, const int32_t* coords, const double* scaffold, const double* dz_dP, const int32_t* lm_ids,
+    const int32_t* pair_ref, const int32_t* pair_tgt, const int32_t* pair_slot, const int32_t* pair_batch,
+    const int32_t* ref_ptr, const int32_t* ref_pairs, const int32_t* units, const int32_t* unit_base,
+    const int32_t* unit_slices, int32_t num_units, int32_t K, int32_t R, int32_t L, int32_t M, int32_t N, int32_t Himg,
+    int32_t Wimg, int32_t P, const double* intr4, int32_t dim, const double* sigma_batch, const void* frames_ws,
+    const double* refbuf, const double* rbuf, const double* pairbuf, double* sigma_pair_ws, double* partial, double* H,
+    double* g, double* photo_err, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  COMO_REQUIRE(Knm && coords && scaffold && dz_dP && lm_ids && pair_ref && pair_tgt && pair_slot && pair_batch && ref_ptr &&
+                   ref_pairs && units && unit_base && unit_slices && intr4 && sigma_batch && frames_ws && refbuf && rbuf &&
+                   pairbuf && sigma_pair_ws && partial && H && g && photo_err,
+               "ba_photo_accum: null pointer argument");
+  COMO_REQUIRE(M >= 4 && M <= BA_MAXM && (M % 4) == 0, "ba_photo: M must be a multiple of 4 and <= 64 (got %d)", M);
+  COMO_REQUIRE(dim == 8 * (K + R) + 3 * L, "ba_photo_accum: dim %d != 8(K+R)+3L", dim);
+  COMO_REQUIRE(num_units >= 1 && P >= 1, "ba_photo_accum: bad sizes");
+  const BADims d = make_dims(K, R, L, M, N, Himg, Wimg, P, intr4);
+  const BAFrame* frames = (const BAFrame*)frames_ws;
+  sigma_expand_kernel<<<(P + 127) / 128, 128, 0, st>>>(sigma_batch, pair_batch, P, sigma_pair_ws);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(ba_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccumSmem));
+    attr_set = true;
   }
-  rc = median_launch<double>(rbuf, seg_off, nbatch, (long long)batch_size * N, 1.4826, sigma_batch, nullptr,
-                             ws + Lo.medws, Lo.medws_bytes, st);
+  ba_accum_kernel<<<num_units, AC_THREADS, sizeof(AccumSmem), st>>>(Knm, coords, scaffold, frames, ref_ptr, ref_pairs, pair_tgt,
+                                                                     sigma_pair_ws, (const BAUnit*)units, d, refbuf, rbuf,
+                                                                     pairbuf, partial);
+  int rc = check_launch("ba_accum");
   if (rc) return rc;
-  sigma_expand_kernel<<<(P + 127) / 128, 128, 0, st>>>(sigma_batch, P, batch_size, sigma_pair);
-  if (sigma_out) cudaMemcpyAsync(sigma_out, sigma_batch, sizeof(double) * nbatch, cudaMemcpyDeviceToDevice, st);
-  {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(ba_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccumSmem));
-      attr_set = true;
-    }
-    ba_accum_kernel<<<num_units, AC_THREADS, sizeof(AccumSmem), st>>>(
-        Knm, coords, scaffold, frames, ref_ptr, ref_pairs, pair_tgt, sigma_pair, (const BAUnit*)units, d, refbuf, rbuf,
-        pairbuf, partial);
-    rc = check_launch("ba_accum");
-    if (rc) return rc;
+  const size_t smem = (size_t)(BA_MAXM * BA_MAXM + 9 * BA_MAXM) * sizeof(double);
+  static bool attr2 = false;
+  if (!attr2) {
+    cudaFuncSetAttribute(ba_scatter_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr2 = true;
   }
-  {
-    const size_t smem = (size_t)(BA_MAXM * BA_MAXM + 9 * BA_MAXM) * sizeof(double);
-    static bool attr2 = false;
-    if (!attr2) {
-      cudaFuncSetAttribute(ba_scatter_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr2 = true;
-    }
-    ba_scatter_ref_kernel<<<K, 256, smem, st>>>(partial, unit_base, unit_slices, scaffold, dz_dP, lm_ids, d, dim, H, g);
-    ba_scatter_pair_kernel<<<P, 256, 0, st>>>(partial, unit_base, unit_slices, pair_ref, pair_tgt, pair_slot, scaffold,
-                                              dz_dP, lm_ids, d, dim, H, g, photo_err);
-    rc = check_launch("ba_scatter");
-  }
-  return rc;
+  ba_scatter_ref_kernel<<<K, 256, smem, st>>>(partial, unit_base, unit_slices, scaffold, dz_dP, lm_ids, d, dim, H, g);
+  ba_scatter_pair_kernel<<<P, 256, 0, st>>>(partial, unit_base, unit_slices, pair_ref, pair_tgt, pair_slot, scaffold, dz_dP,
+                                            lm_ids, d, dim, H, g, photo_err);
+  return check_launch("ba_scatter");
 }

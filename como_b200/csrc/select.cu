@@ -193,6 +193,35 @@ template int median_launch<float>(const float*, const long long*, int, long long
 
 using namespace como;
 
+template <typename T>
+static int median_pass(const T* values, const long long* seg_off, int num_segs, long long max_seg_len, int digit,
+                       unsigned* hist, cudaStream_t stream) {
+  long long chunks = (max_seg_len + (long long)SEL_THREADS * 8 - 1) / ((long long)SEL_THREADS * 8);
+  const long long cap = (long long)sm_count() * 8 / (num_segs > 0 ? num_segs : 1);
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  select_pass_kernel<T><<<dim3((unsigned)chunks, (unsigned)num_segs), SEL_THREADS, 0, stream>>>(values, seg_off, num_segs, digit, hist);
+  return check_launch("median_pass");
+}
+
+// Distributed use: zero `hist` (passes x segments x 2048 uint32), then for digit = 0..passes-1 call the pass and
+// all-reduce (sum) hist[digit] across ranks before the next one; finish turns the histograms into the value.
+extern "C" int32_t como_b200_median_num_passes(int32_t elem_bytes) { return elem_bytes == 8 ? 6 : 3; }
+extern "C" int como_b200_median_pass_f64(const double* values, const int64_t* seg_offsets, int32_t num_segments,
+                                         int64_t max_segment_len, int32_t digit, void* hist, void* stream) {
+  COMO_REQUIRE(values && seg_offsets && hist, "median_pass_f64: null pointer argument");
+  COMO_REQUIRE(digit >= 0 && digit < 6 && num_segments >= 1, "median_pass_f64: bad digit/segments");
+  return median_pass<double>(values, (const long long*)seg_offsets, num_segments, max_segment_len, digit, (unsigned*)hist,
+                             (cudaStream_t)stream);
+}
+extern "C" int como_b200_median_finish_f64(int32_t num_segments, const void* hist, double scale, double* out, int64_t* count,
+                                           void* stream) {
+  COMO_REQUIRE(hist && out && num_segments >= 1, "median_finish_f64: bad arguments");
+  select_finish_kernel<double><<<num_segments, SEL_THREADS, 0, (cudaStream_t)stream>>>(num_segments, (const unsigned*)hist, scale,
+                                                                                      out, (long long*)count);
+  return check_launch("median_finish");
+}
+
 extern "C" size_t como_b200_median_workspace_bytes(int32_t num_segments, int32_t elem_bytes) {
   const int passes = (elem_bytes == 8) ? 6 : 3;
   return (size_t)passes * (num_segments > 0 ? num_segments : 0) * SEL_BINS * sizeof(unsigned);

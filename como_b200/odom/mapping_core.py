@@ -102,11 +102,9 @@ def _build_pair_plan(s, cfg, kp, dev, rank=0, world=1):
     ref, tgt, ow_kf, ow_t = setup_photometric_pairs(K, R, s.kf_timestamps, s.recent_timestamps, None,
                                                     cfg["photo_construction"])
     q.pairs_full = (ref, tgt, ow_kf, ow_t)
-    pair_ref = ref + ow_kf
-    pair_tgt = tgt + [K + t for t in ow_t]
-    keep = [i for i in range(len(pair_ref)) if pair_ref[i] % world == rank]
-    pair_ref = [pair_ref[i] for i in keep]
-    pair_tgt = [pair_tgt[i] for i in keep]
+    pair_ref, pair_tgt, pair_batch, nbatch = partition_pairs(ref, tgt, ow_kf, ow_t, K,
+                                                             int(cfg["photo_construction"]["pairwise_batch_size"]),
+                                                             rank, world)
     P = len(pair_ref)
     q.P, q.R = P, R
     by_ref = [[] for _ in range(K)]
@@ -140,13 +138,35 @@ def _build_pair_plan(s, cfg, kp, dev, rank=0, world=1):
     q.ref_ptr, q.ref_pairs = _i32(ref_ptr, dev), _i32(ref_pairs if ref_pairs else [0], dev)
     q.units = _i32(units if units else [[0] * 8], dev)
     q.unit_base, q.unit_slices = _i32(unit_base, dev), _i32(unit_slices, dev)
-    q.batch = int(cfg["photo_construction"]["pairwise_batch_size"])
-    if P > 0:
-        q.ws = torch.empty(int(_lib.ba_photo_workspace_bytes(K, R, kp.N, P, q.num_units, q.batch)), dtype=torch.uint8,
-                           device=dev)
-    else:
-        q.ws = None
+    q.nbatch = nbatch
+    q.pair_batch = _i32(pair_batch if pair_batch else [0], dev)
+    seg = [0]
+    for b in range(nbatch):
+        seg.append(seg[-1] + sum(1 for x in pair_batch if x == b) * kp.N)
+    q.seg_off = torch.tensor(seg, dtype=torch.int64).to(dev)
+    q.max_seg = max(1, max(seg[b + 1] - seg[b] for b in range(nbatch)))
+    N = kp.N
+    q.frames = torch.empty(int(_lib.ba_frames_bytes(K + R)), dtype=torch.uint8, device=dev)
+    q.refbuf = torch.empty(K * N * 8, dtype=F64, device=dev)
+    q.rbuf = torch.empty(max(P, 1) * N, dtype=F64, device=dev)
+    q.pairbuf = torch.empty(max(P, 1) * N * 4, dtype=F64, device=dev)
+    q.sigma_pair = torch.empty(max(P, 1), dtype=F64, device=dev)
+    q.partial = torch.empty(int(_lib.ba_partial_doubles(max(q.num_units, 1))), dtype=F64, device=dev)
+    q.hist = torch.zeros(int(_lib.median_num_passes(8)), nbatch, 2048, dtype=torch.int32, device=dev)
+    q.sigma = torch.empty(nbatch, dtype=F64, device=dev)
     return q
+
+
+def partition_pairs(ref, tgt, ow_kf, ow_t, K, batch_size, rank=0, world=1):
+    """Pure host logic (tested on CPU with gloo): the global pair list in the reference's order
+    (keyframe pairs, then one-way pairs; photo.py:262-300), its batches of `batch_size` pairs, and the
+    share of this rank: pairs whose REFERENCE keyframe k satisfies k % world == rank, order preserved.
+    Returns (pair_ref, pair_tgt [frame index, one-way frames offset by K], pair_batch, num_batches)."""
+    all_ref = list(ref) + list(ow_kf)
+    all_tgt = list(tgt) + [K + t for t in ow_t]
+    nbatch = max(1, (len(all_ref) + batch_size - 1) // batch_size)
+    keep = [i for i in range(len(all_ref)) if all_ref[i] % world == rank]
+    return ([all_ref[i] for i in keep], [all_tgt[i] for i in keep], [i // batch_size for i in keep], nbatch)
 
 
 def get_plans(s, cfg, dev, rank=0, world=1):
@@ -178,9 +198,11 @@ def solve_system(H, g):
     return torch.cholesky_solve(g[:, None], Lc, upper=False)
 
 
-def iterate(s, cfg, allreduce=None, rank=0, world=1, return_debug=False):
-    """One BA Gauss-Newton iteration; mutates `s` like Mapping.iterate.  `allreduce(H, g, err)` (optional)
-    sums the normal equations across ranks when the pair blocks are sharded (NCCL over NVLink)."""
+def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return_debug=False):
+    """One BA Gauss-Newton iteration; mutates `s` like Mapping.iterate.  When the pair blocks of one window
+    are sharded over `world` ranks (reference keyframe k on rank k % world), `hist_allreduce(t)` sums the
+    median digit histograms and `allreduce(H, g, err)` sums the photometric normal equations across ranks
+    (NCCL over NVLink); priors, solve and update are replicated on every rank."""
     dev = _lib.require_cuda(s.kf_poses, s.Knm_Kmminv, s.P_m, s.kf_img_and_grads)
     for name in ("kf_poses", "kf_aff_params", "P_m", "Knm_Kmminv", "kf_img_and_grads", "L_mm", "pm_first_obs",
                  "median_depths"):
@@ -242,18 +264,35 @@ def iterate(s, cfg, allreduce=None, rank=0, world=1, return_debug=False):
         Hm.zero_()
         g.zero_()
         err.zero_()
-        nb = max(1, (pp.P + pp.batch - 1) // pp.batch)
-        sig = _buf(cache, "sigma", (nb,), F64, dev)
+        sig = pp.sigma
         if pp.P > 0:
-            st = _lib.ba_photo(
+            st = _lib.ba_photo_residual(
                 _lib.ptr(s.kf_poses), _lib.ptr(s.kf_aff_params), _lib.ptr(rec_poses), _lib.ptr(rec_aff),
                 _lib.ptr(s.kf_img_and_grads), _lib.ptr(rec_img), _lib.ptr(s.Knm_Kmminv), _lib.ptr(kp.coords),
-                _lib.ptr(kp.vals_n), _lib.ptr(scaf), _lib.ptr(dz_dP), _lib.ptr(kp.lm_ids), _lib.ptr(pp.pair_ref),
-                _lib.ptr(pp.pair_tgt), _lib.ptr(pp.pair_slot), _lib.ptr(pp.ref_ptr), _lib.ptr(pp.ref_pairs),
-                _lib.ptr(pp.units), _lib.ptr(pp.unit_base), _lib.ptr(pp.unit_slices), pp.num_units, K, R, L, M, N, H,
-                W, pp.P, pp.batch, intr4, dim, _lib.ptr(Hm), _lib.ptr(g), _lib.ptr(err), _lib.ptr(sig), _lib.ptr(pp.ws),
-                pp.ws.numel(), stream)
-            _lib.check(st, "como_b200_ba_photo")
+                _lib.ptr(kp.vals_n), _lib.ptr(scaf), _lib.ptr(pp.pair_tgt), _lib.ptr(pp.ref_ptr), _lib.ptr(pp.ref_pairs),
+                K, R, M, N, H, W, pp.P, intr4, _lib.ptr(pp.frames), _lib.ptr(pp.refbuf), _lib.ptr(pp.rbuf),
+                _lib.ptr(pp.pairbuf), stream)
+            _lib.check(st, "como_b200_ba_photo_residual")
+        # exact robust scale per pair batch; with sharded pairs the digit histograms are summed across ranks
+        pp.hist.zero_()
+        for dgt in range(pp.hist.shape[0]):
+            if pp.P > 0:
+                st = _lib.median_pass_f64(_lib.ptr(pp.rbuf), _lib.ptr(pp.seg_off), pp.nbatch, pp.max_seg, dgt,
+                                          _lib.ptr(pp.hist), stream)
+                _lib.check(st, "como_b200_median_pass_f64")
+            if hist_allreduce is not None:
+                hist_allreduce(pp.hist[dgt])
+        st = _lib.median_finish_f64(pp.nbatch, _lib.ptr(pp.hist), 1.4826, _lib.ptr(sig), None, stream)
+        _lib.check(st, "como_b200_median_finish_f64")
+        if pp.P > 0:
+            st = _lib.ba_photo_accum(
+                _lib.ptr(s.Knm_Kmminv), _lib.ptr(kp.coords), _lib.ptr(scaf), _lib.ptr(dz_dP), _lib.ptr(kp.lm_ids),
+                _lib.ptr(pp.pair_ref), _lib.ptr(pp.pair_tgt), _lib.ptr(pp.pair_slot), _lib.ptr(pp.pair_batch),
+                _lib.ptr(pp.ref_ptr), _lib.ptr(pp.ref_pairs), _lib.ptr(pp.units), _lib.ptr(pp.unit_base),
+                _lib.ptr(pp.unit_slices), pp.num_units, K, R, L, M, N, H, W, pp.P, intr4, dim, _lib.ptr(sig),
+                _lib.ptr(pp.frames), _lib.ptr(pp.refbuf), _lib.ptr(pp.rbuf), _lib.ptr(pp.pairbuf), _lib.ptr(pp.sigma_pair),
+                _lib.ptr(pp.partial), _lib.ptr(Hm), _lib.ptr(g), _lib.ptr(err), stream)
+            _lib.check(st, "como_b200_ba_photo_accum")
         if allreduce is not None:
             allreduce(Hm, g, err)
         dbg = None

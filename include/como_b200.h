@@ -83,6 +83,13 @@ size_t como_b200_median_workspace_bytes(int32_t num_segments, int32_t elem_bytes
 int como_b200_median_f64(const double* values, const int64_t* seg_offsets, int32_t num_segments,
                          int64_t max_segment_len, double scale, double* out, int64_t* count, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* building blocks of the same selection for a median over values spread across ranks: zero hist
+ * (como_b200_median_num_passes x segments x 2048 uint32), then pass(digit) [+ all-reduce of hist[digit]] ..., finish. */
+int32_t como_b200_median_num_passes(int32_t elem_bytes);
+int como_b200_median_pass_f64(const double* values, const int64_t* seg_offsets, int32_t num_segments,
+                              int64_t max_segment_len, int32_t digit, void* hist, void* stream);
+int como_b200_median_finish_f64(int32_t num_segments, const void* hist, double scale, double* out, int64_t* count,
+                                void* stream);
 int como_b200_median_f32(const float* values, const int64_t* seg_offsets, int32_t num_segments,
                          int64_t max_segment_len, float scale, float* out, int64_t* count, void* workspace,
                          size_t workspace_bytes, void* stream);
@@ -115,25 +122,38 @@ int como_b200_predictor_apply(const double* Knm, const double* scaffold, int32_t
 int como_b200_predictor_colsum(const double* Knm, int64_t HW, int32_t M, double* colsum, void* stream);
 
 /* create_photo_system (como/odom/backend/photo.py:236-353) without the materialised (b,N,3,M,1)
- * Jacobian: residual pass, exact median per pair batch, accumulation pass, scatter into H, g.
- * Pair p: reference keyframe pair_ref[p], target frame pair_tgt[p], pair_slot[p] = position in the
- * reference keyframe's target list; ref_ptr (K+1) / ref_pairs (P): CSR of pairs by reference keyframe.
- * units (num_units, como_b200_ba_unit_ints() int32 each): [ref, pix_begin, pix_end, tgt_begin, tgt_end, primary,0,0],
- * ordered (ref, target group, slice); unit_base[ref] = first unit, unit_slices[ref] = slices per group.
- * photo_err: += sum w (r/sigma)^2; sigma_out (ceil(P/batch)) optional. */
-size_t como_b200_ba_photo_workspace_bytes(int32_t K, int32_t R, int32_t N, int32_t P, int32_t num_units,
-                                          int32_t batch_size);
+ * Jacobian, in three steps so that the robust scale can be made global across GPUs:
+ *   1. como_b200_ba_photo_residual : frame table + residual of every (pair, pixel)  -> rbuf (P,N) [NaN = invalid],
+ *                                    pairbuf (P,N,4), refbuf (K,N,8)
+ *   2. exact median of |rbuf| per pair batch: como_b200_median_pass_f64 x 6 (all-reduce hist[digit] between
+ *      passes when the pairs are sharded) + como_b200_median_finish_f64 with scale 1.4826  -> sigma_batch
+ *   3. como_b200_ba_photo_accum    : Huber weights, J^T J / J^T r blocks, scatter into H, g (atomics)
+ * Pair p: reference keyframe pair_ref[p], target frame pair_tgt[p], pair_slot[p] = position in the reference
+ * keyframe's target list, pair_batch[p] = its batch (photo.py:262-300); ref_ptr (K+1) / ref_pairs (P): CSR of
+ * pairs by reference keyframe.  units (num_units, como_b200_ba_unit_ints() int32 each):
+ * [ref, pix_begin, pix_end, tgt_begin, tgt_end, primary, 0, 0], ordered (ref, target group, slice);
+ * unit_base[ref] = first unit, unit_slices[ref] = slices per group (0: no pair on this rank).
+ * photo_err += sum w (r/sigma)^2. */
+size_t como_b200_ba_frames_bytes(int32_t num_frames);
+size_t como_b200_ba_partial_doubles(int32_t num_units);
 int32_t como_b200_ba_unit_ints(void);
 int32_t como_b200_ba_target_group(void);
-int como_b200_ba_photo(const double* kf_poses, const double* kf_aff, const double* rec_poses, const double* rec_aff,
-                       const double* kf_img, const double* rec_img, const double* Knm, const int32_t* coords,
-                       const double* vals_n, const double* scaffold, const double* dz_dP, const int32_t* lm_ids,
-                       const int32_t* pair_ref, const int32_t* pair_tgt, const int32_t* pair_slot,
-                       const int32_t* ref_ptr, const int32_t* ref_pairs, const int32_t* units,
-                       const int32_t* unit_base, const int32_t* unit_slices, int32_t num_units, int32_t K, int32_t R,
-                       int32_t L, int32_t M, int32_t N, int32_t Himg, int32_t Wimg, int32_t P, int32_t batch_size,
-                       const double* intr4, int32_t dim, double* H, double* g, double* photo_err, double* sigma_out,
-                       void* workspace, size_t workspace_bytes, void* stream);
+int como_b200_ba_photo_residual(const double* kf_poses, const double* kf_aff, const double* rec_poses,
+                                const double* rec_aff, const double* kf_img, const double* rec_img, const double* Knm,
+                                const int32_t* coords, const double* vals_n, const double* scaffold,
+                                const int32_t* pair_tgt, const int32_t* ref_ptr, const int32_t* ref_pairs, int32_t K,
+                                int32_t R, int32_t M, int32_t N, int32_t Himg, int32_t Wimg, int32_t P,
+                                const double* intr4, void* frames_ws, double* refbuf, double* rbuf, double* pairbuf,
+                                void* stream);
+int como_b200_ba_photo_accum(const double* Knm, const int32_t* coords, const double* scaffold, const double* dz_dP,
+                             const int32_t* lm_ids, const int32_t* pair_ref, const int32_t* pair_tgt,
+                             const int32_t* pair_slot, const int32_t* pair_batch, const int32_t* ref_ptr,
+                             const int32_t* ref_pairs, const int32_t* units, const int32_t* unit_base,
+                             const int32_t* unit_slices, int32_t num_units, int32_t K, int32_t R, int32_t L, int32_t M,
+                             int32_t N, int32_t Himg, int32_t Wimg, int32_t P, const double* intr4, int32_t dim,
+                             const double* sigma_batch, const void* frames_ws, const double* refbuf, const double* rbuf,
+                             const double* pairbuf, double* sigma_pair_ws, double* partial, double* H, double* g,
+                             double* photo_err, void* stream);
 
 /* Prior factors of Mapping.iterate (Mapping.py:809-917; como/odom/factors/*.py).  LtL (K,M,M) = L_mm^-T L_mm^-1.
  * sigmas4 HOST = [pixel_sigma_first, pose_prior, scale_prior, mean_depth_prior]; err8 += [_, gp, logdepth, pixel,

@@ -159,9 +159,12 @@ def bilinear3(img3, u, v):
 
 
 # ------------------------------------------------------------------------------------------ iterate
-def iterate(s, cfg):
+def iterate(s, cfg, rank=0, world=1, photo_only=False):
     """One BA GN iteration on a state dict `s` (keys = the reference Mapping attribute names).
-    Mutates s like Mapping.iterate and returns a dict of intermediates (H, g, delta, errors, pairs ...)."""
+    Mutates s like Mapping.iterate and returns a dict of intermediates (H, g, delta, errors, pairs ...).
+    rank/world model the multi-GPU sharding: the robust scale uses ALL pairs of a batch, but only the pairs
+    whose reference keyframe k has k % world == rank are accumulated; with photo_only the function returns
+    after the photometric blocks (the quantity the ranks all-reduce)."""
     Kmat = s["intrinsics"][0]
     fx, fy, cx, cy = Kmat[0, 0], Kmat[1, 1], Kmat[0, 2], Kmat[1, 2]
     kf_poses = s["kf_poses"]
@@ -284,6 +287,8 @@ def iterate(s, cfg):
         allr = torch.cat([p[7][p[4]].abs() for p in pend])
         sigma = 1.4826 * lower_median(allr)
         for (i, indj, Rj, Pcj, valid, dI, vsc, r) in pend:
+            if i % world != rank:
+                continue
             wr = (r / sigma).abs()
             wgt = torch.where(wr < HUBER_K, torch.ones_like(wr), HUBER_K / wr) * valid.to(F64)
             sc = torch.sqrt(wgt) / sigma
@@ -319,6 +324,8 @@ def iterate(s, cfg):
             add_block(li, li, HPP)
         pair_dbg.append(float(sigma))
     H_photo, g_photo = H.clone(), g.clone()
+    if photo_only:
+        return dict(H_photo=H_photo, g_photo=g_photo, photo_err=photo_err, sigmas=pair_dbg)
 
     # ---- priors (a23)
     logmed = torch.log(med)[:, None, None]
