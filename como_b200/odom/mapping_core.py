@@ -327,3 +327,27 @@ def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return
         dbg.update(H=Hm.clone(), g=g.clone(), delta=delta.clone(), err=err.clone())
         return dbg
     return getattr(s, "converged", False)
+
+
+def store_vars(s, pm, logzm, Knm_Kmminv):
+    """Drop-in for Mapping.store_vars (como/odom/Mapping.py:749-758): dense depth of every keyframe from the
+    predictor (one streaming pass over Knm_Kmminv) and the exact per-keyframe median depth."""
+    dev = _lib.require_cuda(logzm, Knm_Kmminv)
+    K, H, W, M = Knm_Kmminv.shape
+    s.pm = pm
+    s.logzm = logzm
+    with torch.cuda.device(dev):
+        scaf = torch.zeros(K, M, SCAF, dtype=F64, device=dev)
+        scaf[:, :, 0] = logzm.reshape(K, M).to(F64)
+        depth = torch.empty(K, 1, H, W, dtype=F64, device=dev)
+        st = _lib.predictor_apply(_lib.ptr(Knm_Kmminv.contiguous()), _lib.ptr(scaf), K, H * W, M, _lib.ptr(depth),
+                                  _lib.stream_ptr(dev))
+        _lib.check(st, "como_b200_predictor_apply")
+        med = torch.empty(K, dtype=F64, device=dev)
+        seg = (torch.arange(K + 1, dtype=torch.int64) * (H * W)).to(dev)
+        ws = torch.empty(int(_lib.median_workspace_bytes(K, 8)), dtype=torch.uint8, device=dev)
+        st = _lib.median_f64(_lib.ptr(depth), _lib.ptr(seg), K, H * W, 1.0, _lib.ptr(med), None, _lib.ptr(ws), ws.numel(),
+                             _lib.stream_ptr(dev))
+        _lib.check(st, "como_b200_median_f64")
+    s.depth_imgs = depth
+    s.median_depths = med

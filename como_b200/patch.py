@@ -1,0 +1,59 @@
+"""Drop-in installer: routes the reference package's hot path to the B200 kernels without touching
+como_dataset.py, the GUI, the orchestration or the data loaders.
+
+    import como_b200.patch as p; p.install()       # before `from como.odom...` objects are created
+    python como/como_dataset.py ...                 # unchanged entry point
+
+What is replaced (reference name -> como_b200 implementation):
+  sys.modules["como_backends"]                                  -> como_b200.como_backends
+  como.depth_cov.core.samplers.sample_sparse_coords             -> como_b200.depth_cov.core.samplers.sample_sparse_coords
+  como.odom.frontend.photo_tracking.photo_tracking_pyr / precalc_jacobians (also as imported by como.odom.Tracking)
+  como.odom.Mapping.Mapping.iterate / store_vars / prep_predictor
+  como.odom.backend.linear_system.solve_system
+Everything else (two-frame initialisation, keyframe creation, correspondence search, UNet) keeps running the
+reference's own Python on the same device.  Requires tracking.dtype float / mapping.dtype double, color gray.
+"""
+import sys
+
+
+def install():
+    import como_b200.como_backends as cb
+
+    sys.modules["como_backends"] = cb  # must happen before como.depth_cov.core.samplers is imported
+    import como.depth_cov.core.samplers as ref_samplers
+    import como.odom.backend.linear_system as ref_ls
+    import como.odom.frontend.photo_tracking as ref_pt
+    import como.odom.Mapping as ref_mapping
+    import como.odom.Tracking as ref_tracking
+
+    from como_b200.depth_cov.core import predictor as b_pred
+    from como_b200.depth_cov.core import samplers as b_samplers
+    from como_b200.odom import mapping_core as mc
+    from como_b200.odom.frontend import photo_tracking as b_pt
+
+    ref_samplers.como_backends = cb
+    ref_samplers.sample_sparse_coords = b_samplers.sample_sparse_coords
+    for mod in list(sys.modules.values()):
+        if mod is not None and getattr(mod, "__name__", "").startswith("como.") and hasattr(mod, "sample_sparse_coords"):
+            mod.sample_sparse_coords = b_samplers.sample_sparse_coords
+    ref_pt.photo_tracking_pyr = b_pt.photo_tracking_pyr
+    ref_pt.precalc_jacobians = b_pt.precalc_jacobians
+    ref_tracking.photo_tracking_pyr = b_pt.photo_tracking_pyr
+    ref_tracking.precalc_jacobians = b_pt.precalc_jacobians
+    ref_ls.solve_system = mc.solve_system
+
+    def iterate(self):
+        return mc.iterate(self, self.cfg)
+
+    def store_vars(self, pm, logzm, Knm_Kmminv):
+        return mc.store_vars(self, pm, logzm, Knm_Kmminv)
+
+    def prep_predictor(self, cov_params_img, coords_m):
+        scale = float(self.model.cov_modules[-1].get_scale())
+        return b_pred.prep_predictor(cov_params_img, coords_m, scale, photo_img_size=self.kf_img_and_grads.shape[-2:])
+
+    ref_mapping.Mapping.iterate = iterate
+    ref_mapping.Mapping.store_vars = store_vars
+    ref_mapping.Mapping.prep_predictor = prep_predictor
+    return {"patched": ["como_backends", "sample_sparse_coords", "photo_tracking_pyr", "precalc_jacobians",
+                        "Mapping.iterate", "Mapping.store_vars", "Mapping.prep_predictor", "solve_system"]}

@@ -1,0 +1,36 @@
+"""CPU-only: como_b200.patch.install() rebinds the reference's hot-path names (needs the reference tree,
+so it only runs in the authoring container)."""
+import sys
+
+import pytest
+
+from oracle import ref_harness
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not present")
+def test_install_rebinds_reference_names():
+    ref_harness.load_reference()
+    saved = sys.modules.get("como_backends")
+    try:
+        import como_b200.patch as P
+
+        info = P.install()
+        import como.odom.Mapping as RM
+        import como.odom.Tracking as RT
+        import como.depth_cov.core.samplers as RS
+        import como_b200.odom.frontend.photo_tracking as BPT
+
+        assert RT.photo_tracking_pyr is BPT.photo_tracking_pyr
+        assert RT.precalc_jacobians is BPT.precalc_jacobians
+        assert RM.Mapping.iterate.__module__ == "como_b200.patch"
+        assert RS.sample_sparse_coords.__module__ == "como_b200.depth_cov.core.samplers"
+        assert sys.modules["como_backends"].__name__ == "como_b200.como_backends"
+        assert "Mapping.iterate" in info["patched"]
+        # no CPU fallback: the patched operators refuse CPU tensors loudly
+        import torch
+        with pytest.raises(RuntimeError, match="same device"):
+            sys.modules["como_backends"].cross_covariance(torch.zeros(1, 1, 2), torch.zeros(1, 1, 2, 2),
+                                                          torch.zeros(1, 1, 2), torch.zeros(1, 1, 2, 2), 1.0)
+    finally:
+        if saved is not None:
+            sys.modules["como_backends"] = saved
