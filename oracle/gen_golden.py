@@ -21,8 +21,8 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 def _np(t):
     if isinstance(t, torch.Tensor):
-        return t.detach().cpu().numpy()
-    return np.asarray(t)
+        return t.detach().cpu().numpy().copy()  # copy: the reference mutates several tensors in place later
+    return np.array(t)
 
 
 def ref_cfg():
