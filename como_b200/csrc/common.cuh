@@ -123,4 +123,49 @@ __host__ __device__ inline void chol_solve_small(double* A, double* b) {
   }
 }
 
+// Warp-cooperative 8x8 SPD solve (fp64): lane i < 8 owns row i of the symmetric matrix (r[0..7]) and its
+// right-hand side; returns x_i on lane i (valid for lanes 0..7).  Right-looking Cholesky with one rsqrt per
+// column instead of a sqrt + 8 divisions, substitutions through shuffles / 64 doubles of shared scratch.
+// Must be called by all 32 lanes of one warp; non-PD input gives NaN (never traps).
+__device__ __forceinline__ double warp_chol_solve8(double r[8], double rhs, double* s_L /* >= 64 doubles */) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double inv_diag[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double djj = __shfl_sync(full, r[j], j);
+    const double rs = rsqrt(djj);
+    inv_diag[j] = rs;              // 1 / L[j][j]
+    const double lij = r[j] * rs;  // L[i][j] for lane i >= j (lane j: sqrt(djj))
+    r[j] = lij;
+#pragma unroll
+    for (int k = j + 1; k < 8; ++k) {
+      const double lkj = __shfl_sync(full, lij, k);
+      r[k] -= lij * lkj;           // meaningful for lanes i >= k
+    }
+  }
+  if (lane < 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s_L[lane * 8 + k] = r[k];
+  }
+  __syncwarp();
+  // forward substitution L y = b
+  double sacc = rhs, y = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double yj = __shfl_sync(full, sacc * inv_diag[j], j);
+    if (lane == j) y = yj;
+    sacc -= r[j] * yj;             // lanes i > j use L[i][j]
+  }
+  // back substitution L^T x = y : x_j = (y_j - sum_{k>j} L[k][j] x_k) / L[j][j]
+  double t = y, x = 0.0;
+#pragma unroll
+  for (int j = 7; j >= 0; --j) {
+    const double xj = __shfl_sync(full, t * inv_diag[j], j);
+    if (lane == j) x = xj;
+    if (lane < j) t -= s_L[j * 8 + lane] * xj;
+  }
+  return x;
+}
+
 }  // namespace como

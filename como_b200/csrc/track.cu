@@ -127,6 +127,8 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
   __shared__ unsigned s_warp[TRK_WARPS];
   __shared__ unsigned s_sel[3];
   __shared__ int s_done;
+  __shared__ double s_chol[64];
+  __shared__ double s_delta[8];
 
   for (int b = tid; b < HIST_BINS; b += TRK_THREADS) s_hist[b] = 0;
   if (tid < 16) s_T[tid] = T_io[prob * 16 + tid];
@@ -317,55 +319,64 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         if (s8 == 0 && k < NACC) s_acc[k] = s;
       }
       __syncthreads();
-      if (tid == 0) {
-        double Hm[64], g[8];
-        int q = 0;
-        for (int k = 0; k < 8; ++k)
-          for (int m = k; m < 8; ++m) {
-            Hm[k * 8 + m] = s_acc[q];
-            Hm[m * 8 + k] = s_acc[q];
-            ++q;
-          }
-        double gn2 = 0.0;
-        for (int k = 0; k < 8; ++k) {
-          g[k] = s_acc[36 + k];
-          gn2 += g[k] * g[k];
+      if (wid == 0) {
+        // 8x8 solve by one warp: lane i < 8 owns row i (packed upper triangle -> full row)
+        double row[8];
+        const int li = lane & 7;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const int a = li < m ? li : m, b = li < m ? m : li;
+          row[m] = s_acc[a * 8 - (a * (a - 1)) / 2 + (b - a)];
         }
-        const double mse = s_acc[44] / (double)nvalid;
-        chol_solve_small<8>(Hm, g);  // g <- delta
-        double dn2 = 0.0;
-        for (int k = 0; k < 8; ++k) dn2 += g[k] * g[k];
-        // T <- T * Exp(-delta[0:6]); COMO tangent [omega, v] -> lietorch [tau=v, phi=omega]
-        const double tau[3] = {-g[3], -g[4], -g[5]};
-        const double phi[3] = {-g[0], -g[1], -g[2]};
-        double E[16];
-        se3_exp_tau_phi(tau, phi, E);
-        float Tn[16];
-        for (int r = 0; r < 4; ++r)
-          for (int cc = 0; cc < 4; ++cc) {
-            double s = 0.0;
-            for (int k = 0; k < 4; ++k) s += (double)s_T[r * 4 + k] * E[k * 4 + cc];
-            Tn[r * 4 + cc] = (float)s;
+        if (lane >= 8) {
+#pragma unroll
+          for (int m = 0; m < 8; ++m) row[m] = (m == li) ? 1.0 : 0.0;  // harmless identity rows
+        }
+        const double gi = s_acc[36 + li];
+        const double di = warp_chol_solve8(row, lane < 8 ? gi : 0.0, s_chol);
+        double dn2 = (lane < 8) ? di * di : 0.0, gn2 = (lane < 8) ? gi * gi : 0.0;
+        dn2 = warp_sum(dn2);
+        gn2 = warp_sum(gn2);
+        if (lane < 8) s_delta[lane] = di;
+        __syncwarp();
+        if (lane == 0) {
+          const double mse = s_acc[44] / (double)nvalid;
+          // T <- T * Exp(-delta[0:6]); COMO tangent [omega, v] -> lietorch [tau=v, phi=omega]
+          const double tau[3] = {-s_delta[3], -s_delta[4], -s_delta[5]};
+          const double phi[3] = {-s_delta[0], -s_delta[1], -s_delta[2]};
+          double E[16];
+          se3_exp_tau_phi(tau, phi, E);
+          float Tn[16];
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              double sacc = 0.0;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) sacc += (double)s_T[r * 4 + k] * E[k * 4 + cc];
+              Tn[r * 4 + cc] = (float)sacc;
+            }
+#pragma unroll
+          for (int k = 0; k < 16; ++k) s_T[k] = Tn[k];
+          s_aff[0] = (float)((double)s_aff[0] - s_delta[6]);
+          s_aff[1] = (float)((double)s_aff[1] - s_delta[7]);
+          const double dn = sqrt(dn2), gnorm = sqrt(gn2);
+          const double rel = fabs((mse_prev - mse) / mse_prev);  // NaN on the first iteration -> false
+          const bool done = (it + 1 >= term.max_iter) || (dn < (double)term.delta_norm) ||
+                            (rel < (double)term.rel_tol) || (gnorm < (double)term.grad_norm) || (nvalid == 0);
+          s_done = done ? 1 : 0;
+          s_acc[45] = mse;
+          if (c == 0 && stats != nullptr && total_iter < stats_cap) {
+            float* st = stats + ((size_t)prob * stats_cap + total_iter) * COMO_B200_TRACK_STAT_STRIDE;
+            st[0] = (float)l;
+            st[1] = (float)mse;
+            st[2] = (float)gnorm;
+            st[3] = (float)dn;
+            st[4] = sigma;
+            st[5] = (float)nvalid;
+            st[6] = done ? 1.0f : 0.0f;
+            st[7] = 0.0f;
           }
-        for (int k = 0; k < 16; ++k) s_T[k] = Tn[k];
-        s_aff[0] = (float)((double)s_aff[0] - g[6]);
-        s_aff[1] = (float)((double)s_aff[1] - g[7]);
-        const double dn = sqrt(dn2), gnorm = sqrt(gn2);
-        const double rel = fabs((mse_prev - mse) / mse_prev);  // NaN on the first iteration -> false
-        const bool done = (it + 1 >= term.max_iter) || (dn < (double)term.delta_norm) ||
-                          (rel < (double)term.rel_tol) || (gnorm < (double)term.grad_norm) || (nvalid == 0);
-        s_done = done ? 1 : 0;
-        s_acc[45] = mse;
-        if (c == 0 && stats != nullptr && total_iter < stats_cap) {
-          float* st = stats + ((size_t)prob * stats_cap + total_iter) * COMO_B200_TRACK_STAT_STRIDE;
-          st[0] = (float)l;
-          st[1] = (float)mse;
-          st[2] = (float)gnorm;
-          st[3] = (float)dn;
-          st[4] = sigma;
-          st[5] = (float)nvalid;
-          st[6] = done ? 1.0f : 0.0f;
-          st[7] = 0.0f;
         }
       }
       __syncthreads();
