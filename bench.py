@@ -243,7 +243,9 @@ def run_ba_ours(args, rank, world, device):
     K, R, H, W, M = args.kf, args.oneway, 480, 640, 64
     s = synth.make_ba_window(K, R, H, W, M=M, device=device, seed=rank)
     cfg = synth.ba_cfg()
+    snap = snapshot_small(s) if rank == 0 else None   # CPU baseline runs on the untouched initial state
     allreduce = None
+    hist_allreduce = None
     shard = world > 1 and args.shard
     if shard:
         def allreduce(Hm, g, err):
@@ -251,8 +253,12 @@ def run_ba_ours(args, rank, world, device):
             torch.distributed.all_reduce(g)
             torch.distributed.all_reduce(err)
 
+        def hist_allreduce(t):
+            torch.distributed.all_reduce(t)
+
     def step():
-        MC.iterate(s, cfg, allreduce=allreduce, rank=rank if shard else 0, world=world if shard else 1)
+        MC.iterate(s, cfg, allreduce=allreduce, hist_allreduce=hist_allreduce, rank=rank if shard else 0,
+                   world=world if shard else 1)
 
     for _ in range(args.warmup):
         step()
@@ -340,16 +346,31 @@ def run_ba_ours(args, rank, world, device):
                      "alg_bytes_per_launch": ab["predictor_apply"], "launch_ms": pa_ms},
         "clocks": clocks,
     }
-    return res, s, cfg
+    res["finite"] = bool(torch.isfinite(s.kf_poses).all() and torch.isfinite(s.P_m).all())
+    res["final_total_err"] = float(s.total_err_prev)
+    return res, (s, snap), cfg
 
 
-def cpu_ba_baseline(s, cfg, max_iters=1):
-    """Oracle port of Mapping.iterate on the host cores (torch CPU, fp64), on the same window."""
-    from oracle import ba_oracle as BO
-
+def snapshot_small(s):
+    """Host copy of everything but the big constant tensors (those are copied lazily by the CPU baseline)."""
     sc = {}
     for k, v in s.__dict__.items():
         if k.startswith("_"):
+            continue
+        if isinstance(v, torch.Tensor) and v.numel() < (1 << 24):
+            sc[k] = v.detach().cpu().clone()
+        elif not isinstance(v, torch.Tensor):
+            sc[k] = list(v) if isinstance(v, list) else v
+    return sc
+
+
+def cpu_ba_baseline(s_and_snap, cfg, max_iters=1):
+    """Oracle port of Mapping.iterate on the host cores (torch CPU, fp64), on the same window (initial state)."""
+    from oracle import ba_oracle as BO
+
+    s, sc = s_and_snap
+    for k, v in s.__dict__.items():
+        if k.startswith("_") or k in sc:
             continue
         sc[k] = v.detach().cpu() if isinstance(v, torch.Tensor) else v
     t0 = time.time()
@@ -441,7 +462,10 @@ def main():
     else:
         res, s, cfg = run_ba_ours(args, rank, world, device)
         if rank == 0:
-            res["cpu_baseline"] = cpu_ba_baseline(s, cfg) if world == 1 else None
+            try:
+                res["cpu_baseline"] = cpu_ba_baseline(s, cfg) if world == 1 else None
+            except Exception as ex:  # the headline must still be printed
+                res["cpu_baseline"] = {"error": repr(ex)[:200]}
             print(json.dumps(res))
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -61,6 +61,20 @@ def make_cov_image(H, W, seed=0, dtype=torch.float32, device="cpu"):
     return torch.stack((x, off, off, z), dim=1).to(dtype=dtype, device=device)
 
 
+def make_cov_image_wide(H, W, seed=0, dtype=torch.float64, device="cpu"):
+    """Variant with moderate, slowly varying length scales (std 0.07-0.15 in normalised coordinates): anchors
+    0.1 apart stay moderately correlated, so K_mm is well conditioned and the predictor interpolates smoothly --
+    closer to what the trained DepthCov network produces than `make_cov_image`'s wide range."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand(1, 3, max(H // 24, 2), max(W // 24, 2), generator=g)
+    f = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False).clamp(0.02, 0.98)
+    x = 5e-3 * torch.exp(1.5 * f[:, 0])
+    z = 5e-3 * torch.exp(1.5 * f[:, 1])
+    rho = 0.5 * (2 * f[:, 2] - 1)
+    off = torch.sqrt(x * z - 1e-8) * rho
+    return torch.stack((x, off, off, z), dim=1).to(dtype=dtype, device=device)
+
+
 TRACK_PERTURB = (0.01, -0.008, 0.005, 0.02, -0.01, 0.015)  # [omega, v], SURVEY 8d
 
 
@@ -192,7 +206,7 @@ def make_ba_window(K, R, H, W, M=64, device="cuda", seed=0, step=6.0, ndrop=20, 
     border = 3
     for k in range(K):
         img, T = frame(k)
-        cov = make_cov_image(H, W, seed=1000 + seed * 100 + k, dtype=f64, device=dev)
+        cov = make_cov_image_wide(H, W, seed=1000 + seed * 100 + k, dtype=f64, device=dev)
         if k == 0:
             c, _ = sample_sparse_coords(cov, M, "greedy_conditional_entropy", max_stdev_thresh=1e-2, border=border,
                                         dist_thresh=0.1, signal_var=torch.tensor(1.0), fixed_var=0.0)

@@ -28,7 +28,7 @@ def test_cross_covariance_vs_reference(golden_dir):
     K2 = CB.cross_covariance(x1[:, ::2], c("cc_E1")[:, ::2], c("cc_x2"), c("cc_E2"), 0.83).cpu().numpy()
     np.testing.assert_allclose(K2, g["cc_K"][:, ::2], rtol=3e-7)
     K3 = CB.cross_covariance(x1.double(), c("cc_E1").double(), c("cc_x2").double(), c("cc_E2").double(), 0.83)
-    np.testing.assert_allclose(K3.cpu().numpy(), g["cc_K"], rtol=2e-6)
+    np.testing.assert_allclose(K3.cpu().numpy(), g["cc_K"], rtol=2e-5, atol=1e-9)  # fp64 result vs the fp32 golden
     with pytest.raises(RuntimeError, match="same device"):
         CB.cross_covariance(x1.cpu(), c("cc_E1"), c("cc_x2"), c("cc_E2"), 0.83)
 
