@@ -62,14 +62,14 @@ def make_cov_image(H, W, seed=0, dtype=torch.float32, device="cpu"):
 
 
 def make_cov_image_wide(H, W, seed=0, dtype=torch.float64, device="cpu"):
-    """Variant with moderate, slowly varying length scales (std 0.07-0.15 in normalised coordinates): anchors
-    0.1 apart stay moderately correlated, so K_mm is well conditioned and the predictor interpolates smoothly --
-    closer to what the trained DepthCov network produces than `make_cov_image`'s wide range."""
+    """Variant with long, slowly varying length scales (std 0.45-0.65 in normalised coordinates): the predictor
+    rows sum to ~1 (0.9..1.06), i.e. the GP interpolates between anchors instead of reverting to its zero mean --
+    what the trained DepthCov network produces on smooth surfaces."""
     g = torch.Generator().manual_seed(seed)
     low = torch.rand(1, 3, max(H // 24, 2), max(W // 24, 2), generator=g)
     f = torch.nn.functional.interpolate(low, size=(H, W), mode="bicubic", align_corners=False).clamp(0.02, 0.98)
-    x = 5e-3 * torch.exp(1.5 * f[:, 0])
-    z = 5e-3 * torch.exp(1.5 * f[:, 1])
+    x = 2e-1 * torch.exp(0.7 * f[:, 0])
+    z = 2e-1 * torch.exp(0.7 * f[:, 1])
     rho = 0.5 * (2 * f[:, 2] - 1)
     off = torch.sqrt(x * z - 1e-8) * rho
     return torch.stack((x, off, off, z), dim=1).to(dtype=dtype, device=device)
@@ -171,10 +171,24 @@ def make_tracking_case(H, W, num_levels, seed=0, cell=16, device="cpu", noise2=0
 # landmark count grows like the real system (L ~ M + ndrop (K-1)); predictors from the fused K-matrix
 # kernel.  Needs CUDA.  Returns a mapping_core.WindowState with the reference Mapping attribute names.
 # ---------------------------------------------------------------------------------------------
-def make_ba_window(K, R, H, W, M=64, device="cuda", seed=0, step=6.0, ndrop=20, pose_noise=2e-3, window_full=False):
-    from como_b200.depth_cov.core.predictor import prep_predictor
-    from como_b200.depth_cov.core.samplers import sample_sparse_coords
+def make_ba_window(K, R, H, W, M=64, device="cuda", seed=0, step=6.0, ndrop=20, pose_noise=2e-3, window_full=False,
+                   sampler=None, predictor=None, img_noise=0.04):
+    """`sampler(cov, n, curr_coords_or_None) -> (1,k,2) coords` and `predictor(cov, coords) -> (Kinv, L, slab)` default
+    to the CUDA product implementations; tests inject CPU oracles to build the same scene without a GPU."""
     from como_b200.odom.mapping_core import WindowState
+
+    if sampler is None:
+        from como_b200.depth_cov.core.samplers import sample_sparse_coords as _ssc
+
+        def sampler(cov, n, curr):
+            c, _ = _ssc(cov, n, "greedy_conditional_entropy", max_stdev_thresh=1e-2, border=3, dist_thresh=0.1,
+                        signal_var=torch.tensor(1.0), fixed_var=0.0, curr_coords=curr)
+            return c
+    if predictor is None:
+        from como_b200.depth_cov.core.predictor import prep_predictor as _pp
+
+        def predictor(cov, coords):
+            return _pp(cov, coords, 1.0)
 
     dev = torch.device(device)
     f64 = torch.float64
@@ -187,6 +201,9 @@ def make_ba_window(K, R, H, W, M=64, device="cuda", seed=0, step=6.0, ndrop=20, 
     def frame(k):
         x0 = int(k * step)
         rgb = tex[..., x0:x0 + W]
+        # independent sensor noise per frame: keeps the robust scale sigma = 1.4826 med|r| at a realistic level
+        # (noise-free copies of one texture let sigma -> 0 and the photometric weights explode)
+        rgb = (rgb + img_noise * (torch.rand(rgb.shape, generator=g, dtype=f64) - 0.5).to(dev)).clamp(0, 1)
         gray = _gray(rgb)
         gx, gy = _scharr(gray)
         T = torch.eye(4, dtype=f64)
@@ -208,8 +225,7 @@ def make_ba_window(K, R, H, W, M=64, device="cuda", seed=0, step=6.0, ndrop=20, 
         img, T = frame(k)
         cov = make_cov_image_wide(H, W, seed=1000 + seed * 100 + k, dtype=f64, device=dev)
         if k == 0:
-            c, _ = sample_sparse_coords(cov, M, "greedy_conditional_entropy", max_stdev_thresh=1e-2, border=border,
-                                        dist_thresh=0.1, signal_var=torch.tensor(1.0), fixed_var=0.0)
+            c = sampler(cov, M, None)
             coords = c[0].to(f64)
             lms = list(range(M))
             nlm = M
@@ -221,16 +237,14 @@ def make_ba_window(K, R, H, W, M=64, device="cuda", seed=0, step=6.0, ndrop=20, 
             order = torch.randperm(M, generator=g)[:ndrop].tolist()
             keep = [m for m in range(M) if bool(inside[m]) and m not in order]
             tracked = prev[keep]
-            c, _ = sample_sparse_coords(cov, M, "greedy_conditional_entropy", max_stdev_thresh=1e-2, border=border,
-                                        dist_thresh=0.1, signal_var=torch.tensor(1.0), fixed_var=0.0,
-                                        curr_coords=tracked[None].float())
+            c = sampler(cov, M, tracked[None].float())
             new = c[0].to(f64)
             coords = torch.cat((tracked, new), 0)[:M]
             new_dim = coords.shape[0] - len(keep)
             lms = [lm_of_slot[-1][m] for m in keep] + list(range(nlm, nlm + new_dim))
             nlm += new_dim
         assert coords.shape[0] == M, "sampler returned too few anchors for the synthetic window"
-        Kinv, Lm, slab = prep_predictor(cov, coords[None], 1.0)
+        Kinv, Lm, slab = predictor(cov, coords[None])
         zs = Z * (1.0 + 0.01 * (torch.rand(M, generator=g, dtype=f64) - 0.5)).to(dev)
         # world points of the NEW landmarks of this keyframe (GT pose, perturbed depth)
         pix = torch.stack((coords[:, 1], coords[:, 0]), -1)  # (x, y)

@@ -188,13 +188,16 @@ def build_reference_window(H, W, NKF, NOW, M, cfg_num_kf, step=3.0):
         # perturbed initial pose/affine so the optimiser has something to do
         T = T.clone()
         T[0, 0, 3] += 0.002 * ((-1) ** k)
-        T[0, 1, 3] += 0.001
+        T[0, 1, 3] += 0.0007 * k + 0.0003  # distinct per keyframe: equal offsets put rows exactly on the v = 1 border
         m.add_keyframe(rgb, T, torch.tensor([[[0.01 * k], [-0.005 * k]]], dtype=torch.double), 1.0 + k)
     nwin = m.kf_poses.shape[0]
     t0 = m.kf_timestamps[0]
     for j in range(NOW):
         kk = (j % (nwin - 1)) + 0.5 + (t0 - 1.0)
         rgb, T = frame(kk)
+        T = T.clone()
+        T[0, 1, 3] += 0.00053 + 0.00021 * j   # keep projections off the exact v = 1 / v = H-2 rows
+        T[0, 0, 3] += 0.0011 * ((-1) ** j)
         m.add_one_way_frame(rgb, T, torch.zeros(1, 2, 1, dtype=torch.double), 1.0 + kk + 0.001 * j)
     # the reference keeps recent frames time ordered; emulate arrival order by sorting all recent state
     order = sorted(range(len(m.recent_timestamps)), key=lambda i: m.recent_timestamps[i])

@@ -146,3 +146,22 @@ def test_small_batch_size_splits_median_segments():
     assert len(o["sigmas"]) == 3
     assert rel(dbg["sigma"], torch.tensor(o["sigmas"])) < 1e-6
     assert rel(dbg["H"], o["H"]) < 1e-6
+
+
+def test_synthetic_window_iterations_stay_finite_and_converge():
+    """Ten GN iterations on a synthetic window: finite state, stable robust scale, shrinking updates."""
+    from como_b200 import synth
+    from como_b200.odom import mapping_core as MC
+
+    s = synth.make_ba_window(6, 9, 96, 128, M=32, seed=3, ndrop=8)
+    cfg = synth.ba_cfg()
+    sig, dn = [], []
+    for it in range(10):
+        dbg = MC.iterate(s, cfg, return_debug=True)
+        sig.append(float(dbg["sigma"][0]))
+        dn.append(float(dbg["delta"].abs().max()))
+    assert torch.isfinite(s.kf_poses).all() and torch.isfinite(s.P_m).all()
+    assert 0.5 * sig[0] < sig[-1] < 2.0 * sig[0]
+    assert dn[-1] < 0.2 * dn[0]
+    gt = torch.tensor([k * 6.0 * 2.0 / (525 * 128 / 640) for k in range(6)], dtype=torch.float64)
+    assert float((s.kf_poses[:, 0, 3].cpu() - gt).abs().max()) < 0.05

@@ -113,3 +113,36 @@ def test_all_points_masked_or_invalid_does_not_hang():
     T, aff, stats = cuda_track(case, case["T_init"], case["aff_init"], TERM)
     assert stats.shape[0] == 2  # one (degenerate) iteration per level, flagged done
     assert torch.isnan(T).any() or torch.isfinite(T).all()
+
+
+def test_config1_shape_320x240_one_iteration_vs_oracle():
+    """BASELINE config 1: 2-frame 320x240 photometric tracking, 3 levels, 1 GN iteration per level."""
+    from como_b200 import synth
+
+    case = synth.make_tracking_case(240, 320, 3, seed=2, cell=8)
+    term = dict(TERM, max_iter=1)
+    T, aff, stats = cuda_track(case, case["T_init"], case["aff_init"], term)
+    To, affo, trace = TO.track_pyr(case["T_init"], case["aff_init"], case["vals"], case["P"], case["dI_dT"],
+                                   case["mask"], case["K"], case["img"], term)
+    assert stats.shape[0] == len(trace) == 3
+    st = stats.cpu().numpy()
+    assert abs(st[0, 1] - trace[0]["mse"]) <= (1e-4 + 2.0 / trace[0]["nvalid"]) * trace[0]["mse"]
+    assert se3_log_err(T[0].cpu().numpy(), To.numpy()) < 1e-4
+    np.testing.assert_allclose(aff.cpu().numpy().ravel(), affo.numpy().ravel(), atol=1e-4)
+
+
+def test_batched_independent_sequences_match_single_launches():
+    """BASELINE config 5 shape: independent sequences batched in one launch give the per-sequence results."""
+    from como_b200 import synth
+    from como_b200.odom.frontend.photo_tracking import photo_tracking_pyr_batch
+
+    cases = [synth.make_tracking_case(120, 160, 3, seed=s, cell=8, device="cuda") for s in range(5)]
+    probs = [(c["vals"], c["P"], c["dI_dT"], c["mask"], c["K"], c["img"]) for c in cases]
+    T0 = torch.cat([c["T_init"] for c in cases])
+    a0 = torch.cat([c["aff_init"] for c in cases])
+    Tb, ab, nit = photo_tracking_pyr_batch(T0, a0, probs, TERM)
+    for i, c in enumerate(cases):
+        T1, a1, st = cuda_track({k: v for k, v in c.items() if isinstance(v, list)}, c["T_init"], c["aff_init"], TERM)
+        assert int(nit[i]) == st.shape[0]
+        # different CTA counts change the summation order only
+        assert se3_log_err(Tb[i].cpu().numpy(), T1[0].cpu().numpy()) < 1e-5
