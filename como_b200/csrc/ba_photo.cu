@@ -61,8 +61,10 @@ ba_residual_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ c
     lv[v][0] = s_vec[v][m0 < BA_MAXM ? m0 : 0];
     lv[v][1] = s_vec[v][m0 + 1 < BA_MAXM ? m0 + 1 : 0];
   }
-  // ---- stage 1: 32 rows, 7 dot products each
-  double mine[7] = {0, 0, 0, 0, 0, 0, 0};
+  // ---- stage 1: 32 rows, 7 dot products each.  Four rows at a time: 4 x 8 partial products per lane are
+  // summed across the warp with one transposed butterfly (31 double shuffles for 28 dot products); lane
+  // 8*row+q ends with dot product q of that row and parks it in shared memory for stage 2.
+  __shared__ double s_dot[RA_THREADS / 32][32][8];
   const int32_t* crd = coords + 2 * ((size_t)i * d.N);
   for (int j0 = 0; j0 < 32; j0 += 4) {
     double2 row[4];
@@ -75,19 +77,20 @@ ba_residual_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ c
         row[jj] = *reinterpret_cast<const double2*>(Knm + (((size_t)i * d.H + r) * d.W + c) * d.M + m0);
       }
     }
+    double v[32];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-      double acc[7];
 #pragma unroll
-      for (int v = 0; v < 7; ++v) acc[v] = row[jj].x * lv[v][0] + row[jj].y * lv[v][1];
-#pragma unroll
-      for (int v = 0; v < 7; ++v) acc[v] = warp_sum(acc[v]);
-      if (lane == j0 + jj) {
-#pragma unroll
-        for (int v = 0; v < 7; ++v) mine[v] = acc[v];
-      }
+      for (int q = 0; q < 7; ++q) v[jj * 8 + q] = row[jj].x * lv[q][0] + row[jj].y * lv[q][1];
+      v[jj * 8 + 7] = 0.0;
     }
+    const double tot = warp_transpose_sum32(v);
+    s_dot[wid][j0 + (lane >> 3)][lane & 7] = tot;
   }
+  __syncwarp();
+  double mine[7];
+#pragma unroll
+  for (int q = 0; q < 7; ++q) mine[q] = s_dot[wid][lane][q];
   // ---- stage 2: lane <-> pixel
   const int n = n0 + lane;
   if (n >= d.N) return;
@@ -162,11 +165,11 @@ struct BAUnit {
 
 struct AccumSmem {
   double X[2][TP][BA_MAXM];          // predictor rows (bulk-copied), double buffered
-  double Z[TG][TP][ZW + 1];
-  double E[TG][TP][8];
-  double part[TG][TP][10];           // per (target,pixel): alpha^2, alpha r, alpha J_i[8]  (primary units)
-  double coef[TP][10];               // summed over all targets of the reference keyframe
-  double refz[TP][REF_STRIDE];
+  double refz[2][TP][REF_STRIDE];    // z_n, q_n of the tile (one bulk copy), double buffered
+  double Z[TG][TP][ZW];              // [J_i | J_j | r] of the unit's own target group
+  double E[TP][8 * TG];              // alpha * J_j, row = 8 * target + component
+  double dba[2][TP][10];             // per pixel: A = sum alpha^2, B = sum alpha r, D[8] = sum alpha J_i (parity buffered)
+  double zero[2];
   unsigned long long mbar[2];
 };
 
@@ -217,14 +220,17 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
   const int T_all = ref_ptr[i + 1] - ref_ptr[i];
   const int ntgt = un.tgt_end - un.tgt_begin;  // <= TG targets owned by this unit
   const unsigned row_bytes = (unsigned)(d.M * sizeof(double));
+  const bool primary = un.primary != 0;
 
   if (tid == 0) {
     mbar_init(&S.mbar[0], 1);
     mbar_init(&S.mbar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // zero the padding columns of X once (bulk copies only write the first M columns)
+  // zero once: padding columns of X (bulk copies only write the first M columns), both dba buffers, zero slot
   for (int t = tid; t < 2 * TP * BA_MAXM; t += AC_THREADS) (&S.X[0][0][0])[t] = 0.0;
+  for (int t = tid; t < 2 * TP * 10; t += AC_THREADS) (&S.dba[0][0][0])[t] = 0.0;
+  if (tid < 2) S.zero[tid] = 0.0;
   __syncthreads();
 
   double accG[4][4], accS[5][4], accZ[5];
@@ -238,19 +244,41 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
     for (int b = 0; b < 4; ++b) accS[a][b] = 0.0;
     accZ[a] = 0.0;
   }
+  // small-Gram outputs owned by this thread: o = tid + 256 a -> (target, row, col) of the packed 17x17 triangle
+  int zmap[5];
+#pragma unroll
+  for (int a = 0; a < 5; ++a) {
+    const int o = tid + AC_THREADS * a;
+    const int tg = o / NSMALL, idx = o % NSMALL;
+    int ra = 0, rem = idx;
+    while (rem >= ZW - ra) {
+      rem -= ZW - ra;
+      ++ra;
+    }
+    zmap[a] = (tg < ntgt) ? ((tg << 16) | (ra << 8) | (ra + rem)) : -1;
+  }
+  // the target this thread serves in the unit's first coefficient group (constant over tiles)
+  const int g_first = primary ? 0 : un.tgt_begin;
+  const int g_last = primary ? T_all : un.tgt_end;
+  const int t_first = g_first + tt;
+  const bool has_first = t_first < g_last;
+  const int pair_first = has_first ? ref_pairs[ref_ptr[i] + t_first] : 0;
 
   const int ntiles = (un.pix_end - un.pix_begin + TP - 1) / TP;
   const int32_t* crd = coords + 2 * ((size_t)i * d.N);
   auto issue_tile = [&](int tile, int buf) {
-    // one elected warp issues the row copies of a tile; lane <-> row
+    // one elected warp issues the copies of a tile; lane <-> predictor row, lane 0 also the refbuf slab
     if (tid < 32) {
-      const int n = un.pix_begin + tile * TP + tid;
+      const int nb0 = un.pix_begin + tile * TP;
+      const int n = nb0 + tid;
       const bool ok = n < un.pix_end;
-      const unsigned nrows = (unsigned)min(TP, un.pix_end - (un.pix_begin + tile * TP));
+      const unsigned nrows = (unsigned)min(TP, un.pix_end - nb0);
       if (tid == 0) {
         // order the generic-proxy reads of this buffer (previous tile) before the async-proxy writes
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&S.mbar[buf], nrows * row_bytes);
+        mbar_expect_tx(&S.mbar[buf], nrows * row_bytes + nrows * (unsigned)(REF_STRIDE * sizeof(double)));
+        bulk_g2s(&S.refz[buf][0][0], refbuf + ((size_t)i * d.N + nb0) * REF_STRIDE,
+                 nrows * (unsigned)(REF_STRIDE * sizeof(double)), &S.mbar[buf]);
       }
       __syncwarp();
       if (ok) {
@@ -259,24 +287,34 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
       }
     }
   };
-  if (ntiles > 0) issue_tile(0, 0);
+  // register prefetch of the (target, pixel) record of a tile
+  double pf_r = 0.0;
+  double2 pf_a = make_double2(0.0, 0.0), pf_b = make_double2(0.0, 0.0);
+  auto prefetch = [&](int tile) {
+    const int n = un.pix_begin + tile * TP + pl;
+    pf_r = __longlong_as_double(0x7ff8000000000000LL);
+    if (has_first && n < un.pix_end) {
+      pf_r = rbuf[(size_t)pair_first * d.N + n];
+      const double* pb = pairbuf + ((size_t)pair_first * d.N + n) * PAIR_STRIDE;
+      pf_a = *reinterpret_cast<const double2*>(pb);
+      pf_b = *reinterpret_cast<const double2*>(pb + 2);
+    }
+  };
+  if (ntiles > 0) {
+    issue_tile(0, 0);
+    prefetch(0);
+  }
 
   for (int tile = 0; tile < ntiles; ++tile) {
     const int buf = tile & 1;
     if (tile + 1 < ntiles) issue_tile(tile + 1, buf ^ 1);
     const int nb = un.pix_begin + tile * TP;
     const int npx = min(TP, un.pix_end - nb);
-    // per-pixel reference data
-    for (int t = tid; t < TP * REF_STRIDE; t += AC_THREADS) {
-      const int p = t / REF_STRIDE, q = t % REF_STRIDE;
-      S.refz[p][q] = (p < npx) ? refbuf[((size_t)i * d.N + nb + p) * REF_STRIDE + q] : 0.0;
-    }
-    __syncthreads();
+    // this tile's predictor rows + reference data have landed
+    mbar_wait(&S.mbar[buf], (tile >> 1) & 1);
 
     // ---------------- coefficient stage: (target, pixel) threads
     // primary units walk ALL targets of the keyframe (A,B,D need the sum); others only their own group
-    const int g_first = un.primary ? 0 : un.tgt_begin;
-    const int g_last = un.primary ? T_all : un.tgt_end;
     double pa2 = 0.0, par = 0.0, pD[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int g0 = g_first; g0 < g_last; g0 += TG) {
       const int t = g0 + tt;
@@ -285,12 +323,22 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
 #pragma unroll
       for (int q = 0; q < 8; ++q) Ji[q] = Jj[q] = 0.0;
       if (t < g_last && pl < npx) {
-        const int p = ref_pairs[ref_ptr[i] + t];
         const int n = nb + pl;
-        const double r = rbuf[(size_t)p * d.N + n];
+        int p;
+        double r;
+        double2 q0, q1;
+        if (g0 == g_first) {
+          p = pair_first;
+          r = pf_r;
+          q0 = pf_a;
+          q1 = pf_b;
+        } else {
+          p = ref_pairs[ref_ptr[i] + t];
+          r = rbuf[(size_t)p * d.N + n];
+          q0 = *reinterpret_cast<const double2*>(pairbuf + ((size_t)p * d.N + n) * PAIR_STRIDE);
+          q1 = *reinterpret_cast<const double2*>(pairbuf + ((size_t)p * d.N + n) * PAIR_STRIDE + 2);
+        }
         if (r == r) {
-          const double2 q0 = *reinterpret_cast<const double2*>(pairbuf + ((size_t)p * d.N + n) * PAIR_STRIDE);
-          const double2 q1 = *reinterpret_cast<const double2*>(pairbuf + ((size_t)p * d.N + n) * PAIR_STRIDE + 2);
           const double sigma = sigma_pair[p];
           const double wr = fabs(r / sigma);
           const double wgt = (wr < HUBER_KD) ? 1.0 : HUBER_KD / wr;
@@ -300,7 +348,7 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
           const double vsc = q1.y;
           const BAFrame* Fj = frames + pair_tgt[p];
           // geometry of this pixel
-          const double z = S.refz[pl][0];
+          const double z = S.refz[buf][pl][0];
           const int rr = crd[2 * n], cc = crd[2 * n + 1];
           const double Pc[3] = {z * (((double)cc - d.cx) / d.fx), z * (((double)rr - d.cy) / d.fy), z};
           double RPc[3], Pw[3], Pj[3];
@@ -320,12 +368,12 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
           double bvec[3], sk[3];
           mat3T_vec(Fi.Rwc, dIw, bvec);
           row_times_skew(bvec, Pc, sk);
-          Ji[0] = -sk[0] + alpha * S.refz[pl][1];
-          Ji[1] = -sk[1] + alpha * S.refz[pl][2];
-          Ji[2] = -sk[2] + alpha * S.refz[pl][3];
-          Ji[3] = bvec[0] + alpha * S.refz[pl][4];
-          Ji[4] = bvec[1] + alpha * S.refz[pl][5];
-          Ji[5] = bvec[2] + alpha * S.refz[pl][6];
+          Ji[0] = -sk[0] + alpha * S.refz[buf][pl][1];
+          Ji[1] = -sk[1] + alpha * S.refz[buf][pl][2];
+          Ji[2] = -sk[2] + alpha * S.refz[buf][pl][3];
+          Ji[3] = bvec[0] + alpha * S.refz[buf][pl][4];
+          Ji[4] = bvec[1] + alpha * S.refz[buf][pl][5];
+          Ji[5] = bvec[2] + alpha * S.refz[buf][pl][6];
           Ji[6] = vsc * sc;
           Ji[7] = -sc;
           // target pose: dI/dPc [Pc_j^ | -I]
@@ -349,74 +397,86 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
         for (int q = 0; q < 8; ++q) {
           S.Z[tt][pl][q] = Ji[q];
           S.Z[tt][pl][8 + q] = Jj[q];
-          S.E[tt][pl][q] = alpha * Jj[q];
+          S.E[pl][8 * tt + q] = alpha * Jj[q];
         }
         S.Z[tt][pl][16] = rs;
       }
     }
-    if (un.primary) {
-      S.part[tt][pl][0] = pa2;
-      S.part[tt][pl][1] = par;
+    if (primary) {
+      // sum over the keyframe's targets (one warp per target slot): shared-memory atomics into the parity buffer
+      double* dst = &S.dba[buf][pl][0];
+      if (pa2 != 0.0 || par != 0.0) {
+        atomicAdd(dst + 0, pa2);
+        atomicAdd(dst + 1, par);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) S.part[tt][pl][2 + q] = pD[q];
-    }
-    __syncthreads();
-    if (un.primary) {
-      for (int t = tid; t < TP * 10; t += AC_THREADS) {
-        const int p = t / 10, q = t % 10;
-        double s = 0.0;
-#pragma unroll
-        for (int g = 0; g < TG; ++g) s += S.part[g][p][q];
-        S.coef[p][q] = s;
+        for (int q = 0; q < 8; ++q) atomicAdd(dst + 2 + q, pD[q]);
       }
     }
-    // wait for this tile's predictor rows
-    mbar_wait(&S.mbar[buf], (tile >> 1) & 1);
+    // next tile's records: issued now, consumed after the product stage
+    if (tile + 1 < ntiles) prefetch(tile + 1);
     __syncthreads();
 
     // ---------------- product stage (register tiled)
-    for (int p = 0; p < npx; ++p) {
-      const double4 xb = *reinterpret_cast<const double4*>(&S.X[buf][p][4 * tx]);
-      const double b4[4] = {xb.x, xb.y, xb.z, xb.w};
-      if (un.primary) {
-        const double4 xa = *reinterpret_cast<const double4*>(&S.X[buf][p][4 * ty]);
-        const double A = S.coef[p][0];
+    // the other parity's dba buffer was last read one tile ago: clear it for the next tile's atomics
+    for (int t = tid; t < TP * 10; t += AC_THREADS) (&S.dba[buf ^ 1][0][0])[t] = 0.0;
+    // stack rows handled by this thread: row = ty + 16*a;  0..7 D, 8 B, 9 + 8*t + q -> E[.][8 t + q]
+    const double* cfp[5];
+    int cfs[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+      const int row = ty + 16 * a;
+      cfp[a] = &S.zero[0];
+      cfs[a] = 0;
+      if (row < 9) {
+        if (primary) {
+          cfp[a] = &S.dba[buf][0][row < 8 ? 2 + row : 1];
+          cfs[a] = 10;
+        }
+      } else if (row < 9 + 8 * ntgt) {
+        cfp[a] = &S.E[0][row - 9];
+        cfs[a] = 8 * TG;
+      }
+    }
+    const double* xrow = &S.X[buf][0][0];
+    if (primary) {
+      for (int p = 0; p < npx; ++p) {
+        const double4 xb = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + 4 * tx);
+        const double4 xa = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + 4 * ty);
+        const double A = S.dba[buf][p][0];
+        const double b4[4] = {xb.x, xb.y, xb.z, xb.w};
         const double a4[4] = {A * xa.x, A * xa.y, A * xa.z, A * xa.w};
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
           for (int b = 0; b < 4; ++b) accG[a][b] += a4[a] * b4[b];
-      }
-      // stack rows handled by this thread: row = ty + 16*a;  0..7 D, 8 B, 9 + 8*t + q -> E[t][q]
 #pragma unroll
-      for (int a = 0; a < 5; ++a) {
-        const int row = ty + 16 * a;
-        double cf = 0.0;
-        if (row < 9) {
-          if (un.primary) cf = (row < 8) ? S.coef[p][2 + row] : S.coef[p][1];
-        } else if (row < 9 + 8 * ntgt) {
-          cf = S.E[(row - 9) >> 3][p][(row - 9) & 7];
+        for (int a = 0; a < 5; ++a) {
+          const double cf = cfp[a][p * cfs[a]];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) accS[a][b] += cf * b4[b];
         }
+      }
+    } else {
+      for (int p = 0; p < npx; ++p) {
+        const double4 xb = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + 4 * tx);
+        const double b4[4] = {xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-        for (int b = 0; b < 4; ++b) accS[a][b] += cf * b4[b];
+        for (int a = 0; a < 5; ++a) {
+          const double cf = cfp[a][p * cfs[a]];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) accS[a][b] += cf * b4[b];
+        }
       }
     }
-    // small Grams: output o = tid + 256*a -> (target, packed index)
+    // small Grams
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
-      const int o = tid + AC_THREADS * a;
-      const int tg = o / NSMALL, idx = o % NSMALL;
-      if (tg < ntgt) {
-        // unpack idx -> (ra, rb)
-        int ra = 0, rem = idx;
-        while (rem >= ZW - ra) {
-          rem -= ZW - ra;
-          ++ra;
-        }
-        const int rbq = ra + rem;
-        double s = 0.0;
-        for (int p = 0; p < npx; ++p) s += S.Z[tg][p][ra] * S.Z[tg][p][rbq];
-        accZ[a] += s;
+      if (zmap[a] >= 0) {
+        const double* za = &S.Z[zmap[a] >> 16][0][(zmap[a] >> 8) & 0xff];
+        const double* zb = &S.Z[zmap[a] >> 16][0][zmap[a] & 0xff];
+        double sacc = 0.0;
+        for (int p = 0; p < npx; ++p) sacc += za[p * ZW] * zb[p * ZW];
+        accZ[a] += sacc;
       }
     }
     __syncthreads();
@@ -424,7 +484,7 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
 
   // ---------------- write the unit's partial sums
   double* out = partial + (size_t)blockIdx.x * PART_STRIDE;
-  if (un.primary) {
+  if (primary) {
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -440,7 +500,7 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
   for (int a = 0; a < 5; ++a) {
     const int o = tid + AC_THREADS * a;
     const int tg = o / NSMALL, idx = o % NSMALL;
-    if (tg < TG) outZ[tg * SMALL_STRIDE + idx] = (tg < ntgt) ? accZ[a] : 0.0;
+    if (tg < TG) outZ[tg * SMALL_STRIDE + idx] = (zmap[a] >= 0) ? accZ[a] : 0.0;
   }
 }
 

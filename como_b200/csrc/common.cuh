@@ -123,6 +123,23 @@ __host__ __device__ inline void chol_solve_small(double* A, double* b) {
   }
 }
 
+// Transposed butterfly: every lane holds 32 partial values v[0..31]; afterwards lane l holds the warp-wide
+// total of value index l (31 double shuffles instead of 32 x 5).
+__device__ __forceinline__ double warp_transpose_sum32(double v[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool hi = (lane & half) != 0;
+#pragma unroll
+    for (int q = 0; q < half; ++q) {
+      const double send = hi ? v[q] : v[q + half];
+      const double recv = __shfl_xor_sync(0xffffffffu, send, half);
+      v[q] = (hi ? v[q + half] : v[q]) + recv;
+    }
+  }
+  return v[0];
+}
+
 // Warp-cooperative 8x8 SPD solve (fp64): lane i < 8 owns row i of the symmetric matrix (r[0..7]) and its
 // right-hand side; returns x_i on lane i (valid for lanes 0..7).  Right-looking Cholesky with one rsqrt per
 // column instead of a sqrt + 8 divisions, substitutions through shuffles / 64 doubles of shared scratch.

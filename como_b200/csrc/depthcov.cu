@@ -139,16 +139,22 @@ __global__ void sampler_commit_kernel(SamplerState* __restrict__ st, const float
     k_ni[r] = cov_native_f32(sx[2 * r], sx[2 * r + 1], sE[4 * r], sE[4 * r + 1], sE[4 * r + 2], sE[4 * r + 3], xj[0], xj[1],
                              Ej[0], Ej[1], Ej[2], Ej[3], signal_var);
   __syncthreads();
+  // forward substitution, column oriented: thread r owns row r; every acc[r] still receives its
+  // subtractions in ascending column order (the same fp32 sequence as the row-oriented loop)
+  float* Lb = L + (size_t)b * n * n;
+  __shared__ float s_l[128];
+  const int r = threadIdx.x;
+  float acc = (r < i) ? k_ni[r] : 0.0f;
+  for (int c = 0; c < i; ++c) {
+    if (r == c) s_l[c] = acc / Lb[c * n + c];
+    __syncthreads();
+    if (r > c && r < i) acc -= Lb[r * n + c] * s_l[c];
+  }
+  __syncthreads();
+  if (r < i) Lb[i * n + r] = s_l[r];
   if (threadIdx.x == 0) {
-    float* Lb = L + (size_t)b * n * n;
     float ss = 0.0f;
-    for (int r = 0; r < i; ++r) {
-      float acc = k_ni[r];
-      for (int c = 0; c < r; ++c) acc -= Lb[r * n + c] * Lb[i * n + c];
-      const float v = acc / Lb[r * n + r];
-      Lb[i * n + r] = v;
-      ss += v * v;
-    }
+    for (int q = 0; q < i; ++q) ss += s_l[q] * s_l[q];
     float k_ii = signal_var;
     if (has_fixed) k_ii += fixed_var;
     Lb[i * n + i] = sqrtf(k_ii - ss);
@@ -469,7 +475,7 @@ extern "C" int como_b200_sampler_greedy(const float* dom_xy, const float* dom_E,
   for (int b = 0; b < B; ++b) cudaMemcpyAsync(&state[b].count, &h.count, sizeof(int), cudaMemcpyHostToDevice, st);
   cudaStreamSynchronize(st);
   for (int i = m; i < n; ++i) {
-    sampler_commit_kernel<<<B, 64, 0, st>>>(state, dom_xy, dom_E, d, sel_xy, sel_E, (long long*)sel_idx, L, n, signal_var,
+    sampler_commit_kernel<<<B, 128, 0, st>>>(state, dom_xy, dom_E, d, sel_xy, sel_E, (long long*)sel_idx, L, n, signal_var,
                                             fixed_var, has_fixed, max_stdev_thresh, terminate_early);
     sampler_domain_kernel<<<dim3(nblk, B), SB_THREADS, 0, st>>>(state, dom_xy, dom_E, d, sel_xy, sel_E, L, n, obs_info, var,
                                                                 dist_ok, signal_var, dist_thresh * dist_thresh, cand_val,
