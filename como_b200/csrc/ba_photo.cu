@@ -150,7 +150,8 @@ ba_residual_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ c
 }
 
 // ================================================================================================ pass B
-constexpr int AC_THREADS = 256;
+constexpr int AC_THREADS = 512;      // warps 0-7: product role, warps 8-15: coefficient role
+constexpr int AC_ROLE = 256;
 constexpr int TP = 32;               // pixels per tile
 constexpr int TG = 8;                // targets per group
 constexpr int ZW = 17;               // [J_i(8) | J_j(8) | r]
@@ -165,12 +166,12 @@ struct BAUnit {
 
 struct AccumSmem {
   double X[2][TP][BA_MAXM];          // predictor rows (bulk-copied), double buffered
-  double refz[2][TP][REF_STRIDE];    // z_n, q_n of the tile (one bulk copy), double buffered
-  double Z[TG][TP][ZW];              // [J_i | J_j | r] of the unit's own target group
-  double E[TP][8 * TG];              // alpha * J_j, row = 8 * target + component
-  double dba[2][TP][10];             // per pixel: A = sum alpha^2, B = sum alpha r, D[8] = sum alpha J_i (parity buffered)
+  double refz[2][TP][REF_STRIDE];    // z_n, q_n of a tile (one bulk copy), double buffered, one tile ahead of X
+  double Z[2][TG][TP][ZW];           // [J_i | J_j | r] of the unit's own target group
+  double E[2][TP][8 * TG];           // alpha * J_j, row = 8 * target + component
+  double dba[2][TP][10];             // per pixel: A = sum alpha^2, B = sum alpha r, D[8] = sum alpha J_i
   double zero[2];
-  unsigned long long mbar[2];
+  unsigned long long mbarX[2], mbarR[2];
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -202,7 +203,9 @@ __device__ __forceinline__ int tri_index(int a, int b) {  // a <= b < 17 -> inde
   return a * ZW - (a * (a - 1)) / 2 + (b - a);
 }
 
-__global__ void __launch_bounds__(AC_THREADS, 2)
+// Warp-specialised: the coefficient warps (8-15) rebuild the per-(target,pixel) Jacobians of tile t+1 while
+// the product warps (0-7) run the register-tiled products of tile t; one CTA-wide barrier per tile.
+__global__ void __launch_bounds__(AC_THREADS, 1)
 ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coords, const double* __restrict__ scaf,
                 const BAFrame* __restrict__ frames, const int32_t* __restrict__ ref_ptr,
                 const int32_t* __restrict__ ref_pairs, const int32_t* __restrict__ pair_tgt,
@@ -214,25 +217,203 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
   const BAUnit un = units[blockIdx.x];
   const int i = un.ref;
   const int tid = threadIdx.x;
-  const int ty = tid >> 4, tx = tid & 15;   // 16 x 16 register tiling of the 64 x 64 / 80 x 64 outputs
-  const int tt = tid >> 5, pl = tid & 31;   // (target in group, pixel in tile) for the coefficient stage
-  const BAFrame Fi = frames[i];
+  const bool is_coef = tid >= AC_ROLE;
+  const int rt = tid & (AC_ROLE - 1);        // role-local thread id
   const int T_all = ref_ptr[i + 1] - ref_ptr[i];
   const int ntgt = un.tgt_end - un.tgt_begin;  // <= TG targets owned by this unit
   const unsigned row_bytes = (unsigned)(d.M * sizeof(double));
   const bool primary = un.primary != 0;
+  const int ntiles = (un.pix_end - un.pix_begin + TP - 1) / TP;
+  const int32_t* crd = coords + 2 * ((size_t)i * d.N);
 
   if (tid == 0) {
-    mbar_init(&S.mbar[0], 1);
-    mbar_init(&S.mbar[1], 1);
+    mbar_init(&S.mbarX[0], 1);
+    mbar_init(&S.mbarX[1], 1);
+    mbar_init(&S.mbarR[0], 1);
+    mbar_init(&S.mbarR[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // zero once: padding columns of X (bulk copies only write the first M columns), both dba buffers, zero slot
+  // zero once: padding columns of X (bulk copies only write the first M columns), dba, the zero slot
   for (int t = tid; t < 2 * TP * BA_MAXM; t += AC_THREADS) (&S.X[0][0][0])[t] = 0.0;
   for (int t = tid; t < 2 * TP * 10; t += AC_THREADS) (&S.dba[0][0][0])[t] = 0.0;
   if (tid < 2) S.zero[tid] = 0.0;
   __syncthreads();
 
+  auto issue_X = [&](int tile, int buf) {      // called by warp 0 (product role): lane <-> predictor row
+    const int nb0 = un.pix_begin + tile * TP;
+    const int n = nb0 + tid;
+    const unsigned nrows = (unsigned)min(TP, un.pix_end - nb0);
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&S.mbarX[buf], nrows * row_bytes);
+    }
+    __syncwarp();
+    if (n < un.pix_end) {
+      const int r = crd[2 * n], c = crd[2 * n + 1];
+      bulk_g2s(&S.X[buf][tid][0], Knm + (((size_t)i * d.H + r) * d.W + c) * d.M, row_bytes, &S.mbarX[buf]);
+    }
+  };
+  auto issue_R = [&](int tile, int buf) {      // called by one thread of the coefficient role
+    const int nb0 = un.pix_begin + tile * TP;
+    const unsigned bytes = (unsigned)min(TP, un.pix_end - nb0) * (unsigned)(REF_STRIDE * sizeof(double));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&S.mbarR[buf], bytes);
+    bulk_g2s(&S.refz[buf][0][0], refbuf + ((size_t)i * d.N + nb0) * REF_STRIDE, bytes, &S.mbarR[buf]);
+  };
+
+  if (is_coef) {
+    // ================================================================ coefficient role
+    const int tt = rt >> 5, pl = rt & 31;      // (target slot, pixel in tile)
+    const BAFrame Fi = frames[i];
+    const int g_first = primary ? 0 : un.tgt_begin;
+    const int g_last = primary ? T_all : un.tgt_end;
+    const int t_first = g_first + tt;
+    const bool has_first = t_first < g_last;
+    const int pair_first = has_first ? ref_pairs[ref_ptr[i] + t_first] : 0;
+    const BAFrame* Fj_first = frames + (has_first ? pair_tgt[pair_first] : 0);
+    const double sigma_first = has_first ? sigma_pair[pair_first] : 1.0;
+    double pf_r = 0.0;
+    double2 pf_a = make_double2(0.0, 0.0), pf_b = make_double2(0.0, 0.0);
+    auto prefetch = [&](int tile) {
+      const int n = un.pix_begin + tile * TP + pl;
+      pf_r = __longlong_as_double(0x7ff8000000000000LL);
+      if (has_first && n < un.pix_end) {
+        pf_r = rbuf[(size_t)pair_first * d.N + n];
+        const double* pb = pairbuf + ((size_t)pair_first * d.N + n) * PAIR_STRIDE;
+        pf_a = *reinterpret_cast<const double2*>(pb);
+        pf_b = *reinterpret_cast<const double2*>(pb + 2);
+      }
+    };
+    // builds Z/E/dba of `tile` into buffer `buf`
+    auto build = [&](int tile, int buf) {
+      const int nb = un.pix_begin + tile * TP;
+      const int npx = min(TP, un.pix_end - nb);
+      double pa2 = 0.0, par = 0.0, pD[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int g0 = g_first; g0 < g_last; g0 += TG) {
+        const int t = g0 + tt;
+        const bool own_group = (g0 == un.tgt_begin);
+        double Ji[8], Jj[8], rs = 0.0, alpha = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) Ji[q] = Jj[q] = 0.0;
+        if (t < g_last && pl < npx) {
+          const int n = nb + pl;
+          double r, sigma;
+          double2 q0, q1;
+          const BAFrame* Fj;
+          if (g0 == g_first) {
+            r = pf_r;
+            q0 = pf_a;
+            q1 = pf_b;
+            Fj = Fj_first;
+            sigma = sigma_first;
+          } else {
+            const int p = ref_pairs[ref_ptr[i] + t];
+            r = rbuf[(size_t)p * d.N + n];
+            q0 = *reinterpret_cast<const double2*>(pairbuf + ((size_t)p * d.N + n) * PAIR_STRIDE);
+            q1 = *reinterpret_cast<const double2*>(pairbuf + ((size_t)p * d.N + n) * PAIR_STRIDE + 2);
+            Fj = frames + pair_tgt[p];
+            sigma = sigma_pair[p];
+          }
+          if (r == r) {
+            const double wr = fabs(r / sigma);
+            const double wgt = (wr < HUBER_KD) ? 1.0 : HUBER_KD / wr;
+            const double sc = sqrt(wgt) / sigma;
+            rs = r * sc;
+            const double dIs[3] = {q0.x * sc, q0.y * sc, q1.x * sc};
+            const double vsc = q1.y;
+            const double z = S.refz[buf][pl][0];
+            const int rr = crd[2 * n], cc = crd[2 * n + 1];
+            const double Pc[3] = {z * (((double)cc - d.cx) / d.fx), z * (((double)rr - d.cy) / d.fy), z};
+            double RPc[3], Pw[3], Pj[3];
+            mat3_vec(Fi.Rwc, Pc, RPc);
+            Pw[0] = RPc[0] + Fi.twc[0];
+            Pw[1] = RPc[1] + Fi.twc[1];
+            Pw[2] = RPc[2] + Fi.twc[2];
+            mat3_vec(Fj->Rcw, Pw, Pj);
+            Pj[0] += Fj->tcw[0];
+            Pj[1] += Fj->tcw[1];
+            Pj[2] += Fj->tcw[2];
+            double dIw[3];
+            mat3T_vec(Fj->Rcw, dIs, dIw);                       // dI/dPw = dI/dPc R_cw,j (row vector)
+            alpha = dIw[0] * RPc[0] + dIw[1] * RPc[1] + dIw[2] * RPc[2];
+            double bvec[3], sk[3];
+            mat3T_vec(Fi.Rwc, dIw, bvec);                       // reference pose: dI/dPw [-R Pc^ | R] + alpha q^T
+            row_times_skew(bvec, Pc, sk);
+            Ji[0] = -sk[0] + alpha * S.refz[buf][pl][1];
+            Ji[1] = -sk[1] + alpha * S.refz[buf][pl][2];
+            Ji[2] = -sk[2] + alpha * S.refz[buf][pl][3];
+            Ji[3] = bvec[0] + alpha * S.refz[buf][pl][4];
+            Ji[4] = bvec[1] + alpha * S.refz[buf][pl][5];
+            Ji[5] = bvec[2] + alpha * S.refz[buf][pl][6];
+            Ji[6] = vsc * sc;
+            Ji[7] = -sc;
+            row_times_skew(dIs, Pj, sk);                        // target pose: dI/dPc [Pc_j^ | -I]
+            Jj[0] = sk[0];
+            Jj[1] = sk[1];
+            Jj[2] = sk[2];
+            Jj[3] = -dIs[0];
+            Jj[4] = -dIs[1];
+            Jj[5] = -dIs[2];
+            Jj[6] = -Ji[6];
+            Jj[7] = -Ji[7];
+          }
+        }
+        pa2 += alpha * alpha;
+        par += alpha * rs;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pD[q] += alpha * Ji[q];
+        if (own_group) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            S.Z[buf][tt][pl][q] = Ji[q];
+            S.Z[buf][tt][pl][8 + q] = Jj[q];
+            S.E[buf][pl][8 * tt + q] = alpha * Jj[q];
+          }
+          S.Z[buf][tt][pl][16] = rs;
+        }
+      }
+      if (primary && (pa2 != 0.0 || par != 0.0)) {
+        double* dst = &S.dba[buf][pl][0];
+        atomicAdd(dst + 0, pa2);
+        atomicAdd(dst + 1, par);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) atomicAdd(dst + 2 + q, pD[q]);
+      }
+    };
+
+    if (ntiles > 0) {
+      if (rt == 0) {
+        issue_R(0, 0);
+        if (ntiles > 1) issue_R(1, 1);
+      }
+      prefetch(0);
+      mbar_wait(&S.mbarR[0], 0);
+      build(0, 0);
+      if (ntiles > 1) prefetch(1);
+    }
+    __syncthreads();
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int buf = tile & 1;
+      if (tile + 1 < ntiles) {
+        // dba[buf^1] was consumed by the product role during the previous iteration
+        for (int t = rt; t < TP * 10; t += AC_ROLE) (&S.dba[buf ^ 1][0][0])[t] = 0.0;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_wait(&S.mbarR[buf ^ 1], ((tile + 1) >> 1) & 1);
+        build(tile + 1, buf ^ 1);
+        // refz[buf] (tile) is free now for tile + 2; its copy overlaps the next iteration
+        if (tile + 2 < ntiles) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");   // all coefficient threads are done reading refz[buf]... see note
+          if (rt == 0) issue_R(tile + 2, buf);
+          prefetch(tile + 2);
+        }
+      }
+      __syncthreads();
+    }
+    return;
+  }
+
+  // ================================================================== product role
+  const int ty = rt >> 4, tx = rt & 15;       // 16 x 16 register tiling of the 64 x 64 / 80 x 64 outputs
   double accG[4][4], accS[5][4], accZ[5];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -244,11 +425,11 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
     for (int b = 0; b < 4; ++b) accS[a][b] = 0.0;
     accZ[a] = 0.0;
   }
-  // small-Gram outputs owned by this thread: o = tid + 256 a -> (target, row, col) of the packed 17x17 triangle
+  // small-Gram outputs owned by this thread: o = rt + 256 a -> (target, row, col) of the packed 17x17 triangle
   int zmap[5];
 #pragma unroll
   for (int a = 0; a < 5; ++a) {
-    const int o = tid + AC_THREADS * a;
+    const int o = rt + AC_ROLE * a;
     const int tg = o / NSMALL, idx = o % NSMALL;
     int ra = 0, rem = idx;
     while (rem >= ZW - ra) {
@@ -257,168 +438,14 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
     }
     zmap[a] = (tg < ntgt) ? ((tg << 16) | (ra << 8) | (ra + rem)) : -1;
   }
-  // the target this thread serves in the unit's first coefficient group (constant over tiles)
-  const int g_first = primary ? 0 : un.tgt_begin;
-  const int g_last = primary ? T_all : un.tgt_end;
-  const int t_first = g_first + tt;
-  const bool has_first = t_first < g_last;
-  const int pair_first = has_first ? ref_pairs[ref_ptr[i] + t_first] : 0;
-
-  const int ntiles = (un.pix_end - un.pix_begin + TP - 1) / TP;
-  const int32_t* crd = coords + 2 * ((size_t)i * d.N);
-  auto issue_tile = [&](int tile, int buf) {
-    // one elected warp issues the copies of a tile; lane <-> predictor row, lane 0 also the refbuf slab
-    if (tid < 32) {
-      const int nb0 = un.pix_begin + tile * TP;
-      const int n = nb0 + tid;
-      const bool ok = n < un.pix_end;
-      const unsigned nrows = (unsigned)min(TP, un.pix_end - nb0);
-      if (tid == 0) {
-        // order the generic-proxy reads of this buffer (previous tile) before the async-proxy writes
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&S.mbar[buf], nrows * row_bytes + nrows * (unsigned)(REF_STRIDE * sizeof(double)));
-        bulk_g2s(&S.refz[buf][0][0], refbuf + ((size_t)i * d.N + nb0) * REF_STRIDE,
-                 nrows * (unsigned)(REF_STRIDE * sizeof(double)), &S.mbar[buf]);
-      }
-      __syncwarp();
-      if (ok) {
-        const int r = crd[2 * n], c = crd[2 * n + 1];
-        bulk_g2s(&S.X[buf][tid][0], Knm + (((size_t)i * d.H + r) * d.W + c) * d.M, row_bytes, &S.mbar[buf]);
-      }
-    }
-  };
-  // register prefetch of the (target, pixel) record of a tile
-  double pf_r = 0.0;
-  double2 pf_a = make_double2(0.0, 0.0), pf_b = make_double2(0.0, 0.0);
-  auto prefetch = [&](int tile) {
-    const int n = un.pix_begin + tile * TP + pl;
-    pf_r = __longlong_as_double(0x7ff8000000000000LL);
-    if (has_first && n < un.pix_end) {
-      pf_r = rbuf[(size_t)pair_first * d.N + n];
-      const double* pb = pairbuf + ((size_t)pair_first * d.N + n) * PAIR_STRIDE;
-      pf_a = *reinterpret_cast<const double2*>(pb);
-      pf_b = *reinterpret_cast<const double2*>(pb + 2);
-    }
-  };
-  if (ntiles > 0) {
-    issue_tile(0, 0);
-    prefetch(0);
-  }
-
+  if (ntiles > 0 && tid < 32) issue_X(0, 0);
+  __syncthreads();   // pairs with the coefficient role's prologue barrier
   for (int tile = 0; tile < ntiles; ++tile) {
     const int buf = tile & 1;
-    if (tile + 1 < ntiles) issue_tile(tile + 1, buf ^ 1);
+    if (tile + 1 < ntiles && tid < 32) issue_X(tile + 1, buf ^ 1);
     const int nb = un.pix_begin + tile * TP;
     const int npx = min(TP, un.pix_end - nb);
-    // this tile's predictor rows + reference data have landed
-    mbar_wait(&S.mbar[buf], (tile >> 1) & 1);
-
-    // ---------------- coefficient stage: (target, pixel) threads
-    // primary units walk ALL targets of the keyframe (A,B,D need the sum); others only their own group
-    double pa2 = 0.0, par = 0.0, pD[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int g0 = g_first; g0 < g_last; g0 += TG) {
-      const int t = g0 + tt;
-      const bool own_group = (g0 == un.tgt_begin);
-      double Ji[8], Jj[8], rs = 0.0, alpha = 0.0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) Ji[q] = Jj[q] = 0.0;
-      if (t < g_last && pl < npx) {
-        const int n = nb + pl;
-        int p;
-        double r;
-        double2 q0, q1;
-        if (g0 == g_first) {
-          p = pair_first;
-          r = pf_r;
-          q0 = pf_a;
-          q1 = pf_b;
-        } else {
-          p = ref_pairs[ref_ptr[i] + t];
-          r = rbuf[(size_t)p * d.N + n];
-          q0 = *reinterpret_cast<const double2*>(pairbuf + ((size_t)p * d.N + n) * PAIR_STRIDE);
-          q1 = *reinterpret_cast<const double2*>(pairbuf + ((size_t)p * d.N + n) * PAIR_STRIDE + 2);
-        }
-        if (r == r) {
-          const double sigma = sigma_pair[p];
-          const double wr = fabs(r / sigma);
-          const double wgt = (wr < HUBER_KD) ? 1.0 : HUBER_KD / wr;
-          const double sc = sqrt(wgt) / sigma;
-          rs = r * sc;
-          const double dIs[3] = {q0.x * sc, q0.y * sc, q1.x * sc};
-          const double vsc = q1.y;
-          const BAFrame* Fj = frames + pair_tgt[p];
-          // geometry of this pixel
-          const double z = S.refz[buf][pl][0];
-          const int rr = crd[2 * n], cc = crd[2 * n + 1];
-          const double Pc[3] = {z * (((double)cc - d.cx) / d.fx), z * (((double)rr - d.cy) / d.fy), z};
-          double RPc[3], Pw[3], Pj[3];
-          mat3_vec(Fi.Rwc, Pc, RPc);
-          Pw[0] = RPc[0] + Fi.twc[0];
-          Pw[1] = RPc[1] + Fi.twc[1];
-          Pw[2] = RPc[2] + Fi.twc[2];
-          mat3_vec(Fj->Rcw, Pw, Pj);
-          Pj[0] += Fj->tcw[0];
-          Pj[1] += Fj->tcw[1];
-          Pj[2] += Fj->tcw[2];
-          // dI/dPw = dI/dPc R_cw,j   (row vector)
-          double dIw[3];
-          mat3T_vec(Fj->Rcw, dIs, dIw);
-          alpha = dIw[0] * RPc[0] + dIw[1] * RPc[1] + dIw[2] * RPc[2];
-          // reference pose: dI/dPw [-R Pc^ | R] + alpha q^T ;   b = dIw R_wc,i (row vector)
-          double bvec[3], sk[3];
-          mat3T_vec(Fi.Rwc, dIw, bvec);
-          row_times_skew(bvec, Pc, sk);
-          Ji[0] = -sk[0] + alpha * S.refz[buf][pl][1];
-          Ji[1] = -sk[1] + alpha * S.refz[buf][pl][2];
-          Ji[2] = -sk[2] + alpha * S.refz[buf][pl][3];
-          Ji[3] = bvec[0] + alpha * S.refz[buf][pl][4];
-          Ji[4] = bvec[1] + alpha * S.refz[buf][pl][5];
-          Ji[5] = bvec[2] + alpha * S.refz[buf][pl][6];
-          Ji[6] = vsc * sc;
-          Ji[7] = -sc;
-          // target pose: dI/dPc [Pc_j^ | -I]
-          row_times_skew(dIs, Pj, sk);
-          Jj[0] = sk[0];
-          Jj[1] = sk[1];
-          Jj[2] = sk[2];
-          Jj[3] = -dIs[0];
-          Jj[4] = -dIs[1];
-          Jj[5] = -dIs[2];
-          Jj[6] = -Ji[6];
-          Jj[7] = -Ji[7];
-        }
-      }
-      pa2 += alpha * alpha;
-      par += alpha * rs;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) pD[q] += alpha * Ji[q];
-      if (own_group) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          S.Z[tt][pl][q] = Ji[q];
-          S.Z[tt][pl][8 + q] = Jj[q];
-          S.E[pl][8 * tt + q] = alpha * Jj[q];
-        }
-        S.Z[tt][pl][16] = rs;
-      }
-    }
-    if (primary) {
-      // sum over the keyframe's targets (one warp per target slot): shared-memory atomics into the parity buffer
-      double* dst = &S.dba[buf][pl][0];
-      if (pa2 != 0.0 || par != 0.0) {
-        atomicAdd(dst + 0, pa2);
-        atomicAdd(dst + 1, par);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) atomicAdd(dst + 2 + q, pD[q]);
-      }
-    }
-    // next tile's records: issued now, consumed after the product stage
-    if (tile + 1 < ntiles) prefetch(tile + 1);
-    __syncthreads();
-
-    // ---------------- product stage (register tiled)
-    // the other parity's dba buffer was last read one tile ago: clear it for the next tile's atomics
-    for (int t = tid; t < TP * 10; t += AC_THREADS) (&S.dba[buf ^ 1][0][0])[t] = 0.0;
+    mbar_wait(&S.mbarX[buf], (tile >> 1) & 1);
     // stack rows handled by this thread: row = ty + 16*a;  0..7 D, 8 B, 9 + 8*t + q -> E[.][8 t + q]
     const double* cfp[5];
     int cfs[5];
@@ -433,12 +460,13 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
           cfs[a] = 10;
         }
       } else if (row < 9 + 8 * ntgt) {
-        cfp[a] = &S.E[0][row - 9];
+        cfp[a] = &S.E[buf][0][row - 9];
         cfs[a] = 8 * TG;
       }
     }
     const double* xrow = &S.X[buf][0][0];
     if (primary) {
+#pragma unroll 2
       for (int p = 0; p < npx; ++p) {
         const double4 xb = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + 4 * tx);
         const double4 xa = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + 4 * ty);
@@ -457,6 +485,7 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
         }
       }
     } else {
+#pragma unroll 2
       for (int p = 0; p < npx; ++p) {
         const double4 xb = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + 4 * tx);
         const double b4[4] = {xb.x, xb.y, xb.z, xb.w};
@@ -472,9 +501,10 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
       if (zmap[a] >= 0) {
-        const double* za = &S.Z[zmap[a] >> 16][0][(zmap[a] >> 8) & 0xff];
-        const double* zb = &S.Z[zmap[a] >> 16][0][zmap[a] & 0xff];
+        const double* za = &S.Z[buf][zmap[a] >> 16][0][(zmap[a] >> 8) & 0xff];
+        const double* zb = &S.Z[buf][zmap[a] >> 16][0][zmap[a] & 0xff];
         double sacc = 0.0;
+#pragma unroll 4
         for (int p = 0; p < npx; ++p) sacc += za[p * ZW] * zb[p * ZW];
         accZ[a] += sacc;
       }
@@ -498,7 +528,7 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
   double* outZ = outS + STACK_ROWS * BA_MAXM;
 #pragma unroll
   for (int a = 0; a < 5; ++a) {
-    const int o = tid + AC_THREADS * a;
+    const int o = rt + AC_ROLE * a;
     const int tg = o / NSMALL, idx = o % NSMALL;
     if (tg < TG) outZ[tg * SMALL_STRIDE + idx] = (zmap[a] >= 0) ? accZ[a] : 0.0;
   }
