@@ -150,14 +150,15 @@ ba_residual_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ c
 }
 
 // ================================================================================================ pass B
-constexpr int AC_THREADS = 512;      // warps 0-7: product role, warps 8-15: coefficient role
+constexpr int AC_THREADS = 384;      // warps 0-7: product role (256 threads), warps 8-11: coefficient role (128)
 constexpr int AC_ROLE = 256;
+constexpr int AC_COEF = AC_THREADS - AC_ROLE;
 constexpr int TP = 32;               // pixels per tile
-constexpr int TG = 8;                // targets per group
+constexpr int TG = 4;                // targets per group (one coefficient warp each)
 constexpr int ZW = 17;               // [J_i(8) | J_j(8) | r]
 constexpr int NSMALL = 153;          // upper triangle of the 17x17 Gram
 constexpr int SMALL_STRIDE = 160;
-constexpr int STACK_ROWS = 80;       // 8 (D) + 1 (B) + 8*TG (E) = 73, padded to 5 x 16
+constexpr int STACK_ROWS = 48;       // 8 (D) + 1 (B) + 8*TG (E) = 41, padded
 constexpr int PART_STRIDE = BA_MAXM * BA_MAXM + STACK_ROWS * BA_MAXM + TG * SMALL_STRIDE;  // doubles per unit
 
 struct BAUnit {
@@ -396,14 +397,13 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
       const int buf = tile & 1;
       if (tile + 1 < ntiles) {
         // dba[buf^1] was consumed by the product role during the previous iteration
-        for (int t = rt; t < TP * 10; t += AC_ROLE) (&S.dba[buf ^ 1][0][0])[t] = 0.0;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int t = rt; t < TP * 10; t += AC_COEF) (&S.dba[buf ^ 1][0][0])[t] = 0.0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait(&S.mbarR[buf ^ 1], ((tile + 1) >> 1) & 1);
         build(tile + 1, buf ^ 1);
         // refz[buf] (tile) is free now for tile + 2; its copy overlaps the next iteration
         if (tile + 2 < ntiles) {
-          asm volatile("bar.sync 1, 256;" ::: "memory");   // all coefficient threads are done reading refz[buf]... see note
-          if (rt == 0) issue_R(tile + 2, buf);
+          if (rt == 0) issue_R(tile + 2, buf);   // refz[buf] (tile) was last read during the previous iteration
           prefetch(tile + 2);
         }
       }
@@ -413,22 +413,44 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
   }
 
   // ================================================================== product role
-  const int ty = rt >> 4, tx = rt & 15;       // 16 x 16 register tiling of the 64 x 64 / 80 x 64 outputs
-  double accG[4][4], accS[5][4], accZ[5];
+  // 256 threads.  G = sum_p A_p x_p x_p^T is symmetric: only its 136 upper-triangular 4x4 blocks are formed
+  // (threads 0..135, mirrored on write-out).  The other 120 threads share the stack rows that are actually
+  // live (9 + 8 * ntgt of 80): item = (row, group of 4 columns), dealt round-robin.
+  constexpr int NGT = 136;                  // G-tile threads
+  constexpr int NST = AC_ROLE - NGT;        // stack threads (120)
+  constexpr int MAXIT = 6;                  // ceil((9 + 8 TG) * 16 / 120)
+  const bool g_thread = rt < NGT;
+  int bi = 0, bj = 0;
+  if (g_thread) {                           // rt -> (bi <= bj) in the 16 x 16 block grid
+    int rem = rt;
+    while (rem >= 16 - bi) {
+      rem -= 16 - bi;
+      ++bi;
+    }
+    bj = bi + rem;
+  }
+  const int live_rows = (primary ? 9 : 0) + 0;   // rows 0..8 only carry data in primary units
+  const int row_lo = primary ? 0 : 9;            // first live stack row
+  const int row_hi = 9 + 8 * ntgt;               // one past the last live stack row
+  (void)live_rows;
+  const int nitems = (row_hi - row_lo) * 16;
+  const int nit = g_thread ? 0 : (nitems - (rt - NGT) + NST - 1) / NST;   // items of this stack thread
+  constexpr int NZ = (TG * NSMALL + AC_ROLE - 1) / AC_ROLE;   // small-Gram outputs per thread (3)
+  double accG[4][4], accS[MAXIT][4], accZ[NZ];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) accG[a][b] = 0.0;
 #pragma unroll
-  for (int a = 0; a < 5; ++a) {
+  for (int a = 0; a < MAXIT; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) accS[a][b] = 0.0;
-    accZ[a] = 0.0;
-  }
-  // small-Gram outputs owned by this thread: o = rt + 256 a -> (target, row, col) of the packed 17x17 triangle
-  int zmap[5];
 #pragma unroll
-  for (int a = 0; a < 5; ++a) {
+  for (int a = 0; a < NZ; ++a) accZ[a] = 0.0;
+  // small-Gram outputs owned by this thread: o = rt + 256 a -> (target, row, col) of the packed 17x17 triangle
+  int zmap[NZ];
+#pragma unroll
+  for (int a = 0; a < NZ; ++a) {
     const int o = rt + AC_ROLE * a;
     const int tg = o / NSMALL, idx = o % NSMALL;
     int ra = 0, rem = idx;
@@ -446,60 +468,61 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
     const int nb = un.pix_begin + tile * TP;
     const int npx = min(TP, un.pix_end - nb);
     mbar_wait(&S.mbarX[buf], (tile >> 1) & 1);
-    // stack rows handled by this thread: row = ty + 16*a;  0..7 D, 8 B, 9 + 8*t + q -> E[.][8 t + q]
-    const double* cfp[5];
-    int cfs[5];
-#pragma unroll
-    for (int a = 0; a < 5; ++a) {
-      const int row = ty + 16 * a;
-      cfp[a] = &S.zero[0];
-      cfs[a] = 0;
-      if (row < 9) {
-        if (primary) {
-          cfp[a] = &S.dba[buf][0][row < 8 ? 2 + row : 1];
-          cfs[a] = 10;
-        }
-      } else if (row < 9 + 8 * ntgt) {
-        cfp[a] = &S.E[buf][0][row - 9];
-        cfs[a] = 8 * TG;
-      }
-    }
     const double* xrow = &S.X[buf][0][0];
-    if (primary) {
-#pragma unroll 2
-      for (int p = 0; p < npx; ++p) {
-        const double4 xb = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + 4 * tx);
-        const double4 xa = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + 4 * ty);
-        const double A = S.dba[buf][p][0];
-        const double b4[4] = {xb.x, xb.y, xb.z, xb.w};
-        const double a4[4] = {A * xa.x, A * xa.y, A * xa.z, A * xa.w};
+    if (g_thread) {
+      if (primary) {
+#pragma unroll 4
+        for (int p = 0; p < npx; ++p) {
+          const double4 xb = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + 4 * bj);
+          const double4 xa = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + 4 * bi);
+          const double A = S.dba[buf][p][0];
+          const double b4[4] = {xb.x, xb.y, xb.z, xb.w};
+          const double a4[4] = {A * xa.x, A * xa.y, A * xa.z, A * xa.w};
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+          for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) accG[a][b] += a4[a] * b4[b];
-#pragma unroll
-        for (int a = 0; a < 5; ++a) {
-          const double cf = cfp[a][p * cfs[a]];
-#pragma unroll
-          for (int b = 0; b < 4; ++b) accS[a][b] += cf * b4[b];
+            for (int b = 0; b < 4; ++b) accG[a][b] += a4[a] * b4[b];
         }
       }
     } else {
+      // per item: coefficient pointer / pixel stride and the column group
+      const double* cfp[MAXIT];
+      int cfs[MAXIT], col[MAXIT];
+#pragma unroll
+      for (int a = 0; a < MAXIT; ++a) {
+        const int item = (rt - NGT) + a * NST;
+        const int row = row_lo + item / 16;
+        col[a] = 4 * (item % 16);
+        cfp[a] = &S.zero[0];
+        cfs[a] = 0;
+        if (a < nit) {
+          if (row < 9) {
+            cfp[a] = &S.dba[buf][0][row < 8 ? 2 + row : 1];
+            cfs[a] = 10;
+          } else {
+            cfp[a] = &S.E[buf][0][row - 9];
+            cfs[a] = 8 * TG;
+          }
+        }
+      }
 #pragma unroll 2
       for (int p = 0; p < npx; ++p) {
-        const double4 xb = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + 4 * tx);
-        const double b4[4] = {xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-        for (int a = 0; a < 5; ++a) {
-          const double cf = cfp[a][p * cfs[a]];
-#pragma unroll
-          for (int b = 0; b < 4; ++b) accS[a][b] += cf * b4[b];
+        for (int a = 0; a < MAXIT; ++a) {
+          if (a < nit) {
+            const double cf = cfp[a][p * cfs[a]];
+            const double4 xb = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + col[a]);
+            accS[a][0] += cf * xb.x;
+            accS[a][1] += cf * xb.y;
+            accS[a][2] += cf * xb.z;
+            accS[a][3] += cf * xb.w;
+          }
         }
       }
     }
     // small Grams
 #pragma unroll
-    for (int a = 0; a < 5; ++a) {
+    for (int a = 0; a < NZ; ++a) {
       if (zmap[a] >= 0) {
         const double* za = &S.Z[buf][zmap[a] >> 16][0][(zmap[a] >> 8) & 0xff];
         const double* zb = &S.Z[buf][zmap[a] >> 16][0][zmap[a] & 0xff];
@@ -512,22 +535,38 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
     __syncthreads();
   }
 
-  // ---------------- write the unit's partial sums
+  // ---------------- write the unit's partial sums (the scatter kernels read full G / all stack rows)
   double* out = partial + (size_t)blockIdx.x * PART_STRIDE;
-  if (primary) {
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) out[(4 * ty + a) * BA_MAXM + 4 * tx + b] = accG[a][b];
-  }
   double* outS = out + BA_MAXM * BA_MAXM;
+  if (g_thread) {
+    if (primary) {
 #pragma unroll
-  for (int a = 0; a < 5; ++a)
+      for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) outS[(ty + 16 * a) * BA_MAXM + 4 * tx + b] = accS[a][b];
+        for (int b = 0; b < 4; ++b) {
+          out[(4 * bi + a) * BA_MAXM + 4 * bj + b] = accG[a][b];
+          out[(4 * bj + b) * BA_MAXM + 4 * bi + a] = accG[a][b];
+        }
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < MAXIT; ++a) {
+      if (a < nit) {
+        const int item = (rt - NGT) + a * NST;
+        const int row = row_lo + item / 16, c0 = 4 * (item % 16);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) outS[row * BA_MAXM + c0 + b] = accS[a][b];
+      }
+    }
+  }
+  // stack rows that are not live in this unit are defined as zero
+  for (int t = rt; t < STACK_ROWS * BA_MAXM; t += AC_ROLE) {
+    const int row = t / BA_MAXM;
+    if (row < row_lo || row >= row_hi) outS[t] = 0.0;
+  }
   double* outZ = outS + STACK_ROWS * BA_MAXM;
 #pragma unroll
-  for (int a = 0; a < 5; ++a) {
+  for (int a = 0; a < NZ; ++a) {
     const int o = rt + AC_ROLE * a;
     const int tg = o / NSMALL, idx = o % NSMALL;
     if (tg < TG) outZ[tg * SMALL_STRIDE + idx] = (zmap[a] >= 0) ? accZ[a] : 0.0;
