@@ -161,6 +161,9 @@ constexpr int SMALL_STRIDE = 160;
 constexpr int STACK_ROWS = 48;       // 8 (D) + 1 (B) + 8*TG (E) = 41, padded
 constexpr int PART_STRIDE = BA_MAXM * BA_MAXM + STACK_ROWS * BA_MAXM + TG * SMALL_STRIDE;  // doubles per unit
 
+constexpr int EPITCH = 8 * TG + 1;
+constexpr int DPITCH = 11;
+
 struct BAUnit {
   int ref, pix_begin, pix_end, tgt_begin, tgt_end, primary, pad0, pad1;
 };
@@ -169,8 +172,8 @@ struct AccumSmem {
   double X[2][TP][BA_MAXM];          // predictor rows (bulk-copied), double buffered
   double refz[2][TP][REF_STRIDE];    // z_n, q_n of a tile (one bulk copy), double buffered, one tile ahead of X
   double Z[2][TG][TP][ZW];           // [J_i | J_j | r] of the unit's own target group
-  double E[2][TP][8 * TG];           // alpha * J_j, row = 8 * target + component
-  double dba[2][TP][10];             // per pixel: A = sum alpha^2, B = sum alpha r, D[8] = sum alpha J_i
+  double E[2][TP][EPITCH];           // alpha * J_j, row = 8 * target + component (pitch padded: no bank conflicts)
+  double dba[2][TP][DPITCH];         // per pixel: A = sum alpha^2, B = sum alpha r, D[8] = sum alpha J_i
   double zero[2];
   unsigned long long mbarX[2], mbarR[2];
 };
@@ -236,7 +239,7 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
   }
   // zero once: padding columns of X (bulk copies only write the first M columns), dba, the zero slot
   for (int t = tid; t < 2 * TP * BA_MAXM; t += AC_THREADS) (&S.X[0][0][0])[t] = 0.0;
-  for (int t = tid; t < 2 * TP * 10; t += AC_THREADS) (&S.dba[0][0][0])[t] = 0.0;
+  for (int t = tid; t < 2 * TP * DPITCH; t += AC_THREADS) (&S.dba[0][0][0])[t] = 0.0;
   if (tid < 2) S.zero[tid] = 0.0;
   __syncthreads();
 
@@ -272,7 +275,8 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
     const bool has_first = t_first < g_last;
     const int pair_first = has_first ? ref_pairs[ref_ptr[i] + t_first] : 0;
     const BAFrame* Fj_first = frames + (has_first ? pair_tgt[pair_first] : 0);
-    const double sigma_first = has_first ? sigma_pair[pair_first] : 1.0;
+    const double isig_first = has_first ? 1.0 / sigma_pair[pair_first] : 1.0;
+    const double inv_fx = 1.0 / d.fx, inv_fy = 1.0 / d.fy;
     double pf_r = 0.0;
     double2 pf_a = make_double2(0.0, 0.0), pf_b = make_double2(0.0, 0.0);
     auto prefetch = [&](int tile) {
@@ -298,7 +302,7 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
         for (int q = 0; q < 8; ++q) Ji[q] = Jj[q] = 0.0;
         if (t < g_last && pl < npx) {
           const int n = nb + pl;
-          double r, sigma;
+          double r, isig;
           double2 q0, q1;
           const BAFrame* Fj;
           if (g0 == g_first) {
@@ -306,25 +310,24 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
             q0 = pf_a;
             q1 = pf_b;
             Fj = Fj_first;
-            sigma = sigma_first;
+            isig = isig_first;
           } else {
             const int p = ref_pairs[ref_ptr[i] + t];
             r = rbuf[(size_t)p * d.N + n];
             q0 = *reinterpret_cast<const double2*>(pairbuf + ((size_t)p * d.N + n) * PAIR_STRIDE);
             q1 = *reinterpret_cast<const double2*>(pairbuf + ((size_t)p * d.N + n) * PAIR_STRIDE + 2);
             Fj = frames + pair_tgt[p];
-            sigma = sigma_pair[p];
+            isig = 1.0 / sigma_pair[p];
           }
           if (r == r) {
-            const double wr = fabs(r / sigma);
-            const double wgt = (wr < HUBER_KD) ? 1.0 : HUBER_KD / wr;
-            const double sc = sqrt(wgt) / sigma;
+            const double wr = fabs(r) * isig;
+            const double sc = (wr < HUBER_KD) ? isig : sqrt(HUBER_KD / wr) * isig;
             rs = r * sc;
             const double dIs[3] = {q0.x * sc, q0.y * sc, q1.x * sc};
             const double vsc = q1.y;
             const double z = S.refz[buf][pl][0];
             const int rr = crd[2 * n], cc = crd[2 * n + 1];
-            const double Pc[3] = {z * (((double)cc - d.cx) / d.fx), z * (((double)rr - d.cy) / d.fy), z};
+            const double Pc[3] = {z * (((double)cc - d.cx) * inv_fx), z * (((double)rr - d.cy) * inv_fy), z};
             double RPc[3], Pw[3], Pj[3];
             mat3_vec(Fi.Rwc, Pc, RPc);
             Pw[0] = RPc[0] + Fi.twc[0];
@@ -397,7 +400,7 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
       const int buf = tile & 1;
       if (tile + 1 < ntiles) {
         // dba[buf^1] was consumed by the product role during the previous iteration
-        for (int t = rt; t < TP * 10; t += AC_COEF) (&S.dba[buf ^ 1][0][0])[t] = 0.0;
+        for (int t = rt; t < TP * DPITCH; t += AC_COEF) (&S.dba[buf ^ 1][0][0])[t] = 0.0;
         asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait(&S.mbarR[buf ^ 1], ((tile + 1) >> 1) & 1);
         build(tile + 1, buf ^ 1);
@@ -413,36 +416,20 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
   }
 
   // ================================================================== product role
-  // 256 threads.  G = sum_p A_p x_p x_p^T is symmetric: only its 136 upper-triangular 4x4 blocks are formed
-  // (threads 0..135, mirrored on write-out).  The other 120 threads share the stack rows that are actually
-  // live (9 + 8 * ntgt of 80): item = (row, group of 4 columns), dealt round-robin.
-  constexpr int NGT = 136;                  // G-tile threads
-  constexpr int NST = AC_ROLE - NGT;        // stack threads (120)
-  constexpr int MAXIT = 6;                  // ceil((9 + 8 TG) * 16 / 120)
-  const bool g_thread = rt < NGT;
-  int bi = 0, bj = 0;
-  if (g_thread) {                           // rt -> (bi <= bj) in the 16 x 16 block grid
-    int rem = rt;
-    while (rem >= 16 - bi) {
-      rem -= 16 - bi;
-      ++bi;
-    }
-    bj = bi + rem;
-  }
-  const int live_rows = (primary ? 9 : 0) + 0;   // rows 0..8 only carry data in primary units
-  const int row_lo = primary ? 0 : 9;            // first live stack row
-  const int row_hi = 9 + 8 * ntgt;               // one past the last live stack row
-  (void)live_rows;
-  const int nitems = (row_hi - row_lo) * 16;
-  const int nit = g_thread ? 0 : (nitems - (rt - NGT) + NST - 1) / NST;   // items of this stack thread
+  // 256 threads, 16 x 16 register tiling: thread (ty,tx) owns the 4x4 block (ty,tx) of G = sum_p A_p x_p x_p^T
+  // and 4 columns of the stack rows ty, ty+16, ty+32 (rows 0..7 D, 8 B, 9 + 8 t + q -> alpha J_j of target t).
+  // The pixel loop is software pipelined: operands of pixel p+1 are loaded while pixel p is multiplied.
+  const int ty = rt >> 4, tx = rt & 15;
+  constexpr int NSR = STACK_ROWS / 16;   // 3 stack rows per thread
   constexpr int NZ = (TG * NSMALL + AC_ROLE - 1) / AC_ROLE;   // small-Gram outputs per thread (3)
-  double accG[4][4], accS[MAXIT][4], accZ[NZ];
+  const int row_hi = 9 + 8 * ntgt;       // one past the last live stack row
+  double accG[4][4], accS[NSR][4], accZ[NZ];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) accG[a][b] = 0.0;
 #pragma unroll
-  for (int a = 0; a < MAXIT; ++a)
+  for (int a = 0; a < NSR; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) accS[a][b] = 0.0;
 #pragma unroll
@@ -460,6 +447,18 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
     }
     zmap[a] = (tg < ntgt) ? ((tg << 16) | (ra << 8) | (ra + rem)) : -1;
   }
+  // which of this thread's stack rows are live, and where their coefficients sit (offsets inside E / dba)
+  bool live[NSR];
+  int coff[NSR], cstr[NSR];
+  bool from_dba[NSR];
+#pragma unroll
+  for (int a = 0; a < NSR; ++a) {
+    const int row = ty + 16 * a;
+    from_dba[a] = row < 9;
+    live[a] = from_dba[a] ? primary : (row < row_hi);
+    coff[a] = from_dba[a] ? (row < 8 ? 2 + row : 1) : (row - 9);
+    cstr[a] = from_dba[a] ? DPITCH : EPITCH;
+  }
   if (ntiles > 0 && tid < 32) issue_X(0, 0);
   __syncthreads();   // pairs with the coefficient role's prologue barrier
   for (int tile = 0; tile < ntiles; ++tile) {
@@ -469,56 +468,47 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
     const int npx = min(TP, un.pix_end - nb);
     mbar_wait(&S.mbarX[buf], (tile >> 1) & 1);
     const double* xrow = &S.X[buf][0][0];
-    if (g_thread) {
-      if (primary) {
+    const double* cbase[NSR];
+#pragma unroll
+    for (int a = 0; a < NSR; ++a)
+      cbase[a] = live[a] ? ((from_dba[a] ? &S.dba[buf][0][0] : &S.E[buf][0][0]) + coff[a]) : &S.zero[0];
+    // operands of pixel 0
+    double4 xb = *reinterpret_cast<const double4*>(xrow + 4 * tx);
+    double4 xa = *reinterpret_cast<const double4*>(xrow + 4 * ty);
+    double Acur = S.dba[buf][0][0];
+    double cf[NSR];
+#pragma unroll
+    for (int a = 0; a < NSR; ++a) cf[a] = cbase[a][0];
 #pragma unroll 4
-        for (int p = 0; p < npx; ++p) {
-          const double4 xb = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + 4 * bj);
-          const double4 xa = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + 4 * bi);
-          const double A = S.dba[buf][p][0];
-          const double b4[4] = {xb.x, xb.y, xb.z, xb.w};
-          const double a4[4] = {A * xa.x, A * xa.y, A * xa.z, A * xa.w};
+    for (int p = 0; p < npx; ++p) {
+      // prefetch pixel p+1 (row TP-1 is re-read harmlessly on the last pixel)
+      const int pn = min(p + 1, TP - 1);
+      const double4 xb_n = *reinterpret_cast<const double4*>(xrow + pn * BA_MAXM + 4 * tx);
+      const double4 xa_n = *reinterpret_cast<const double4*>(xrow + pn * BA_MAXM + 4 * ty);
+      const double A_n = S.dba[buf][pn][0];
+      double cf_n[NSR];
 #pragma unroll
-          for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < NSR; ++a) cf_n[a] = live[a] ? cbase[a][pn * cstr[a]] : 0.0;
+      const double b4[4] = {xb.x, xb.y, xb.z, xb.w};
+      if (primary) {
+        const double a4[4] = {Acur * xa.x, Acur * xa.y, Acur * xa.z, Acur * xa.w};
 #pragma unroll
-            for (int b = 0; b < 4; ++b) accG[a][b] += a4[a] * b4[b];
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) accG[a][b] += a4[a] * b4[b];
+      }
+#pragma unroll
+      for (int a = 0; a < NSR; ++a) {
+        if (live[a]) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) accS[a][b] += cf[a] * b4[b];
         }
       }
-    } else {
-      // per item: coefficient pointer / pixel stride and the column group
-      const double* cfp[MAXIT];
-      int cfs[MAXIT], col[MAXIT];
+      xb = xb_n;
+      xa = xa_n;
+      Acur = A_n;
 #pragma unroll
-      for (int a = 0; a < MAXIT; ++a) {
-        const int item = (rt - NGT) + a * NST;
-        const int row = row_lo + item / 16;
-        col[a] = 4 * (item % 16);
-        cfp[a] = &S.zero[0];
-        cfs[a] = 0;
-        if (a < nit) {
-          if (row < 9) {
-            cfp[a] = &S.dba[buf][0][row < 8 ? 2 + row : 1];
-            cfs[a] = 10;
-          } else {
-            cfp[a] = &S.E[buf][0][row - 9];
-            cfs[a] = 8 * TG;
-          }
-        }
-      }
-#pragma unroll 2
-      for (int p = 0; p < npx; ++p) {
-#pragma unroll
-        for (int a = 0; a < MAXIT; ++a) {
-          if (a < nit) {
-            const double cf = cfp[a][p * cfs[a]];
-            const double4 xb = *reinterpret_cast<const double4*>(xrow + p * BA_MAXM + col[a]);
-            accS[a][0] += cf * xb.x;
-            accS[a][1] += cf * xb.y;
-            accS[a][2] += cf * xb.z;
-            accS[a][3] += cf * xb.w;
-          }
-        }
-      }
+      for (int a = 0; a < NSR; ++a) cf[a] = cf_n[a];
     }
     // small Grams
 #pragma unroll
@@ -527,7 +517,7 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
         const double* za = &S.Z[buf][zmap[a] >> 16][0][(zmap[a] >> 8) & 0xff];
         const double* zb = &S.Z[buf][zmap[a] >> 16][0][zmap[a] & 0xff];
         double sacc = 0.0;
-#pragma unroll 4
+#pragma unroll 8
         for (int p = 0; p < npx; ++p) sacc += za[p * ZW] * zb[p * ZW];
         accZ[a] += sacc;
       }
@@ -538,32 +528,16 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
   // ---------------- write the unit's partial sums (the scatter kernels read full G / all stack rows)
   double* out = partial + (size_t)blockIdx.x * PART_STRIDE;
   double* outS = out + BA_MAXM * BA_MAXM;
-  if (g_thread) {
-    if (primary) {
+  if (primary) {
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          out[(4 * bi + a) * BA_MAXM + 4 * bj + b] = accG[a][b];
-          out[(4 * bj + b) * BA_MAXM + 4 * bi + a] = accG[a][b];
-        }
-    }
-  } else {
-#pragma unroll
-    for (int a = 0; a < MAXIT; ++a) {
-      if (a < nit) {
-        const int item = (rt - NGT) + a * NST;
-        const int row = row_lo + item / 16, c0 = 4 * (item % 16);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) outS[row * BA_MAXM + c0 + b] = accS[a][b];
-      }
-    }
+      for (int b = 0; b < 4; ++b) out[(4 * ty + a) * BA_MAXM + 4 * tx + b] = accG[a][b];
   }
-  // stack rows that are not live in this unit are defined as zero
-  for (int t = rt; t < STACK_ROWS * BA_MAXM; t += AC_ROLE) {
-    const int row = t / BA_MAXM;
-    if (row < row_lo || row >= row_hi) outS[t] = 0.0;
-  }
+#pragma unroll
+  for (int a = 0; a < NSR; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) outS[(ty + 16 * a) * BA_MAXM + 4 * tx + b] = live[a] ? accS[a][b] : 0.0;
   double* outZ = outS + STACK_ROWS * BA_MAXM;
 #pragma unroll
   for (int a = 0; a < NZ; ++a) {
