@@ -161,6 +161,7 @@ constexpr int SMALL_STRIDE = 160;
 constexpr int STACK_ROWS = 48;       // 8 (D) + 1 (B) + 8*TG (E) = 41, padded
 constexpr int PART_STRIDE = BA_MAXM * BA_MAXM + STACK_ROWS * BA_MAXM + TG * SMALL_STRIDE;  // doubles per unit
 
+constexpr int XST = 4;               // stages of the predictor-row ring
 constexpr int EPITCH = 8 * TG + 1;
 constexpr int DPITCH = 11;
 
@@ -169,13 +170,13 @@ struct BAUnit {
 };
 
 struct AccumSmem {
-  double X[2][TP][BA_MAXM];          // predictor rows (bulk-copied), double buffered
+  double X[XST][TP][BA_MAXM];        // predictor rows (bulk-copied), XST-deep ring: rows are gathered from HBM
   double refz[2][TP][REF_STRIDE];    // z_n, q_n of a tile (one bulk copy), double buffered, one tile ahead of X
   double Z[2][TG][TP][ZW];           // [J_i | J_j | r] of the unit's own target group
   double E[2][TP][EPITCH];           // alpha * J_j, row = 8 * target + component (pitch padded: no bank conflicts)
   double dba[2][TP][DPITCH];         // per pixel: A = sum alpha^2, B = sum alpha r, D[8] = sum alpha J_i
   double zero[2];
-  unsigned long long mbarX[2], mbarR[2];
+  unsigned long long mbarX[XST], mbarR[2];
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -231,14 +232,13 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
   const int32_t* crd = coords + 2 * ((size_t)i * d.N);
 
   if (tid == 0) {
-    mbar_init(&S.mbarX[0], 1);
-    mbar_init(&S.mbarX[1], 1);
+    for (int q = 0; q < XST; ++q) mbar_init(&S.mbarX[q], 1);
     mbar_init(&S.mbarR[0], 1);
     mbar_init(&S.mbarR[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // zero once: padding columns of X (bulk copies only write the first M columns), dba, the zero slot
-  for (int t = tid; t < 2 * TP * BA_MAXM; t += AC_THREADS) (&S.X[0][0][0])[t] = 0.0;
+  for (int t = tid; t < XST * TP * BA_MAXM; t += AC_THREADS) (&S.X[0][0][0])[t] = 0.0;
   for (int t = tid; t < 2 * TP * DPITCH; t += AC_THREADS) (&S.dba[0][0][0])[t] = 0.0;
   if (tid < 2) S.zero[tid] = 0.0;
   __syncthreads();
@@ -459,15 +459,18 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
     coff[a] = from_dba[a] ? (row < 8 ? 2 + row : 1) : (row - 9);
     cstr[a] = from_dba[a] ? DPITCH : EPITCH;
   }
-  if (ntiles > 0 && tid < 32) issue_X(0, 0);
+  if (tid < 32)
+    for (int q = 0; q < XST - 1 && q < ntiles; ++q) issue_X(q, q);
   __syncthreads();   // pairs with the coefficient role's prologue barrier
   for (int tile = 0; tile < ntiles; ++tile) {
     const int buf = tile & 1;
-    if (tile + 1 < ntiles && tid < 32) issue_X(tile + 1, buf ^ 1);
+    const int xs = tile % XST;
+    // stage (tile + XST - 1) % XST held tile - 1, which every product thread finished before the last barrier
+    if (tile + XST - 1 < ntiles && tid < 32) issue_X(tile + XST - 1, (tile + XST - 1) % XST);
     const int nb = un.pix_begin + tile * TP;
     const int npx = min(TP, un.pix_end - nb);
-    mbar_wait(&S.mbarX[buf], (tile >> 1) & 1);
-    const double* xrow = &S.X[buf][0][0];
+    mbar_wait(&S.mbarX[xs], (tile / XST) & 1);
+    const double* xrow = &S.X[xs][0][0];
     const double* cbase[NSR];
 #pragma unroll
     for (int a = 0; a < NSR; ++a)

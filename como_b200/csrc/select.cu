@@ -34,6 +34,17 @@ template <> struct KeyOf<float> {
   __device__ static float val(K k) { return __uint_as_float(k); }
 };
 
+constexpr int SEL_CAP = 4096;   // candidates finished in shared memory after two global digits
+struct SelSeg {
+  unsigned long long prefix;    // resolved high bits (digits 0,1)
+  unsigned rank;                // rank of the wanted value among the candidates
+  unsigned cand;                // number of candidates (population of the chosen 22-bit bucket)
+  unsigned total;               // valid values in the segment
+  unsigned fallback;            // 1: too many candidates, continue with global digit passes
+  unsigned list_count;          // candidates appended so far
+  unsigned pad;
+};
+
 // digit d (0 = most significant) covers bits [BITS - 11(d+1), BITS - 11 d); the last digit is narrower.
 template <typename T>
 __device__ __forceinline__ int digit_shift(int d) {
@@ -51,7 +62,7 @@ __device__ __forceinline__ int digit_bits(int d) {
 template <typename T>
 __device__ void resolve_prefix(const unsigned* __restrict__ hist, int num_segs, int seg, int upto,
                                typename KeyOf<T>::K& prefix, unsigned long long& rank, unsigned long long& total,
-                               unsigned* s_tmp /* >= SEL_THREADS/32 + 4 */) {
+                               unsigned* s_tmp /* >= SEL_THREADS/32 + 4 */, unsigned* last_count = nullptr) {
   using K = typename KeyOf<T>::K;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   constexpr int PER = SEL_BINS / SEL_THREADS;  // 8
@@ -95,6 +106,7 @@ __device__ void resolve_prefix(const unsigned* __restrict__ hist, int num_segs, 
         if (k >= run && k < run + c[j]) {
           s_tmp[SEL_THREADS / 32 + 0] = tid * PER + j;
           s_tmp[SEL_THREADS / 32 + 1] = k - run;
+          s_tmp[SEL_THREADS / 32 + 2] = c[j];
         }
         run += c[j];
       }
@@ -104,6 +116,9 @@ __device__ void resolve_prefix(const unsigned* __restrict__ hist, int num_segs, 
       const unsigned bin = s_tmp[SEL_THREADS / 32 + 0];
       rank = s_tmp[SEL_THREADS / 32 + 1];
       prefix = (K)(prefix | ((K)bin << digit_shift<T>(d)));
+      if (last_count) *last_count = s_tmp[SEL_THREADS / 32 + 2];
+    } else if (last_count) {
+      *last_count = 0;
     }
     __syncthreads();
   }
@@ -113,12 +128,13 @@ __device__ void resolve_prefix(const unsigned* __restrict__ hist, int num_segs, 
 template <typename T>
 __global__ void __launch_bounds__(SEL_THREADS)
 select_pass_kernel(const T* __restrict__ values, const long long* __restrict__ seg_off, int num_segs, int digit,
-                   unsigned* __restrict__ hist) {
+                   unsigned* __restrict__ hist, const SelSeg* __restrict__ info = nullptr) {
   using K = typename KeyOf<T>::K;
   __shared__ unsigned s_hist[SEL_BINS];
   __shared__ unsigned s_tmp[SEL_THREADS / 32 + 4];
   const int seg = blockIdx.y;
   const int tid = threadIdx.x;
+  if (info != nullptr && info[seg].fallback == 0) return;   // this segment was finished by the compaction path
   for (int b = tid; b < SEL_BINS; b += SEL_THREADS) s_hist[b] = 0;
   K prefix;
   unsigned long long rank, total;
@@ -150,10 +166,11 @@ select_pass_kernel(const T* __restrict__ values, const long long* __restrict__ s
 template <typename T>
 __global__ void __launch_bounds__(SEL_THREADS)
 select_finish_kernel(int num_segs, const unsigned* __restrict__ hist, T scale, T* __restrict__ out,
-                     long long* __restrict__ count) {
+                     long long* __restrict__ count, const SelSeg* __restrict__ info = nullptr) {
   using K = typename KeyOf<T>::K;
   __shared__ unsigned s_tmp[SEL_THREADS / 32 + 4];
   const int seg = blockIdx.x;
+  if (info != nullptr && info[seg].fallback == 0) return;
   K prefix;
   unsigned long long rank, total;
   resolve_prefix<T>(hist, num_segs, seg, KeyOf<T>::PASSES, prefix, rank, total, s_tmp);
@@ -163,24 +180,146 @@ select_finish_kernel(int num_segs, const unsigned* __restrict__ hist, T scale, T
   }
 }
 
+// After digits 0 and 1: gather the values of the chosen 22-bit bucket of every segment (normally a few
+// hundred of 300 k) so that the remaining digits never touch global memory again.
+template <typename T>
+__global__ void __launch_bounds__(SEL_THREADS)
+select_compact_kernel(const T* __restrict__ values, const long long* __restrict__ seg_off, int num_segs,
+                      const unsigned* __restrict__ hist, SelSeg* __restrict__ info, T* __restrict__ lists) {
+  using K = typename KeyOf<T>::K;
+  __shared__ unsigned s_tmp[SEL_THREADS / 32 + 4];
+  const int seg = blockIdx.y, tid = threadIdx.x;
+  K prefix;
+  unsigned long long rank, total;
+  unsigned cand = 0;
+  resolve_prefix<T>(hist, num_segs, seg, 2, prefix, rank, total, s_tmp, &cand);
+  const bool fb = cand > SEL_CAP;
+  if (blockIdx.x == 0 && tid == 0) {
+    info[seg].prefix = (unsigned long long)prefix;
+    info[seg].rank = (unsigned)rank;
+    info[seg].cand = cand;
+    info[seg].total = (unsigned)total;
+    info[seg].fallback = fb ? 1u : 0u;
+  }
+  if (fb || total == 0) return;
+  const int hi_shift = digit_shift<T>(1);
+  const long long beg = seg_off[seg], end = seg_off[seg + 1];
+  for (long long i = beg + (long long)blockIdx.x * SEL_THREADS + tid; i < end; i += (long long)gridDim.x * SEL_THREADS) {
+    const T v = values[i];
+    if (v == v) {
+      const K key = KeyOf<T>::key(v);
+      if ((key >> hi_shift) == (prefix >> hi_shift)) {
+        const unsigned pos = atomicAdd(&info[seg].list_count, 1u);
+        if (pos < SEL_CAP) lists[(size_t)seg * SEL_CAP + pos] = v;
+      }
+    }
+  }
+}
+
+// One CTA per segment: exact rank selection among the gathered candidates (remaining digits in shared memory).
+template <typename T>
+__global__ void __launch_bounds__(SEL_THREADS)
+select_small_kernel(int num_segs, const SelSeg* __restrict__ info, const T* __restrict__ lists, T scale,
+                    T* __restrict__ out, long long* __restrict__ count) {
+  using K = typename KeyOf<T>::K;
+  __shared__ K s_keys[SEL_CAP];
+  __shared__ unsigned s_hist[SEL_BINS];
+  __shared__ unsigned s_warp[SEL_THREADS / 32];
+  __shared__ unsigned s_pick[2];
+  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const SelSeg si = info[seg];
+  if (si.fallback) return;
+  if (si.total == 0) {
+    if (tid == 0) {
+      out[seg] = (T)NAN;
+      if (count) count[seg] = 0;
+    }
+    return;
+  }
+  const int n = (int)si.cand;
+  for (int i = tid; i < n; i += SEL_THREADS) s_keys[i] = KeyOf<T>::key(lists[(size_t)seg * SEL_CAP + i]);
+  K prefix = (K)si.prefix;
+  unsigned rank = si.rank;
+  __syncthreads();
+  for (int d = 2; d < KeyOf<T>::PASSES; ++d) {
+    for (int b = tid; b < SEL_BINS; b += SEL_THREADS) s_hist[b] = 0;
+    __syncthreads();
+    const int sh = digit_shift<T>(d), nb = digit_bits<T>(d), hi = sh + nb;
+    const K dmask = (K)((1u << nb) - 1u);
+    for (int i = tid; i < n; i += SEL_THREADS) {
+      const K key = s_keys[i];
+      if ((key >> hi) == (prefix >> hi)) atomicAdd(&s_hist[(unsigned)((key >> sh) & dmask)], 1u);
+    }
+    __syncthreads();
+    constexpr int PER = SEL_BINS / SEL_THREADS;
+    unsigned c[PER], local = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      c[j] = s_hist[tid * PER + j];
+      local += c[j];
+    }
+    unsigned incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    unsigned base = 0;
+    for (int w = 0; w < wid; ++w) base += s_warp[w];
+    incl += base;
+    const unsigned excl = incl - local;
+    if (rank >= excl && rank < incl) {
+      unsigned run = excl;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        if (rank >= run && rank < run + c[j]) {
+          s_pick[0] = tid * PER + j;
+          s_pick[1] = rank - run;
+        }
+        run += c[j];
+      }
+    }
+    __syncthreads();
+    prefix = (K)(prefix | ((K)s_pick[0] << sh));
+    rank = s_pick[1];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    out[seg] = (T)(scale * KeyOf<T>::val(prefix));
+    if (count) count[seg] = (long long)si.total;
+  }
+}
+
 template <typename T>
 int median_launch(const T* values, const long long* seg_off, int num_segs, long long max_seg_len, T scale, T* out,
                   long long* count, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
-  const size_t need = (size_t)KeyOf<T>::PASSES * num_segs * SEL_BINS * sizeof(unsigned);
+  const size_t hist_bytes = (size_t)KeyOf<T>::PASSES * num_segs * SEL_BINS * sizeof(unsigned);
+  const size_t info_bytes = ((size_t)num_segs * sizeof(SelSeg) + 255) / 256 * 256;
+  const size_t need = hist_bytes + info_bytes + (size_t)num_segs * SEL_CAP * sizeof(T);
   if (workspace_bytes < need) {
     set_last_error("median: workspace %zu < required %zu", workspace_bytes, need);
     return COMO_B200_EWORKSPACE;
   }
   unsigned* hist = (unsigned*)workspace;
-  cudaMemsetAsync(hist, 0, need, stream);
+  SelSeg* info = (SelSeg*)((unsigned char*)workspace + hist_bytes);
+  T* lists = (T*)((unsigned char*)workspace + hist_bytes + info_bytes);
+  cudaMemsetAsync(workspace, 0, hist_bytes + info_bytes, stream);
   long long chunks = (max_seg_len + (long long)SEL_THREADS * 8 - 1) / ((long long)SEL_THREADS * 8);
   const long long cap = (long long)sm_count() * 8 / (num_segs > 0 ? num_segs : 1);
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   dim3 grid((unsigned)chunks, (unsigned)num_segs);
-  for (int d = 0; d < KeyOf<T>::PASSES; ++d)
-    select_pass_kernel<T><<<grid, SEL_THREADS, 0, stream>>>(values, seg_off, num_segs, d, hist);
-  select_finish_kernel<T><<<num_segs, SEL_THREADS, 0, stream>>>(num_segs, hist, scale, out, count);
+  // two global digits, then gather the surviving bucket and finish in shared memory; segments whose bucket
+  // is too large (> SEL_CAP) fall back to the remaining global passes (those kernels exit at once otherwise)
+  select_pass_kernel<T><<<grid, SEL_THREADS, 0, stream>>>(values, seg_off, num_segs, 0, hist);
+  select_pass_kernel<T><<<grid, SEL_THREADS, 0, stream>>>(values, seg_off, num_segs, 1, hist);
+  select_compact_kernel<T><<<grid, SEL_THREADS, 0, stream>>>(values, seg_off, num_segs, hist, info, lists);
+  select_small_kernel<T><<<num_segs, SEL_THREADS, 0, stream>>>(num_segs, info, lists, scale, out, count);
+  for (int d = 2; d < KeyOf<T>::PASSES; ++d)
+    select_pass_kernel<T><<<grid, SEL_THREADS, 0, stream>>>(values, seg_off, num_segs, d, hist, info);
+  select_finish_kernel<T><<<num_segs, SEL_THREADS, 0, stream>>>(num_segs, hist, scale, out, count, info);
   return check_launch("median");
 }
 
@@ -224,7 +363,8 @@ extern "C" int como_b200_median_finish_f64(int32_t num_segments, const void* his
 
 extern "C" size_t como_b200_median_workspace_bytes(int32_t num_segments, int32_t elem_bytes) {
   const int passes = (elem_bytes == 8) ? 6 : 3;
-  return (size_t)passes * (num_segments > 0 ? num_segments : 0) * SEL_BINS * sizeof(unsigned);
+  const size_t ns = (size_t)(num_segments > 0 ? num_segments : 0);
+  return passes * ns * SEL_BINS * sizeof(unsigned) + (ns * sizeof(SelSeg) + 255) / 256 * 256 + ns * SEL_CAP * (size_t)elem_bytes;
 }
 
 extern "C" int como_b200_median_f64(const double* values, const int64_t* seg_offsets, int32_t num_segments,

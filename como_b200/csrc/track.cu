@@ -173,45 +173,86 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
       const float p20 = s_Pm[8], p21 = s_Pm[9], p22 = s_Pm[10], p23 = s_Pm[11];
       const float ea = s_ea, bb = s_aff[1];
 
-      // ---- phase 1: warp, gather, residual, first radix histogram
-      for (int i = i_begin + tid; i < i_end; i += TRK_THREADS) {
-        float r = __int_as_float(0x7fc00000);
-        const bool use = lv.mask ? (lv.mask[i] != 0) : true;
-        if (use) {
-          const float X = lv.P[3 * i + 0], Y = lv.P[3 * i + 1], Z = lv.P[3 * i + 2];
-          const float hx = p00 * X + p01 * Y + p02 * Z + p03;
-          const float hy = p10 * X + p11 * Y + p12 * Z + p13;
-          const float hz = p20 * X + p21 * Y + p22 * Z + p23;
-          const float x = hx / hz, y = hy / hz;
-          const bool valid = (x >= 1.0f) && (x < xmax) && (y >= 1.0f) && (y < ymax) && (hz > 0.0f);
-          if (valid) {
-            // the reference maps pixel coords to [-1,1] and grid_sample maps them back; reproduce
-            // that fp32 round trip (coords.py:18-20, grid_sample unnormalize, align_corners=False)
-            const float xn = __fsub_rn(__fadd_rn(__fmul_rn(2.0f * Ax, x), Ax), 1.0f);
-            const float yn = __fsub_rn(__fadd_rn(__fmul_rn(2.0f * Ay, y), Ay), 1.0f);
-            const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(xn, 1.0f), wf), 1.0f), 0.5f);
-            const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(yn, 1.0f), hf), 1.0f), 0.5f);
-            const float x0f = floorf(ix), y0f = floorf(iy);
-            const int x0 = (int)x0f, y0 = (int)y0f;
-            const float fx0 = ix - x0f, fy0 = iy - y0f;
-            const float fx1 = (x0f + 1.0f) - ix, fy1 = (y0f + 1.0f) - iy;
-            const int xa = min(max(x0, 0), w - 1), xb = min(max(x0 + 1, 0), w - 1);
-            const int ya = min(max(y0, 0), h - 1), yb = min(max(y0 + 1, 0), h - 1);
-            const float v00 = __ldg(lv.img + (size_t)ya * w + xa);
-            const float v01 = __ldg(lv.img + (size_t)ya * w + xb);
-            const float v10 = __ldg(lv.img + (size_t)yb * w + xa);
-            const float v11 = __ldg(lv.img + (size_t)yb * w + xb);
-            float v = v00 * (fx1 * fy1);
-            v += v01 * (fx0 * fy1);
-            v += v10 * (fx1 * fy0);
-            v += v11 * (fx0 * fy0);
-            const float tmp = ea * v;
-            r = (tmp + bb) - lv.vals[i];
-            const unsigned key = __float_as_uint(fabsf(r));
-            atomicAdd(&s_hist[key >> 20], 1u);
+      // ---- phase 1: warp, gather, residual, first radix histogram.  Four pixels per thread and trip so that
+      // the operand loads, and then the 16 bilinear taps, are all in flight together (memory-level parallelism).
+      constexpr int PB = 4;
+      for (int i0 = i_begin + tid; i0 < i_end; i0 += TRK_THREADS * PB) {
+        float X[PB], Y[PB], Z[PB], vref[PB];
+        bool use[PB];
+#pragma unroll
+        for (int k = 0; k < PB; ++k) {
+          const int i = i0 + k * TRK_THREADS;
+          use[k] = (i < i_end) && (lv.mask ? (lv.mask[i] != 0) : true);
+          X[k] = Y[k] = 0.0f;
+          Z[k] = 1.0f;
+          vref[k] = 0.0f;
+          if (use[k]) {
+            X[k] = lv.P[3 * i + 0];
+            Y[k] = lv.P[3 * i + 1];
+            Z[k] = lv.P[3 * i + 2];
+            vref[k] = lv.vals[i];
           }
         }
-        resid[i] = r;
+        float w00[PB], w01[PB], w10[PB], w11[PB];
+        const float* t00[PB];
+        int dxs[PB], dys[PB];
+        bool valid[PB];
+#pragma unroll
+        for (int k = 0; k < PB; ++k) {
+          const float hx = p00 * X[k] + p01 * Y[k] + p02 * Z[k] + p03;
+          const float hy = p10 * X[k] + p11 * Y[k] + p12 * Z[k] + p13;
+          const float hz = p20 * X[k] + p21 * Y[k] + p22 * Z[k] + p23;
+          const float x = hx / hz, y = hy / hz;
+          valid[k] = use[k] && (x >= 1.0f) && (x < xmax) && (y >= 1.0f) && (y < ymax) && (hz > 0.0f);
+          // the reference maps pixel coords to [-1,1] and grid_sample maps them back; reproduce
+          // that fp32 round trip (coords.py:18-20, grid_sample unnormalize, align_corners=False)
+          const float xn = __fsub_rn(__fadd_rn(__fmul_rn(2.0f * Ax, x), Ax), 1.0f);
+          const float yn = __fsub_rn(__fadd_rn(__fmul_rn(2.0f * Ay, y), Ay), 1.0f);
+          const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(xn, 1.0f), wf), 1.0f), 0.5f);
+          const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(yn, 1.0f), hf), 1.0f), 0.5f);
+          const float x0f = floorf(ix), y0f = floorf(iy);
+          const float fx0 = ix - x0f, fy0 = iy - y0f;
+          const float fx1 = (x0f + 1.0f) - ix, fy1 = (y0f + 1.0f) - iy;
+          w00[k] = fx1 * fy1;
+          w01[k] = fx0 * fy1;
+          w10[k] = fx1 * fy0;
+          w11[k] = fx0 * fy0;
+          int x0 = valid[k] ? (int)x0f : 0, y0 = valid[k] ? (int)y0f : 0;
+          const int xa = min(max(x0, 0), w - 1), xb = min(max(x0 + 1, 0), w - 1);
+          const int ya = min(max(y0, 0), h - 1), yb = min(max(y0 + 1, 0), h - 1);
+          t00[k] = lv.img + (size_t)ya * w + xa;
+          dxs[k] = xb - xa;
+          dys[k] = (yb - ya) * w;
+        }
+        float v00[PB], v01[PB], v10[PB], v11[PB];
+#pragma unroll
+        for (int k = 0; k < PB; ++k) {
+          v00[k] = v01[k] = v10[k] = v11[k] = 0.0f;
+          if (valid[k]) {
+            v00[k] = __ldg(t00[k]);
+            v01[k] = __ldg(t00[k] + dxs[k]);
+            v10[k] = __ldg(t00[k] + dys[k]);
+            v11[k] = __ldg(t00[k] + dys[k] + dxs[k]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < PB; ++k) {
+          const int i = i0 + k * TRK_THREADS;
+          if (i < i_end) {
+            float r = __int_as_float(0x7fc00000);
+            if (valid[k]) {
+              float v = v00[k] * w00[k];
+              v += v01[k] * w01[k];
+              v += v10[k] * w10[k];
+              v += v11[k] * w11[k];
+              const float tmp = ea * v;
+              r = (tmp + bb) - vref[k];
+              const unsigned key = __float_as_uint(fabsf(r));
+              atomicAdd(&s_hist[key >> 20], 1u);
+            }
+            resid[i] = r;
+          }
+        }
       }
       flush_hist(s_hist, gh0, HIST_BINS);
       group_barrier(&ctl->barrier, epoch, G);
@@ -265,24 +306,40 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[k] = 0.0f;
       const float inv_sigma = 1.0f / sigma;
-      for (int i = i_begin + tid; i < i_end; i += TRK_THREADS) {
-        const float r = resid[i];
-        if (r == r) {
-          const float4 ja = *reinterpret_cast<const float4*>(lv.J + 8 * (size_t)i);
-          const float4 jb = *reinterpret_cast<const float4*>(lv.J + 8 * (size_t)i + 4);
-          const float tmp = (r - bb) + lv.vals[i];
-          float j[8] = {ja.x, ja.y, ja.z, ja.w, jb.x, jb.y, -tmp, 1.0f};
-          const float wr = r * inv_sigma;
-          const float a = fabsf(wr);
-          const float wgt = (a < HUBER_K) ? 1.0f : HUBER_K / a;
-          acc[44] += wgt * wr * wr;
-          int q = 0;
+      for (int i0 = i_begin + tid; i0 < i_end; i0 += 2 * TRK_THREADS) {
+        float rr[2], vv[2];
+        float4 ja[2], jb[2];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float wj = wgt * j[k];
-            acc[36 + k] += wj * r;
+        for (int k = 0; k < 2; ++k) {
+          const int i = i0 + k * TRK_THREADS;
+          rr[k] = __int_as_float(0x7fc00000);
+          vv[k] = 0.0f;
+          ja[k] = jb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < i_end) {
+            rr[k] = resid[i];
+            vv[k] = lv.vals[i];
+            ja[k] = *reinterpret_cast<const float4*>(lv.J + 8 * (size_t)i);
+            jb[k] = *reinterpret_cast<const float4*>(lv.J + 8 * (size_t)i + 4);
+          }
+        }
 #pragma unroll
-            for (int m = k; m < 8; ++m) acc[q++] += wj * j[m];
+        for (int k = 0; k < 2; ++k) {
+          const float r = rr[k];
+          if (r == r) {
+            const float tmp = (r - bb) + vv[k];
+            float j[8] = {ja[k].x, ja[k].y, ja[k].z, ja[k].w, jb[k].x, jb[k].y, -tmp, 1.0f};
+            const float wr = r * inv_sigma;
+            const float a = fabsf(wr);
+            const float wgt = (a < HUBER_K) ? 1.0f : HUBER_K / a;
+            acc[44] += wgt * wr * wr;
+            int q = 0;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const float wj = wgt * j[kk];
+              acc[36 + kk] += wj * r;
+#pragma unroll
+              for (int m = kk; m < 8; ++m) acc[q++] += wj * j[m];
+            }
           }
         }
       }

@@ -273,17 +273,24 @@ def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return
                 K, R, M, N, H, W, pp.P, intr4, _lib.ptr(pp.frames), _lib.ptr(pp.refbuf), _lib.ptr(pp.rbuf),
                 _lib.ptr(pp.pairbuf), stream)
             _lib.check(st, "como_b200_ba_photo_residual")
-        # exact robust scale per pair batch; with sharded pairs the digit histograms are summed across ranks
-        pp.hist.zero_()
-        for dgt in range(pp.hist.shape[0]):
+        # exact robust scale per pair batch
+        if hist_allreduce is None:
             if pp.P > 0:
-                st = _lib.median_pass_f64(_lib.ptr(pp.rbuf), _lib.ptr(pp.seg_off), pp.nbatch, pp.max_seg, dgt,
-                                          _lib.ptr(pp.hist), stream)
-                _lib.check(st, "como_b200_median_pass_f64")
-            if hist_allreduce is not None:
+                rws = _buf(cache, "rmed_ws", (int(_lib.median_workspace_bytes(pp.nbatch, 8)),), torch.uint8, dev)
+                st = _lib.median_f64(_lib.ptr(pp.rbuf), _lib.ptr(pp.seg_off), pp.nbatch, pp.max_seg, 1.4826, _lib.ptr(sig),
+                                     None, _lib.ptr(rws), rws.numel(), stream)
+                _lib.check(st, "como_b200_median_f64")
+        else:
+            # sharded pairs: the digit histograms are summed across ranks between the radix passes
+            pp.hist.zero_()
+            for dgt in range(pp.hist.shape[0]):
+                if pp.P > 0:
+                    st = _lib.median_pass_f64(_lib.ptr(pp.rbuf), _lib.ptr(pp.seg_off), pp.nbatch, pp.max_seg, dgt,
+                                              _lib.ptr(pp.hist), stream)
+                    _lib.check(st, "como_b200_median_pass_f64")
                 hist_allreduce(pp.hist[dgt])
-        st = _lib.median_finish_f64(pp.nbatch, _lib.ptr(pp.hist), 1.4826, _lib.ptr(sig), None, stream)
-        _lib.check(st, "como_b200_median_finish_f64")
+            st = _lib.median_finish_f64(pp.nbatch, _lib.ptr(pp.hist), 1.4826, _lib.ptr(sig), None, stream)
+            _lib.check(st, "como_b200_median_finish_f64")
         if pp.P > 0:
             st = _lib.ba_photo_accum(
                 _lib.ptr(s.Knm_Kmminv), _lib.ptr(kp.coords), _lib.ptr(scaf), _lib.ptr(dz_dP), _lib.ptr(kp.lm_ids),

@@ -165,3 +165,30 @@ def test_synthetic_window_iterations_stay_finite_and_converge():
     assert dn[-1] < 0.2 * dn[0]
     gt = torch.tensor([k * 6.0 * 2.0 / (525 * 128 / 640) for k in range(6)], dtype=torch.float64)
     assert float((s.kf_poses[:, 0, 3].cpu() - gt).abs().max()) < 0.05
+
+
+def test_distributed_median_passes_match_fused_median():
+    """The pass/finish building blocks (used with an all-reduce between digits when pairs are sharded) give the same
+    order statistic as the fused fast path (compaction after two digits), including the > SEL_CAP fallback."""
+    from como_b200 import _lib
+
+    torch.manual_seed(3)
+    lens = [5000, 70000, 9000]
+    vals = [torch.rand(n, dtype=torch.float64) * 1e-2 for n in lens]
+    vals[1] = 0.5 + 1e-9 * torch.rand(lens[1], dtype=torch.float64)   # one 22-bit bucket holds everything: fallback path
+    vals[2][::5] = float("nan")
+    flat = torch.cat(vals).cuda()
+    off = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64).cuda()
+    ns = len(lens)
+    out1 = torch.empty(ns, dtype=torch.float64, device="cuda")
+    ws = torch.empty(int(_lib.median_workspace_bytes(ns, 8)), dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.median_f64(_lib.ptr(flat), _lib.ptr(off), ns, max(lens), 1.0, _lib.ptr(out1), None, _lib.ptr(ws),
+                               ws.numel(), _lib.stream_ptr()), "median")
+    hist = torch.zeros(int(_lib.median_num_passes(8)), ns, 2048, dtype=torch.int32, device="cuda")
+    for d in range(hist.shape[0]):
+        _lib.check(_lib.median_pass_f64(_lib.ptr(flat), _lib.ptr(off), ns, max(lens), d, _lib.ptr(hist), _lib.stream_ptr()), "pass")
+    out2 = torch.empty(ns, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.median_finish_f64(ns, _lib.ptr(hist), 1.0, _lib.ptr(out2), None, _lib.stream_ptr()), "finish")
+    for i, v in enumerate(vals):
+        ref = float(torch.median(v[~torch.isnan(v)]))
+        assert float(out1[i]) == ref and float(out2[i]) == ref
