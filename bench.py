@@ -241,12 +241,13 @@ def run_ba_ours(args, rank, world, device):
     from como_b200.odom import mapping_core as MC
 
     K, R, H, W, M = args.kf, args.oneway, 480, 640, 64
-    s = synth.make_ba_window(K, R, H, W, M=M, device=device, seed=rank)
+    shard = world > 1 and args.shard
+    # sharded: every rank holds the SAME window (its pair blocks are split); replicas: one window per rank
+    s = synth.make_ba_window(K, R, H, W, M=M, device=device, seed=0 if shard else rank)
     cfg = synth.ba_cfg()
     snap = snapshot_small(s) if rank == 0 else None   # CPU baseline runs on the untouched initial state
     allreduce = None
     hist_allreduce = None
-    shard = world > 1 and args.shard
     if shard:
         def allreduce(Hm, g, err):
             torch.distributed.all_reduce(Hm)

@@ -57,7 +57,11 @@ ba_priors_kernel(const double* __restrict__ scaf, const double* __restrict__ dz_
   __shared__ double s_d[BA_MAXM], s_w[BA_MAXM], s_u[BA_MAXM], s_dT[BA_MAXM][6], s_Y[BA_MAXM][6];
   __shared__ double s_TT[36], s_gT[6], s_err[4];
   __shared__ int s_lm[BA_MAXM];
+  // grid (K, NSLICE): the two big 3M x 3M scatter loops are split over blockIdx.y; everything that must happen
+  // once per keyframe is done by slice 0
   const int k = blockIdx.x, tid = threadIdx.x, M = d.M;
+  const int slice = blockIdx.y, nslice = gridDim.y;
+  const bool lead = slice == 0;
   const double logmed = log(med[k]);
   const double d3[3] = {dz_dP[3 * k], dz_dP[3 * k + 1], dz_dP[3 * k + 2]};
   const int lm_start = 8 * (d.K + d.R);
@@ -88,11 +92,24 @@ ba_priors_kernel(const double* __restrict__ scaf, const double* __restrict__ dz_
   __syncthreads();
   const int M3 = 3 * M;
   // ---- GP marginal-likelihood prior
-  for (int t = tid; t < M3 * M3; t += 256) {
+  for (int t = tid + 256 * slice; t < M3 * M3; t += 256 * nslice) {
     const int ra = t / M3, rb = t % M3;
     const int m = ra / 3, c = ra % 3, m2 = rb / 3, c2 = rb % 3;
     atomicAdd(H + (size_t)(lm_start + 3 * s_lm[m] + c) * dim + (lm_start + 3 * s_lm[m2] + c2),
               W[m * M + m2] * s_u[m] * d3[c] * s_u[m2] * d3[c2]);
+  }
+  if (!lead) {
+    // slices > 0 only help with the big blocks (incl. the keyframe-0 scale prior below)
+    if (k == 0 && !pp.window_full) {
+      const double im = pp.info_mean_depth;
+      for (int t = tid + 256 * slice; t < M3 * M3; t += 256 * nslice) {
+        const int ra = t / M3, rb = t % M3;
+        const int m = ra / 3, c = ra % 3, m2 = rb / 3, c2 = rb % 3;
+        atomicAdd(H + (size_t)(lm_start + 3 * s_lm[m] + c) * dim + (lm_start + 3 * s_lm[m2] + c2),
+                  im * colmean[m] * s_u[m] * d3[c] * colmean[m2] * s_u[m2] * d3[c2]);
+      }
+    }
+    return;
   }
   for (int t = tid; t < M3; t += 256) {
     const int m = t / 3, c = t % 3;
@@ -247,7 +264,7 @@ ba_priors_kernel(const double* __restrict__ scaf, const double* __restrict__ dz_
     }
     __syncthreads();
     const double rv = s_rv, im = pp.info_mean_depth;
-    for (int t = tid; t < M3 * M3; t += 256) {
+    for (int t = tid; t < M3 * M3; t += 256 * nslice) {   // slice 0's share
       const int ra = t / M3, rb = t % M3;
       const int m = ra / 3, c = ra % 3, m2 = rb / 3, c2 = rb % 3;
       atomicAdd(H + (size_t)(lm_start + 3 * s_lm[m] + c) * dim + (lm_start + 3 * s_lm[m2] + c2),
@@ -302,7 +319,7 @@ extern "C" int como_b200_ba_priors(const double* scaffold, const double* dz_dP, 
   pp.scale_anchor = scale_anchor;
   pp.window_full = window_full;
   pp.nfix = nfix;
-  ba_priors_kernel<<<K, 256, 0, (cudaStream_t)stream>>>(scaffold, dz_dP, LtL, median_depths, obs_ref_mask, pm_first_obs,
+  ba_priors_kernel<<<dim3(K, 8), 256, 0, (cudaStream_t)stream>>>(scaffold, dz_dP, LtL, median_depths, obs_ref_mask, pm_first_obs,
                                                         lm_ids, kf_poses, pose_anchor, kf_aff, aff_anchor, colmean, P_m,
                                                         P_m_anchors, fix_ids, pp, d, dim, H, g, err8);
   return check_launch("ba_priors");

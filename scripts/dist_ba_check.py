@@ -42,7 +42,7 @@ def main():
         res = dict(sigma=rel(d2["sigma"], d1["sigma"]), H=rel(d2["H"], d1["H"]), g=rel(d2["g"], d1["g"]),
                    delta=rel(d2["delta"], d1["delta"]), poses=rel(s.kf_poses, s_single.kf_poses),
                    P_m=rel(s.P_m, s_single.P_m), err=abs(float(d2["err"].sum() - d1["err"].sum())) / float(d1["err"].sum()))
-        bad = res["sigma"] > 1e-12 or res["H"] > 1e-9 or res["g"] > 1e-9 or res["poses"] > 1e-6 or res["P_m"] > 1e-6
+        bad = res["sigma"] > 1e-9 or res["H"] > 1e-9 or res["g"] > 1e-8 or res["poses"] > 1e-6 or res["P_m"] > 1e-6
         ok = ok and not bad
         if rank == 0:
             print(f"iter {it}: " + " ".join(f"{k}={v:.2e}" for k, v in res.items()), "BAD" if bad else "ok", flush=True)
