@@ -40,9 +40,9 @@ struct SelSeg {
   unsigned rank;                // rank of the wanted value among the candidates
   unsigned cand;                // number of candidates (population of the chosen 22-bit bucket)
   unsigned total;               // valid values in the segment
-  unsigned fallback;            // 1: too many candidates, continue with global digit passes
+  unsigned fallback;            // 1: not (yet) finished by the compaction path -> global digit passes continue
   unsigned list_count;          // candidates appended so far
-  unsigned pad;
+  unsigned digits;              // number of digits resolved globally before the compaction (2 or 3)
 };
 
 // digit d (0 = most significant) covers bits [BITS - 11(d+1), BITS - 11 d); the last digit is narrower.
@@ -185,24 +185,28 @@ select_finish_kernel(int num_segs, const unsigned* __restrict__ hist, T scale, T
 template <typename T>
 __global__ void __launch_bounds__(SEL_THREADS)
 select_compact_kernel(const T* __restrict__ values, const long long* __restrict__ seg_off, int num_segs,
-                      const unsigned* __restrict__ hist, SelSeg* __restrict__ info, T* __restrict__ lists) {
+                      const unsigned* __restrict__ hist, SelSeg* __restrict__ info, T* __restrict__ lists, int upto,
+                      int first) {
   using K = typename KeyOf<T>::K;
   __shared__ unsigned s_tmp[SEL_THREADS / 32 + 4];
   const int seg = blockIdx.y, tid = threadIdx.x;
+  if (!first && info[seg].fallback == 0) return;   // an earlier compaction already finished this segment
   K prefix;
   unsigned long long rank, total;
   unsigned cand = 0;
-  resolve_prefix<T>(hist, num_segs, seg, 2, prefix, rank, total, s_tmp, &cand);
+  resolve_prefix<T>(hist, num_segs, seg, upto, prefix, rank, total, s_tmp, &cand);
   const bool fb = cand > SEL_CAP;
+  // every CTA of the segment reaches the same verdict; CTA 0 records it (read by LATER launches only)
   if (blockIdx.x == 0 && tid == 0) {
     info[seg].prefix = (unsigned long long)prefix;
     info[seg].rank = (unsigned)rank;
     info[seg].cand = cand;
     info[seg].total = (unsigned)total;
     info[seg].fallback = fb ? 1u : 0u;
+    info[seg].digits = (unsigned)upto;
   }
   if (fb || total == 0) return;
-  const int hi_shift = digit_shift<T>(1);
+  const int hi_shift = digit_shift<T>(upto - 1);
   const long long beg = seg_off[seg], end = seg_off[seg + 1];
   for (long long i = beg + (long long)blockIdx.x * SEL_THREADS + tid; i < end; i += (long long)gridDim.x * SEL_THREADS) {
     const T v = values[i];
@@ -241,7 +245,7 @@ select_small_kernel(int num_segs, const SelSeg* __restrict__ info, const T* __re
   K prefix = (K)si.prefix;
   unsigned rank = si.rank;
   __syncthreads();
-  for (int d = 2; d < KeyOf<T>::PASSES; ++d) {
+  for (int d = (int)si.digits; d < KeyOf<T>::PASSES; ++d) {
     for (int b = tid; b < SEL_BINS; b += SEL_THREADS) s_hist[b] = 0;
     __syncthreads();
     const int sh = digit_shift<T>(d), nb = digit_bits<T>(d), hi = sh + nb;
@@ -315,9 +319,17 @@ int median_launch(const T* values, const long long* seg_off, int num_segs, long 
   // is too large (> SEL_CAP) fall back to the remaining global passes (those kernels exit at once otherwise)
   select_pass_kernel<T><<<grid, SEL_THREADS, 0, stream>>>(values, seg_off, num_segs, 0, hist);
   select_pass_kernel<T><<<grid, SEL_THREADS, 0, stream>>>(values, seg_off, num_segs, 1, hist);
-  select_compact_kernel<T><<<grid, SEL_THREADS, 0, stream>>>(values, seg_off, num_segs, hist, info, lists);
+  select_compact_kernel<T><<<grid, SEL_THREADS, 0, stream>>>(values, seg_off, num_segs, hist, info, lists, 2, 1);
+  int next_digit = 2;
+  if (KeyOf<T>::PASSES > 3) {
+    // narrow value ranges (a fronto-parallel wall: all depths within 0.1 %) overflow a 22-bit bucket: one more
+    // global digit for those segments only, then a second compaction attempt
+    select_pass_kernel<T><<<grid, SEL_THREADS, 0, stream>>>(values, seg_off, num_segs, 2, hist, info);
+    select_compact_kernel<T><<<grid, SEL_THREADS, 0, stream>>>(values, seg_off, num_segs, hist, info, lists, 3, 0);
+    next_digit = 3;
+  }
   select_small_kernel<T><<<num_segs, SEL_THREADS, 0, stream>>>(num_segs, info, lists, scale, out, count);
-  for (int d = 2; d < KeyOf<T>::PASSES; ++d)
+  for (int d = next_digit; d < KeyOf<T>::PASSES; ++d)
     select_pass_kernel<T><<<grid, SEL_THREADS, 0, stream>>>(values, seg_off, num_segs, d, hist, info);
   select_finish_kernel<T><<<num_segs, SEL_THREADS, 0, stream>>>(num_segs, hist, scale, out, count, info);
   return check_launch("median");

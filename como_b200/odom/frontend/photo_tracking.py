@@ -10,6 +10,25 @@ import torch
 from como_b200 import _lib
 
 _ws_cache = {}
+_k9_cache = {}
+last_num_iters = None
+
+
+def _k9_list(K):
+    """3x3 intrinsics -> 9 python floats.  Device tensors are read back once and cached by (storage, version):
+    a device->host copy per level and call would otherwise dominate the launch."""
+    if not isinstance(K, torch.Tensor):
+        return [float(v) for row in K for v in (row if hasattr(row, "__len__") else [row])]
+    if not K.is_cuda:
+        return K.detach().to(torch.float32).reshape(-1).tolist()
+    key = (K.data_ptr(), K._version, K.device.index)
+    v = _k9_cache.get(key)
+    if v is None:
+        if len(_k9_cache) > 4096:
+            _k9_cache.clear()
+        v = K.detach().to("cpu", torch.float32).reshape(-1).tolist()
+        _k9_cache[key] = v
+    return v
 
 
 def _workspace(nbytes, device):
@@ -39,7 +58,7 @@ def _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, keep):
         if img.shape[0] != 1 or img.shape[1] != 1:
             raise NotImplementedError("como_b200 tracking expects img_j[l] of shape (1,1,h,w)")
         img = img.contiguous().float()
-        Kl = intrinsics[l].detach().to("cpu", torch.float32).reshape(-1).tolist()
+        Kl = _k9_list(intrinsics[l])
         keep += [v, P, J, m, img]
         n = v.shape[0]
         max_n = max(max_n, n)
@@ -69,12 +88,14 @@ def photo_tracking_pyr(Tji_init, aff_init, vals_i, Pi, dI_dT, masks, intrinsics,
                               float(term_criteria["rel_tol"]), float(term_criteria["grad_norm"]))
         cap = num_levels * term.max_iter
         stats = torch.zeros(cap, _lib.TRACK_STAT_STRIDE, dtype=torch.float32, device=dev) if return_stats else None
-        nit = torch.zeros(1, dtype=torch.int32, device=dev) if return_stats else None
+        nit = torch.zeros(1, dtype=torch.int32, device=dev)
         nbytes = _lib.track_workspace_bytes(max_n, 1)
         ws = _workspace(nbytes, dev)
         st = _lib.track_pyr(arr, num_levels, 1, C.byref(term), _lib.ptr(T), _lib.ptr(aff), _lib.ptr(stats),
                             _lib.ptr(nit), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
         _lib.check(st, "como_b200_track_pyr")
+    global last_num_iters
+    last_num_iters = nit   # device tensor (no sync): GN iterations of the most recent call, for instrumentation
     Tji = T.to(Tji_init.dtype)
     aff_out = aff.reshape(1, 2, 1).to(aff_init.dtype)
     if return_stats:
@@ -128,7 +149,7 @@ def precalc_jacobians(dI_dw, P, vals, intrinsics):
     Pf = P.reshape(-1, 3).contiguous().float()
     v = vals.reshape(-1).contiguous().float()
     J = torch.empty(b * n, 8, dtype=torch.float32, device=dev)
-    K = (C.c_float * 9)(*intrinsics.detach().to("cpu", torch.float32).reshape(-1).tolist())
+    K = (C.c_float * 9)(*_k9_list(intrinsics))
     with torch.cuda.device(dev):
         st = _lib.precalc_jacobians(_lib.ptr(g), _lib.ptr(Pf), _lib.ptr(v), K, b * n, _lib.ptr(J), _lib.stream_ptr(dev))
     _lib.check(st, "como_b200_precalc_jacobians")
