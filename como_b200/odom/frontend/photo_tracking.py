@@ -139,6 +139,40 @@ def photo_tracking_pyr_batch(Tji_init, aff_init, problems, term_criteria, return
     return T, aff.reshape(B, 2, 1), nit
 
 
+class TrackBatchPlan:
+    """Pre-validated launch description of B independent tracking problems: the per-level descriptors are built
+    once (the operand tensors must stay alive and in place), `run` only copies the initial poses and launches."""
+
+    def __init__(self, problems, term_criteria):
+        self.B = len(problems)
+        self.num_levels = len(problems[0][0])
+        self.dev = _lib.require_cuda(*problems[0][0])
+        self.keep = []
+        with torch.cuda.device(self.dev):
+            self.arr = (_lib.TrackLevel * (self.B * self.num_levels))()
+            max_n = 0
+            for p, (vals_i, Pi, dI_dT, masks, intrinsics, img_j) in enumerate(problems):
+                a, mn = _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, self.keep)
+                max_n = max(max_n, mn)
+                for l in range(self.num_levels):
+                    self.arr[p * self.num_levels + l] = a[l]
+            self.term = _lib.TrackTerm(int(term_criteria["max_iter"]), float(term_criteria["delta_norm"]),
+                                       float(term_criteria["rel_tol"]), float(term_criteria["grad_norm"]))
+            self.ws = torch.empty(int(_lib.track_workspace_bytes(max_n, self.B)), dtype=torch.uint8, device=self.dev)
+            self.T = torch.empty(self.B, 4, 4, dtype=torch.float32, device=self.dev)
+            self.aff = torch.empty(self.B, 2, dtype=torch.float32, device=self.dev)
+            self.nit = torch.zeros(self.B, dtype=torch.int32, device=self.dev)
+
+    def run(self, Tji_init, aff_init):
+        with torch.cuda.device(self.dev):
+            self.T.copy_(Tji_init.reshape(self.B, 4, 4))
+            self.aff.copy_(aff_init.reshape(self.B, 2))
+            st = _lib.track_pyr(self.arr, self.num_levels, self.B, C.byref(self.term), _lib.ptr(self.T), _lib.ptr(self.aff),
+                                None, _lib.ptr(self.nit), _lib.ptr(self.ws), self.ws.numel(), _lib.stream_ptr(self.dev))
+            _lib.check(st, "como_b200_track_pyr")
+        return self.T, self.aff.reshape(self.B, 2, 1), self.nit
+
+
 def precalc_jacobians(dI_dw, P, vals, intrinsics):
     """dI_dw (B,N,C,2), P (B,N,3), vals (B,N,C), intrinsics (3,3) -> (B,N,C,8); C must be 1."""
     dev = _lib.require_cuda(dI_dw, P, vals)
