@@ -362,7 +362,7 @@ def run_ba_ours(args, rank, world, device):
         "e2e": {"value": nwin * args.steps / (e_ms * 1e-3), "unit": "GN-it/s",
                 "h2d_bytes_per_step": int(rgb_host.numel() * 8), "d2h_bytes_per_step": int(res_host.numel() * 8)},
         "gpu_launches": args.steps * 22,
-        "roofline": {"kernel": "predictor_apply_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": "predictor_stream_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                      "alg_bytes_per_launch": ab["predictor_apply"], "launch_ms": pa_ms},
         "clocks": clocks,

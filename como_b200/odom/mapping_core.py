@@ -7,6 +7,7 @@ or the lightweight `WindowState` used by bench.py and the tests.  All tensors mu
 There is no CPU path.
 """
 import ctypes as C
+import os
 import math
 
 import torch
@@ -191,6 +192,9 @@ def _buf(cache, name, shape, dtype, dev):
     return t
 
 
+_OVERLAP = os.environ.get("COMO_B200_BA_OVERLAP", "1") != "0"
+
+
 def solve_system(H, g):
     """Drop-in for lin_sys.solve_system (como/odom/backend/linear_system.py:101-112): dense Cholesky,
     never raises on a non-PD matrix."""
@@ -238,19 +242,37 @@ def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return
                               _lib.ptr(dz_dP), stream)
         _lib.check(st, "como_b200_ba_scaffold")
 
-        # ---- store_vars: dense depth of every keyframe + exact per-keyframe median
+        # ---- store_vars: dense depth of every keyframe + exact per-keyframe median.  HBM-bound and independent
+        # of the normal-equation build below (fp64-pipe bound), so it runs on a side stream: the streaming
+        # predictor CTA (64 KB smem, <64 regs) is sized to share an SM with the accumulation CTA.
         depth = torch.empty(K, 1, H, W, dtype=F64, device=dev)
-        st = _lib.predictor_apply(_lib.ptr(s.Knm_Kmminv), _lib.ptr(scaf), K, H * W, M, _lib.ptr(depth), stream)
-        _lib.check(st, "como_b200_predictor_apply")
         med_new = torch.empty(K, dtype=F64, device=dev)
         seg = cache.get("depth_seg")
         if seg is None or seg.numel() != K + 1:
             seg = (torch.arange(K + 1, dtype=torch.int64) * (H * W)).to(dev)
             cache["depth_seg"] = seg
         mws = _buf(cache, "med_ws", (int(_lib.median_workspace_bytes(K, 8)),), torch.uint8, dev)
-        st = _lib.median_f64(_lib.ptr(depth), _lib.ptr(seg), K, H * W, 1.0, _lib.ptr(med_new), None, _lib.ptr(mws),
-                             mws.numel(), stream)
-        _lib.check(st, "como_b200_median_f64")
+        main = torch.cuda.current_stream(dev)
+        side = main
+        if _OVERLAP:
+            side = cache.get("side_stream")
+            if side is None:
+                side = cache["side_stream"] = torch.cuda.Stream(dev)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+        with torch.cuda.stream(side):
+            sstream = _lib.stream_ptr(dev)
+            st = _lib.predictor_apply(_lib.ptr(s.Knm_Kmminv), _lib.ptr(scaf), K, H * W, M, _lib.ptr(depth), sstream)
+            _lib.check(st, "como_b200_predictor_apply")
+            st = _lib.median_f64(_lib.ptr(depth), _lib.ptr(seg), K, H * W, 1.0, _lib.ptr(med_new), None, _lib.ptr(mws),
+                                 mws.numel(), sstream)
+            _lib.check(st, "como_b200_median_f64")
+        if side is not main:
+            depth.record_stream(side)
+            med_new.record_stream(side)
+            store_done = torch.cuda.Event()
+            store_done.record(side)
         s.pm = scaf[:, :, 2:4].clone()
         s.logzm = scaf[:, :, 0:1].clone()
         s.depth_imgs = depth
@@ -306,6 +328,8 @@ def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return
         if return_debug:
             dbg = dict(H_photo=Hm.clone(), g_photo=g.clone(), sigma=sig.clone(), coords_n=kp.coords.clone(),
                        pairs=pp.pairs_full, vals_n=kp.vals_n.clone())
+        if side is not main:
+            main.wait_event(store_done)
         sg = cfg["sigmas"]
         sig4 = (C.c_double * 4)(1e-2, float(sg["pose_prior"]), float(sg["scale_prior"]), float(sg["mean_depth_prior"]))
         full = bool(s.window_full)

@@ -155,7 +155,7 @@ int como_b200_ba_photo_accum(const double* Knm, const int32_t* coords, const dou
                              const double* pairbuf, double* sigma_pair_ws, double* partial, double* H, double* g,
                              double* photo_err, void* stream);
 
-/* Prior factors of Mapping.iterate (Mapping.py:809-917; como/odom/factors/*.py).  LtL (K,M,M) = L_mm^-T L_mm^-1.
+/* Prior factors of Mapping.iterate (Mapping.py:809-917; como/odom/factors/).  LtL (K,M,M) = L_mm^-T L_mm^-1.
  * sigmas4 HOST = [pixel_sigma_first, pose_prior, scale_prior, mean_depth_prior]; err8 += [_, gp, logdepth, pixel,
  * pose, affine, scale, fixed]. */
 int como_b200_ba_priors(const double* scaffold, const double* dz_dP, const double* LtL, const double* median_depths,
