@@ -276,130 +276,6 @@ __global__ void sampler_pick_kernel(SamplerState* __restrict__ st, const float* 
   }
 }
 
-// ------------------------------------------------------------------------------------------------ K-matrix (Python formula)
-__device__ __forceinline__ double cov_python_f64(double x1r, double x1c, const double* E1, double x2r, double x2c,
-                                                 const double* E2, double scale) {
-  // kernels.py:22-68: diff rounded to float32, everything else in double
-  const double d0 = (double)(float)(x1r - x2r), d1 = (double)(float)(x1c - x2c);
-  const double s00 = E1[0] + E2[0], s01 = E1[1] + E2[1], s11 = E1[3] + E2[3];
-  double Q = s11 * (d0 * d0);
-  Q += -2.0 * s01 * d0 * d1;
-  Q += s00 * (d1 * d1);
-  const double det = s00 * s11 - s01 * s01;
-  Q /= det;
-  Q *= 0.5;
-  const double r1 = sqrt(sqrt(E1[0] * E1[3] - E1[1] * E1[2]));
-  const double r2 = sqrt(sqrt(E2[0] * E2[3] - E2[1] * E2[2]));
-  const double Cc = 2.0 * r1 * r2 / sqrt(det + 1e-8);
-  const double t = 1.7320508075688772 * sqrt(Q + 1e-8);
-  return ((1.0 + t) * exp(-t)) * Cc * scale;
-}
-
-// bilinear lookup of the 4-channel covariance image with border padding (gaussian_kernel.py:52-79);
-// coords are pixel (row, col); normalisation to [-1,1] and back cancels up to rounding.
-__device__ __forceinline__ void interp_cov(const double* __restrict__ img, int H, int W, double row, double col,
-                                           double* E) {
-  double x = col, y = row;
-  x = fmin(fmax(x, 0.0), (double)(W - 1));
-  y = fmin(fmax(y, 0.0), (double)(H - 1));
-  const double x0f = floor(x), y0f = floor(y);
-  int x0 = (int)x0f, y0 = (int)y0f;
-  const double fx = x - x0f, fy = y - y0f;
-  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
-  for (int c = 0; c < 4; ++c) {
-    const double* p = img + (size_t)c * H * W;
-    E[c] = p[(size_t)y0 * W + x0] * (1 - fx) * (1 - fy) + p[(size_t)y0 * W + x1] * fx * (1 - fy) +
-           p[(size_t)y1 * W + x0] * (1 - fx) * fy + p[(size_t)y1 * W + x1] * fx * fy;
-  }
-}
-
-// E_m at the anchors + K_mm (+ jitter on the diagonal).  One CTA per keyframe.
-__global__ void kmm_kernel(const double* __restrict__ cov_img, int H, int W, const double* __restrict__ coords_m, int M,
-                           double scale, double jitter, double* __restrict__ E_m, double* __restrict__ K_mm) {
-  const int b = blockIdx.x;
-  const double* img = cov_img + (size_t)b * 4 * H * W;
-  extern __shared__ double sE[];  // M*4 + M*2
-  double* sx = sE + 4 * M;
-  for (int m = threadIdx.x; m < M; m += blockDim.x) {
-    const double r = coords_m[((size_t)b * M + m) * 2], c = coords_m[((size_t)b * M + m) * 2 + 1];
-    double E[4];
-    interp_cov(img, H, W, r, c, E);
-    for (int q = 0; q < 4; ++q) {
-      sE[4 * m + q] = E[q];
-      E_m[((size_t)b * M + m) * 4 + q] = E[q];
-    }
-    // normalised coordinates as the reference feeds them: 2*A*x + A - 1, A = 1/dims
-    sx[2 * m] = 2.0 * (1.0 / H) * r + (1.0 / H) - 1.0;
-    sx[2 * m + 1] = 2.0 * (1.0 / W) * c + (1.0 / W) - 1.0;
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < M * M; t += blockDim.x) {
-    const int i = t / M, j = t % M;
-    double v = cov_python_f64(sx[2 * i], sx[2 * i + 1], sE + 4 * i, sx[2 * j], sx[2 * j + 1], sE + 4 * j, scale);
-    if (i == j) v += jitter;
-    K_mm[(size_t)b * M * M + t] = v;
-  }
-}
-
-// Fused K_nm (HW x M, never written) times K_mm^-1 (M x M):  out[p, :] = K_nm[p, :] Kinv.
-// CTA = 256 threads = 64 pixels x 4 column groups; K_nm rows for 64 pixels are built in shared memory,
-// then each thread produces 16 outputs of its pixel with fma() over Kinv held in shared memory.
-constexpr int KP_PIX = 64;
-__global__ void __launch_bounds__(256)
-kmat_predictor_kernel(const double* __restrict__ cov_img, int H, int W, const double* __restrict__ coords_m,
-                      const double* __restrict__ E_m, const double* __restrict__ Kinv, int M, double scale,
-                      double* __restrict__ out) {
-  extern __shared__ double sm[];
-  double* sKinv = sm;                      // M*M
-  double* sEm = sKinv + BA_MAXM * BA_MAXM; // M*4
-  double* sxm = sEm + 4 * BA_MAXM;         // M*2
-  double* sK = sxm + 2 * BA_MAXM;          // KP_PIX * (M+1)
-  const int b = blockIdx.y;
-  const double* img = cov_img + (size_t)b * 4 * H * W;
-  const long long HW = (long long)H * W;
-  for (int t = threadIdx.x; t < M * M; t += 256) sKinv[t] = Kinv[(size_t)b * M * M + t];
-  for (int t = threadIdx.x; t < M; t += 256) {
-    for (int q = 0; q < 4; ++q) sEm[4 * t + q] = E_m[((size_t)b * M + t) * 4 + q];
-    const double r = coords_m[((size_t)b * M + t) * 2], c = coords_m[((size_t)b * M + t) * 2 + 1];
-    sxm[2 * t] = 2.0 * (1.0 / H) * r + (1.0 / H) - 1.0;
-    sxm[2 * t + 1] = 2.0 * (1.0 / W) * c + (1.0 / W) - 1.0;
-  }
-  __syncthreads();
-  const int pitch = M + 1;
-  for (long long p0 = (long long)blockIdx.x * KP_PIX; p0 < HW; p0 += (long long)gridDim.x * KP_PIX) {
-    // build K_nm tile: thread t -> pixel t%64, anchors (t/64)*M/4 ...
-    {
-      const int pl = threadIdx.x & (KP_PIX - 1), grp = threadIdx.x >> 6;
-      const long long p = p0 + pl;
-      if (p < HW) {
-        const int r = (int)(p / W), c = (int)(p % W);
-        double En[4];
-        for (int q = 0; q < 4; ++q) En[q] = img[(size_t)q * HW + p];
-        const double xr = 2.0 * (1.0 / H) * (double)r + (1.0 / H) - 1.0, xc = 2.0 * (1.0 / W) * (double)c + (1.0 / W) - 1.0;
-        for (int m = grp * (M / 4); m < (grp + 1) * (M / 4); ++m)
-          sK[pl * pitch + m] = cov_python_f64(xr, xc, En, sxm[2 * m], sxm[2 * m + 1], sEm + 4 * m, scale);
-      }
-    }
-    __syncthreads();
-    {
-      const int pl = threadIdx.x & (KP_PIX - 1), grp = threadIdx.x >> 6;
-      const long long p = p0 + pl;
-      if (p < HW) {
-        const int c0 = grp * (M / 4);
-        double acc[16];
-        for (int q = 0; q < 16; ++q) acc[q] = 0.0;
-        for (int m = 0; m < M; ++m) {
-          const double a = sK[pl * pitch + m];
-          for (int q = 0; q < M / 4; ++q) acc[q] = fma(a, sKinv[m * M + c0 + q], acc[q]);
-        }
-        double* o = out + ((size_t)b * HW + p) * M + c0;
-        for (int q = 0; q < M / 4; ++q) o[q] = acc[q];
-      }
-    }
-    __syncthreads();
-  }
-}
-
 }  // namespace como
 
 using namespace como;
@@ -485,33 +361,4 @@ extern "C" int como_b200_sampler_greedy(const float* dom_xy, const float* dom_E,
   for (int b = 0; b < B; ++b)
     cudaMemcpyAsync(count_out + b, &state[b].count, sizeof(int), cudaMemcpyDeviceToDevice, st);
   return check_launch("sampler_greedy");
-}
-
-extern "C" int como_b200_kmat_kmm(const double* cov_img, int32_t B, int32_t H, int32_t W, const double* coords_m,
-                                  int32_t M, double scale, double jitter, double* E_m, double* K_mm, void* stream) {
-  COMO_REQUIRE(cov_img && coords_m && E_m && K_mm, "kmat_kmm: null pointer argument");
-  COMO_REQUIRE(M >= 1 && M <= 1024, "kmat_kmm: bad M");
-  kmm_kernel<<<B, 256, (size_t)M * 6 * sizeof(double), (cudaStream_t)stream>>>(cov_img, H, W, coords_m, M, scale, jitter, E_m,
-                                                                               K_mm);
-  return check_launch("kmat_kmm");
-}
-
-extern "C" int como_b200_kmat_predictor(const double* cov_img, int32_t B, int32_t H, int32_t W, const double* coords_m,
-                                        const double* E_m, const double* Kmm_inv, int32_t M, double scale,
-                                        double* Knm_Kmminv, void* stream) {
-  COMO_REQUIRE(cov_img && coords_m && E_m && Kmm_inv && Knm_Kmminv, "kmat_predictor: null pointer argument");
-  COMO_REQUIRE(M >= 4 && M <= BA_MAXM && M % 4 == 0, "kmat_predictor: M must be a multiple of 4, <= 64");
-  const size_t smem = (size_t)(BA_MAXM * BA_MAXM + 6 * BA_MAXM + KP_PIX * (BA_MAXM + 1)) * sizeof(double);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(kmat_predictor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr = true;
-  }
-  const long long HW = (long long)H * W;
-  int per = (sm_count() * 3 + B - 1) / B;
-  const long long need = (HW + KP_PIX - 1) / KP_PIX;
-  if (per > need) per = (int)need;
-  kmat_predictor_kernel<<<dim3(per, B), 256, smem, (cudaStream_t)stream>>>(cov_img, H, W, coords_m, E_m, Kmm_inv, M, scale,
-                                                                          Knm_Kmminv);
-  return check_launch("kmat_predictor");
 }

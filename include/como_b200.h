@@ -205,6 +205,34 @@ int como_b200_kmat_predictor(const double* cov_img, int32_t B, int32_t H, int32_
                              const double* E_m, const double* Kmm_inv, int32_t M, double scale, double* Knm_Kmminv,
                              void* stream);
 
+/* Keyframe-creation path: calc_kernel_matrices + get_predictor at arbitrary test points
+ * (como/depth_cov/core/distill_depth.py:8-48) and the normal equations of distill_depth /
+ * distill_conditional_depth_with_scale_prior (distill_depth.py:51-82, 126-153; lstsq_chol utils/lin_alg.py:82-87).
+ * kmat_rows: rows (B,n,M) = K_nm K_mm^-1 at coords_n (B,n,2) [row,col] (fractional, border-clamped bilinear
+ *   covariance lookup); mask_n (B,n) optional (0 -> zero row); var_n (B,n) optional = K_nn - K_nm K_mm^-1 K_mn for
+ *   valid rows; var_min (B) optional = min over valid rows (the torch.min of get_predictor).
+ * weighted_gram (B=1): G (M,M) = sum_n w_n k_n k_n^T, h (M) = sum_n w_n y_n k_n, w_n = wscale / (var_n + var_add)
+ *   (var != NULL) or wscale; stats (2, optional) = [sum w, sum w y^2]; masked rows skipped.
+ * rows_residual (B=1): res_n = k_n . x - y_n; stats3 = [count, sum res, sum (res - mean)^2] over valid rows. */
+int como_b200_kmat_rows(const double* cov_img, int32_t B, int32_t H, int32_t W, const double* coords_m,
+                        const double* E_m, const double* Kmm_inv, int32_t M, double scale, const double* coords_n,
+                        const uint8_t* mask_n, int64_t n, double* rows, double* var_n, double* var_min, void* stream);
+int como_b200_weighted_gram(const double* rows, const double* y, const double* var, const uint8_t* mask, int64_t n,
+                            int32_t M, double var_add, double wscale, double* G, double* h, double* stats,
+                            void* stream);
+int como_b200_rows_residual(const double* rows, const double* x, const double* y, const uint8_t* mask, int64_t n,
+                            int32_t M, double* res, double* stats3, void* stream);
+/* track_and_init helpers (como/odom/frontend/corr.py:37-43, 17-29, 80-96, 116-152).
+ * reproject_dense: z_img (H,W) of the last keyframe, T_ji12 HOST row-major 3x4, intr4 HOST [fx,fy,cx,cy] ->
+ *   coords_j (H*W,2) [row,col], logz_j, z_j (H*W), mask (H*W) = inside [1, dim-1) and z_j > min_depth.
+ * sample_depth_gradmag: zero-padded bilinear lookups at n points of z_img (coords_z -> z_out) and of
+ *   |Scharr(log z_img)| (coords_g -> g_out); either pair may be NULL. */
+int como_b200_reproject_dense(const double* z_img, int32_t H, int32_t W, const double* T_ji12, const double* intr4,
+                              double min_depth, double* coords_j, double* logz_j, double* z_j, uint8_t* mask,
+                              void* stream);
+int como_b200_sample_depth_gradmag(const double* z_img, int32_t H, int32_t W, const double* coords_z,
+                                   const double* coords_g, int32_t n, double* z_out, double* g_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Tracker front-end (fp32).
  * ------------------------------------------------------------------------------------------ */

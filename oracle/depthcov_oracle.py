@@ -75,15 +75,22 @@ def _interp_cov(cov, x_norm):
 
 
 def sample_sparse_coords(cov, num_samples, max_stdev_thresh=-1e8, border=0, terminate_early=False, dist_thresh=0.0,
-                         signal_var=1.0, fixed_var=None, curr_coords=None):
-    """Greedy conditional-entropy anchor selection; returns (coords (1,k,2) long/float, domain_inds (1,k))."""
+                         signal_var=1.0, fixed_var=None, curr_coords=None, coords_domain=None):
+    """Greedy conditional-entropy anchor selection; returns (coords (1,k,2) long/float, domain_inds (1,k)).
+    coords_domain (1,d,2): explicit (fractional) candidate set instead of the bordered pixel grid
+    (samplers.py:68-74)."""
     cov = cov.float()
     b, _, h, w = cov.shape
     assert b == 1
-    rr, cc = torch.meshgrid(torch.arange(border, h - border), torch.arange(border, w - border), indexing="ij")
-    dom = torch.stack((rr.reshape(-1), cc.reshape(-1)), 1)[None]
-    dn = _normalize(dom, (h, w)).float()
-    Ed = torch.permute(cov[:, :, dom[0, :, 0], dom[0, :, 1]], (0, 2, 1)).reshape(1, -1, 2, 2).contiguous()
+    if coords_domain is None:
+        rr, cc = torch.meshgrid(torch.arange(border, h - border), torch.arange(border, w - border), indexing="ij")
+        dom = torch.stack((rr.reshape(-1), cc.reshape(-1)), 1)[None]
+        dn = _normalize(dom, (h, w)).float()
+        Ed = torch.permute(cov[:, :, dom[0, :, 0], dom[0, :, 1]], (0, 2, 1)).reshape(1, -1, 2, 2).contiguous()
+    else:
+        dom = coords_domain
+        dn = _normalize(dom, (h, w)).float()
+        Ed = _interp_cov(cov, dn).contiguous()
     d = dn.shape[1]
     n = min(num_samples, d)
     sv = float(signal_var)
@@ -153,13 +160,15 @@ def sample_sparse_coords(cov, num_samples, max_stdev_thresh=-1e8, border=0, term
 
 def cov_python(x1, E1, x2, E2, scale):
     """covariance.py:22-39 / kernels.py:22-89 in float64 with the float32-rounded coordinate difference."""
-    diff = (x1[:, :, None, :] - x2[:, None, :, :]).float().double()
+    dfl = (x1[:, :, None, :] - x2[:, None, :, :]).float()
+    diff = dfl.double()
+    sq = torch.square(dfl).double()  # torch.square of the float32 difference (kernels.py:27-29,37-39)
     s00 = E1[:, :, None, 0, 0] + E2[:, None, :, 0, 0]
     s01 = E1[:, :, None, 0, 1] + E2[:, None, :, 0, 1]
     s11 = E1[:, :, None, 1, 1] + E2[:, None, :, 1, 1]
-    Q = s11 * diff[..., 0] ** 2
+    Q = s11 * sq[..., 0]
     Q = Q + (-2 * s01 * diff[..., 0] * diff[..., 1])
-    Q = Q + s00 * diff[..., 1] ** 2
+    Q = Q + s00 * sq[..., 1]
     det = s00 * s11 - s01 ** 2
     Q = Q / det * 0.5
     r1 = (E1[..., 0, 0] * E1[..., 1, 1] - E1[..., 0, 1] * E1[..., 1, 0]) ** 0.25

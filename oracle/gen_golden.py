@@ -378,6 +378,85 @@ def gen_cov(name):
     print(name, "size %.2f MB" % (os.path.getsize(os.path.join(GOLD, name + ".npz")) / 1e6))
 
 
+def gen_kfinit(name, H, W, NKF, M, iters=2):
+    """Keyframe-creation golden: inputs and outputs of the LAST track_and_init call of a window
+    built by the reference (corr.py:60-242), with the intermediate results of distill_depth_from_scratch /
+    distill_conditional_depth_from_scratch and of the two sampler calls.  A couple of BA iterations run between
+    keyframes so that depths and poses are not the trivial initial ones."""
+    ref_harness.load_reference()
+    import como.odom.Mapping as MP
+    import como.odom.frontend.corr as CR
+
+    cap = []
+    orig_tai = MP.track_and_init
+    orig_dd, orig_dc, orig_ss = CR.distill_depth_from_scratch, CR.distill_conditional_depth_from_scratch, CR.sample_sparse_coords
+
+    def tai_hook(*a, **k):
+        rec = {"in": [(_np(x).copy() if torch.is_tensor(x) else x) for x in a[:7]], "corr": dict(a[8]), "samp": dict(a[9]),
+               "rgb_img_size": tuple(a[10]), "sub": {}}
+        cap.append(rec)
+        r = orig_tai(*a, **k)
+        rec["out"] = [_np(x).copy() for x in r]
+        return r
+
+    def dd_hook(*a, **k):
+        r = orig_dd(*a, **k)
+        cap[-1]["sub"]["dd_coords_m"] = _np(a[0]).copy()
+        cap[-1]["sub"]["dd_logz_m"] = _np(r[0]).copy()
+        cap[-1]["sub"]["dd_res_std"] = float(torch.std(r[1]))
+        cap[-1]["sub"]["dd_n"] = int(r[1].shape[1])
+        return r
+
+    def dc_hook(*a, **k):
+        r = orig_dc(*a, **k)
+        cap[-1]["sub"]["dc_coords_m"] = _np(a[0]).copy()
+        cap[-1]["sub"]["dc_logz_2"] = _np(r).copy()
+        return r
+
+    def ss_hook(*a, **k):
+        r = orig_ss(*a, **k)
+        i = sum(1 for q in cap[-1]["sub"] if q.startswith("ss") and q.endswith("_coords"))
+        cap[-1]["sub"][f"ss{i}_coords"] = _np(r[0]).copy()
+        cap[-1]["sub"][f"ss{i}_inds"] = _np(r[1]).copy()
+        return r
+
+    MP.track_and_init = tai_hook
+    CR.distill_depth_from_scratch, CR.distill_conditional_depth_from_scratch, CR.sample_sparse_coords = dd_hook, dc_hook, ss_hook
+    orig_add = MP.Mapping.add_keyframe
+
+    def add_hook(self, *a, **k):
+        r = orig_add(self, *a, **k)
+        for _ in range(iters):
+            self.iterate()
+        return r
+
+    MP.Mapping.add_keyframe = add_hook
+    try:
+        m, cfg = build_reference_window(H, W, NKF, 0, M, NKF + 1)
+    finally:
+        MP.track_and_init = orig_tai
+        CR.distill_depth_from_scratch, CR.distill_conditional_depth_from_scratch, CR.sample_sparse_coords = orig_dd, orig_dc, orig_ss
+        MP.Mapping.add_keyframe = orig_add
+    out = {"H": H, "W": W, "M": M, "ncalls": len(cap), "gp_scale": float(m.model.get_scale(-1))}
+    names = ["pose1", "pose2", "coords_m1", "z_m1", "z_img1", "cov_params_img2", "K"]
+    for ci, rec in enumerate(cap):
+        pre = f"c{ci}_"
+        for nm, v in zip(names, rec["in"]):
+            out[pre + nm] = v
+        for nm, v in zip(["coords_2", "z2", "corr_mask", "coords_all", "z_all"], rec["out"]):
+            out[pre + nm] = v
+        for k, v in rec["sub"].items():
+            out[pre + k] = v
+        out[pre + "rgb_img_size"] = np.array(rec["rgb_img_size"])
+    for k, v in cap[-1]["corr"].items():
+        out["corr_" + k] = v
+    for k, v in cap[-1]["samp"].items():
+        out["samp_" + k] = v
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "calls", len(cap), [(int(r["out"][0].shape[1]), int(r["out"][3].shape[1]), int(r["out"][2].sum())) for r in cap],
+          "size %.2f MB" % (os.path.getsize(os.path.join(GOLD, name + ".npz")) / 1e6))
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(GOLD, exist_ok=True)
@@ -390,6 +469,8 @@ def main():
     if what in ("ba", "all"):
         gen_ba("ba_k4_notfull", 48, 64, 4, 3, 16, 5)
         gen_ba("ba_k4_full", 48, 64, 5, 3, 16, 4)
+    if what in ("kfinit", "all"):
+        gen_kfinit("kfinit_64x48", 48, 64, 4, 16)
 
 
 if __name__ == "__main__":
