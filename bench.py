@@ -5,6 +5,8 @@ Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl refere
 torchrun for N>1 (one rank per GPU).  Prints ONE JSON line on rank 0.
 
 Workloads (config.workload):
+  ba_window (default) one Gauss-Newton iteration of a 32-keyframe 640x480 window (BASELINE.json metric).
+  kf_init   one keyframe creation (track_and_init) at 640x480 with 64 anchors.
   track640  B independent 640x480 / 4-level frame-to-keyframe tracking problems per GPU, one cooperative
             launch per step; metric = Gauss-Newton iterations per second (sum over problems).
 A "step" is one pass of the hot path over one batch of synthetic input.  The batch (B x 21 MB of
@@ -372,6 +374,150 @@ def run_ba_ours(args, rank, world, device):
     return res, (s, snap), cfg
 
 
+# --------------------------------------------------------------------------------------------- keyframe-creation workload
+FP64_PEAK_TFLOPS = 37.1   # measured on B200 with scripts/micro/dmma_bench.cu (DFMA == DMMA.8x8x4 == 64 FMA/clk/SM)
+KFINIT_CORR = dict(corr_mode="logz", corr_thresh=3.0e-2, distill_with_prior=True, min_obs_depth=0.0,
+                   logz_grad_mag_thresh=7.0e-2)                                    # config/como.yml:59-64
+KFINIT_SAMP = dict(mode="greedy_conditional_entropy", max_num_coords=64, max_stdev_thresh=1.0e-2, border=3,
+                   fixed_var=0.0, dist_thresh=1.0e-1)                              # config/como.yml:52-58
+
+
+def build_kfinit_case(device, seed=0, H=480, W=640, M=64):
+    """Synthetic keyframe-creation inputs (SURVEY 8d scene): depth 2 + 0.5 sin cos, camera translating +x by 6 px,
+    covariance image with long length scales, anchors of the last keyframe chosen by the sampler itself."""
+    from como_b200 import synth
+    from como_b200.depth_cov.core.samplers import sample_sparse_coords
+
+    cov1 = synth.make_cov_image_wide(H, W, seed=seed).to(device)
+    cov2 = synth.make_cov_image_wide(H, W, seed=seed + 100).to(device)
+    z_img = synth.make_depth(H, W, dtype=torch.float64).to(device).reshape(1, 1, H, W)
+    Km = synth.make_intrinsics(H, W, dtype=torch.float64).to(device).reshape(1, 3, 3)
+    scale = 0.086
+    coords_m1, _ = sample_sparse_coords(cov1, M, "greedy_conditional_entropy", 1e-2, border=3, dist_thresh=0.1,
+                                        signal_var=scale, fixed_var=0.0)
+    z_m1 = z_img[0, 0, coords_m1[0, :, 0], coords_m1[0, :, 1]].reshape(1, -1, 1)
+    pose1 = torch.eye(4, dtype=torch.float64, device=device)[None]
+    pose2 = pose1.clone()
+    pose2[0, 0, 3] = 6.0 * 2.0 / float(Km[0, 0, 0])
+    pose2[0, 1, 3] = 0.0013
+    return dict(pose1=pose1, pose2=pose2, coords_m1=coords_m1.double(), z_m1=z_m1, z_img1=z_img, cov2=cov2, K=Km,
+                scale=scale, H=H, W=W, M=M)
+
+
+def run_kfinit_ours(args, rank, world, device):
+    from como_b200 import _lib
+    from como_b200.depth_cov.core import distill_depth as DD
+    from como_b200.odom.frontend.corr import track_and_init
+
+    c = build_kfinit_case(device, seed=rank)
+    H, W, M = c["H"], c["W"], c["M"]
+
+    def step(cov2=None, z_img=None):
+        return track_and_init(c["pose1"], c["pose2"], c["coords_m1"], c["z_m1"], c["z_img1"] if z_img is None else z_img,
+                              c["cov2"] if cov2 is None else cov2, c["K"], c["scale"], KFINIT_CORR, KFINIT_SAMP, (H, W))
+
+    for _ in range(args.warmup):
+        out = step()
+    torch.cuda.synchronize()
+    barrier(world)
+    sampler = ClockSampler(device.index)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    barrier(world)
+    ms_max = allreduce_max(ev0.elapsed_time(ev1), world, device)
+
+    # end to end: covariance + depth images arrive from pinned host memory, the new anchors go back
+    cov_host = c["cov2"].cpu().pin_memory()
+    z_host = c["z_img1"].cpu().pin_memory()
+    out_host = torch.empty(M * 3 + M, dtype=torch.float64).pin_memory()
+
+    def e2e_step():
+        cov2 = cov_host.to(device, non_blocking=True)
+        zi = z_host.to(device, non_blocking=True)
+        c2, z2, mask, call, zall = step(cov2, zi)
+        n = call.shape[1]
+        out_host[:2 * n].copy_(call.reshape(-1), non_blocking=True)
+        out_host[2 * M:2 * M + n].copy_(zall.reshape(-1), non_blocking=True)
+        out_host[3 * M:3 * M + mask.numel()].copy_(mask.to(torch.float64), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    barrier(world)
+    ev0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    ev1.record()
+    torch.cuda.synchronize()
+    barrier(world)
+    e_ms = allreduce_max(ev0.elapsed_time(ev1), world, device)
+
+    # roofline of the dominant kernel (K-matrix / predictor rows with variance), timed alone
+    n = H * W
+    coords_n = torch.stack((torch.rand(n, device=device) * (H - 1), torch.rand(n, device=device) * (W - 1)), -1)[None].double()
+    mask = torch.ones(n, dtype=torch.uint8, device=device)
+    for _ in range(3):
+        DD.predictor_rows(c["coords_m1"], coords_n, mask, c["cov2"], c["scale"], True)
+    E_m = torch.empty(1, M, 4, dtype=torch.float64, device=device)
+    K_mm = torch.empty(1, M, M, dtype=torch.float64, device=device)
+    st = _lib.stream_ptr(device)
+    _lib.kmat_kmm(_lib.ptr(c["cov2"]), 1, H, W, _lib.ptr(c["coords_m1"]), M, c["scale"], 0.0, _lib.ptr(E_m), _lib.ptr(K_mm), st)
+    Kinv = torch.linalg.inv(K_mm).contiguous()
+    rows = torch.empty(n, M, dtype=torch.float64, device=device)
+    var = torch.empty(n, dtype=torch.float64, device=device)
+    vmin = torch.empty(1, dtype=torch.float64, device=device)
+    reps = 10
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(reps):
+        _lib.kmat_rows(_lib.ptr(c["cov2"]), 1, H, W, _lib.ptr(c["coords_m1"]), _lib.ptr(E_m), _lib.ptr(Kinv), M, c["scale"],
+                       _lib.ptr(coords_n), _lib.ptr(mask), n, _lib.ptr(rows), _lib.ptr(var), _lib.ptr(vmin), st)
+    ev1.record()
+    torch.cuda.synchronize()
+    kernel_ms = ev0.elapsed_time(ev1) / reps
+    alg_flop = 2.0 * n * M * M + 30.0 * n * M   # SURVEY 8d: GEMM 2 n m^2 + ~30 flop per kernel evaluation
+    ach = alg_flop / (kernel_ms * 1e-3) * 1e-12
+    res = {
+        "metric": "keyframe creations/sec at 640x480 (track_and_init, 64 anchors)", "value": world * args.steps / (ms_max * 1e-3),
+        "unit": "KF/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "kf_init", "resolution": "640x480", "anchors": M, "dense_points": n,
+                   "new_anchors": int(out[0].shape[1]), "correspondences": int(out[2].sum()),
+                   "l2": "predictor rows (157 MB per pass, written once and read twice) exceed the 126 MB L2; no flush",
+                   "parallelism": f"replicas x{world} (independent keyframes, no collective)"},
+        "e2e": {"value": world * args.steps / (e_ms * 1e-3), "unit": "KF/s",
+                "h2d_bytes_per_step": int(cov_host.numel() + z_host.numel()) * 8, "d2h_bytes_per_step": int(out_host.numel()) * 8},
+        "gpu_launches": None,
+        "roofline": {"kernel": "kmat_rows_kernel", "bound": "tensor", "achieved": ach, "peak": FP64_PEAK_TFLOPS,
+                     "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS, "traffic": None,
+                     "peak_source": "fp64 DFMA/DMMA peak measured with scripts/micro/dmma_bench.cu (MEASURED_PEAKS.json has no fp64 entry)",
+                     "alg_flop_per_launch": alg_flop, "launch_ms": kernel_ms},
+        "clocks": clocks,
+    }
+    return res, c
+
+
+def cpu_kfinit_baseline(c):
+    """Oracle port of track_and_init on the host cores, same inputs."""
+    from oracle import kfinit_oracle as KO
+
+    cpu = {k: (v.cpu() if isinstance(v, torch.Tensor) else v) for k, v in c.items()}
+    t0 = time.time()
+    KO.track_and_init(cpu["pose1"], cpu["pose2"], cpu["coords_m1"], cpu["z_m1"], cpu["z_img1"], cpu["cov2"], cpu["K"],
+                      cpu["scale"], KFINIT_CORR, KFINIT_SAMP)
+    dt = time.time() - t0
+    return {"value": 1.0 / dt, "unit": "KF/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"1 keyframe creation on the same inputs ({dt:.1f} s)"}
+
+
 def snapshot_small(s):
     """Host copy of everything but the big constant tensors (those are copied lazily by the CPU baseline)."""
     sc = {}
@@ -432,7 +578,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ba_window", choices=["ba_window", "track640"])
+    ap.add_argument("--workload", default="ba_window", choices=["ba_window", "track640", "kf_init"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--kf", type=int, default=BA_K)
     ap.add_argument("--oneway", type=int, default=BA_R)
@@ -513,6 +659,14 @@ def main():
         res, cases = run_track_ours(args, rank, world, device)
         if rank == 0:
             res["cpu_baseline"] = cpu_track_baseline(cases) if world == 1 else None
+            print(json.dumps(res))
+    elif args.workload == "kf_init":
+        res, case = run_kfinit_ours(args, rank, world, device)
+        if rank == 0:
+            try:
+                res["cpu_baseline"] = cpu_kfinit_baseline(case) if world == 1 else None
+            except Exception as ex:
+                res["cpu_baseline"] = {"error": repr(ex)[:200]}
             print(json.dumps(res))
     else:
         res, s, cfg = run_ba_ours(args, rank, world, device)

@@ -10,8 +10,10 @@ What is replaced (reference name -> como_b200 implementation):
   como.odom.frontend.photo_tracking.photo_tracking_pyr / precalc_jacobians (also as imported by como.odom.Tracking)
   como.odom.Mapping.Mapping.iterate / store_vars / prep_predictor
   como.odom.backend.linear_system.solve_system
-Everything else (two-frame initialisation, keyframe creation, correspondence search, UNet) keeps running the
-reference's own Python on the same device.  Requires tracking.dtype float / mapping.dtype double, color gray.
+  como.odom.frontend.corr.track_and_init (also as imported by como.odom.Mapping) and
+  como.depth_cov.core.distill_depth.distill_depth_from_scratch / distill_conditional_depth_from_scratch
+Everything else (two-frame initialisation, UNet, orchestration) keeps running the reference's own Python on the
+same device.  Requires tracking.dtype float / mapping.dtype double, color gray.
 """
 import sys
 
@@ -52,8 +54,20 @@ def install():
         scale = float(self.model.cov_modules[-1].get_scale())
         return b_pred.prep_predictor(cov_params_img, coords_m, scale, photo_img_size=self.kf_img_and_grads.shape[-2:])
 
+    import como.depth_cov.core.distill_depth as ref_dd
+    import como.odom.frontend.corr as ref_corr
+
+    from como_b200.depth_cov.core import distill_depth as b_dd
+    from como_b200.odom.frontend import corr as b_corr
+
+    ref_corr.track_and_init = b_corr.track_and_init
+    ref_mapping.track_and_init = b_corr.track_and_init
+    for name in ("distill_depth_from_scratch", "distill_conditional_depth_from_scratch"):
+        setattr(ref_dd, name, getattr(b_dd, name))
+        setattr(ref_corr, name, getattr(b_dd, name))
     ref_mapping.Mapping.iterate = iterate
     ref_mapping.Mapping.store_vars = store_vars
     ref_mapping.Mapping.prep_predictor = prep_predictor
     return {"patched": ["como_backends", "sample_sparse_coords", "photo_tracking_pyr", "precalc_jacobians",
-                        "Mapping.iterate", "Mapping.store_vars", "Mapping.prep_predictor", "solve_system"]}
+                        "Mapping.iterate", "Mapping.store_vars", "Mapping.prep_predictor", "solve_system",
+                        "track_and_init", "distill_depth_from_scratch", "distill_conditional_depth_from_scratch"]}
