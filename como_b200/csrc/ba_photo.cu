@@ -162,25 +162,56 @@ constexpr int STACK_ROWS = 48;       // 8 (D) + 1 (B) + 8*TG (E) = 41, padded
 constexpr int PART_STRIDE = BA_MAXM * BA_MAXM + STACK_ROWS * BA_MAXM + TG * SMALL_STRIDE;  // doubles per unit
 
 constexpr int XST = 4;               // stages of the predictor-row ring
-constexpr int EPITCH = 8 * TG + 1;
-constexpr int DPITCH = 11;
+// Shared-memory pitches are == 4 (mod 16) doubles: a DMMA fragment load touches 4 consecutive rows x 8 columns
+// and lands on 16 distinct 8-byte banks per half warp.
+constexpr int XPITCH = 68;           // predictor rows
+constexpr int CPITCH = 52;           // per-pixel coefficients: [D(8) | B | alpha J_j (8 TG) | pad(7) | A | pad(3)]
+constexpr int C_B = 8, C_E = 9, C_A = 48;
+constexpr int ZPITCH = 20;           // [J_i(8) | J_j(8) | r | pad(3)]
 
 struct BAUnit {
   int ref, pix_begin, pix_end, tgt_begin, tgt_end, primary, pad0, pad1;
 };
 
 struct AccumSmem {
-  double X[XST][TP][BA_MAXM];        // predictor rows (bulk-copied), XST-deep ring: rows are gathered from HBM
+  double X[XST][TP][XPITCH];         // predictor rows (bulk-copied), XST-deep ring: rows are gathered from HBM
   double refz[2][TP][REF_STRIDE];    // z_n, q_n of a tile (one bulk copy), double buffered, one tile ahead of X
-  double Z[2][TG][TP][ZW];           // [J_i | J_j | r] of the unit's own target group
-  double E[2][TP][EPITCH];           // alpha * J_j, row = 8 * target + component (pitch padded: no bank conflicts)
-  double dba[2][TP][DPITCH];         // per pixel: A = sum alpha^2, B = sum alpha r, D[8] = sum alpha J_i
-  double zero[2];
+  double Z[2][TG][TP + 1][ZPITCH];   // [J_i | J_j | r] of the unit's own target group (+1 row: fragment overrun)
+  double C[2][TP][CPITCH];           // stack coefficients and A = sum alpha^2 per pixel
   unsigned long long mbarX[XST], mbarR[2];
 };
 
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
 __device__ __forceinline__ int tri_index(int a, int b) {  // a <= b < 17 -> index in the packed upper triangle
   return a * ZW - (a * (a - 1)) / 2 + (b - a);
+}
+
+// One k-step (4 pixels) of the warp's 9 Gram tiles and 12 stack tiles; Q = warp quarter (static tile lists).
+template <int Q>
+__device__ __forceinline__ void accum_gram_step(double (&accG)[9][2], const double (&xf)[8], double Ap) {
+  constexpr int RA = 7 - Q, RB = Q;
+  const double fa = Ap * xf[RA], fb = Ap * xf[RB];
+#pragma unroll
+  for (int c = 0; c <= RA; ++c) dmma884(accG[c][0], accG[c][1], fa, xf[c]);                    // tiles (RA, c)
+#pragma unroll
+  for (int c = 0; c <= RB; ++c) dmma884(accG[RA + 1 + c][0], accG[RA + 1 + c][1], fb, xf[c]);  // tiles (RB, c)
+}
+template <int Q>
+__device__ __forceinline__ void accum_stack_step(double (&accS)[12][2], const double (&xf)[8], const double* cr, int s_lo,
+                                                 int s_top) {
+#pragma unroll
+  for (int sr = 0; sr < 6; ++sr) {
+    if (sr >= s_lo && sr < s_top) {
+      const double cf = cr[8 * sr];
+      dmma884(accS[2 * sr][0], accS[2 * sr][1], cf, xf[2 * Q]);
+      dmma884(accS[2 * sr + 1][0], accS[2 * sr + 1][1], cf, xf[2 * Q + 1]);
+    }
+  }
 }
 
 // Warp-specialised: the coefficient warps (8-15) rebuild the per-(target,pixel) Jacobians of tile t+1 while
@@ -212,10 +243,10 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
     mbar_init(&S.mbarR[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // zero once: padding columns of X (bulk copies only write the first M columns), dba, the zero slot
-  for (int t = tid; t < XST * TP * BA_MAXM; t += AC_THREADS) (&S.X[0][0][0])[t] = 0.0;
-  for (int t = tid; t < 2 * TP * DPITCH; t += AC_THREADS) (&S.dba[0][0][0])[t] = 0.0;
-  if (tid < 2) S.zero[tid] = 0.0;
+  // zero once: X (bulk copies only write the first M columns of the rows of a tile), the padding of Z and C
+  for (int t = tid; t < XST * TP * XPITCH; t += AC_THREADS) (&S.X[0][0][0])[t] = 0.0;
+  for (int t = tid; t < 2 * TG * (TP + 1) * ZPITCH; t += AC_THREADS) (&S.Z[0][0][0][0])[t] = 0.0;
+  for (int t = tid; t < 2 * TP * CPITCH; t += AC_THREADS) (&S.C[0][0][0])[t] = 0.0;
   __syncthreads();
 
   auto issue_X = [&](int tile, int buf) {      // called by warp 0 (product role): lane <-> predictor row
@@ -346,17 +377,17 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
           for (int q = 0; q < 8; ++q) {
             S.Z[buf][tt][pl][q] = Ji[q];
             S.Z[buf][tt][pl][8 + q] = Jj[q];
-            S.E[buf][pl][8 * tt + q] = alpha * Jj[q];
+            S.C[buf][pl][C_E + 8 * tt + q] = alpha * Jj[q];
           }
           S.Z[buf][tt][pl][16] = rs;
         }
       }
       if (primary && (pa2 != 0.0 || par != 0.0)) {
-        double* dst = &S.dba[buf][pl][0];
-        atomicAdd(dst + 0, pa2);
-        atomicAdd(dst + 1, par);
+        double* dst = &S.C[buf][pl][0];
+        atomicAdd(dst + C_A, pa2);
+        atomicAdd(dst + C_B, par);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) atomicAdd(dst + 2 + q, pD[q]);
+        for (int q = 0; q < 8; ++q) atomicAdd(dst + q, pD[q]);
       }
     };
 
@@ -374,8 +405,18 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
     for (int tile = 0; tile < ntiles; ++tile) {
       const int buf = tile & 1;
       if (tile + 1 < ntiles) {
-        // dba[buf^1] was consumed by the product role during the previous iteration
-        for (int t = rt; t < TP * DPITCH; t += AC_COEF) (&S.dba[buf ^ 1][0][0])[t] = 0.0;
+        // the accumulated columns (D, B, A) of C[buf^1] were consumed by the product role during the previous
+        // iteration: thread -> (pixel, column group)
+        {
+          const int px = rt & 31, part = rt >> 5;   // 4 parts: D[0..3], D[4..7], B, A
+          double* dst = &S.C[buf ^ 1][px][0];
+          if (part < 2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[4 * part + q] = 0.0;
+          } else {
+            dst[part == 2 ? C_B : C_A] = 0.0;
+          }
+        }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait(&S.mbarR[buf ^ 1], ((tile + 1) >> 1) & 1);
         build(tile + 1, buf ^ 1);
@@ -391,137 +432,139 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
   }
 
   // ================================================================== product role
-  // 256 threads, 16 x 16 register tiling: thread (ty,tx) owns the 4x4 block (ty,tx) of G = sum_p A_p x_p x_p^T
-  // and 4 columns of the stack rows ty, ty+16, ty+32 (rows 0..7 D, 8 B, 9 + 8 t + q -> alpha J_j of target t).
-  // The pixel loop is software pipelined: operands of pixel p+1 are loaded while pixel p is multiplied.
-  const int ty = rt >> 4, tx = rt & 15;
-  constexpr int NSR = STACK_ROWS / 16;   // 3 stack rows per thread
-  constexpr int NZ = (TG * NSMALL + AC_ROLE - 1) / AC_ROLE;   // small-Gram outputs per thread (3)
-  const int row_hi = 9 + 8 * ntgt;       // one past the last live stack row
-  double accG[4][4], accS[NSR][4], accZ[NZ];
+  // FP64 tensor path (mma.sync m8n8k4, SASS DMMA.8x8x4): per 32-pixel tile the sums over pixels are three GEMMs
+  // with the pixel index as K dimension,
+  //   G  (64 x 64, lower tiles)  = (A X)^T X            stack (48 x 64) = C^T X           Z_t (17 x 17) = Z_t^T Z_t,
+  // 36 + 48 + 24 = 108 output tiles of 8 x 8.  Warp w = (quarter q = w & 3, pixel half h = w >> 2) owns 27 tiles
+  // (54 accumulator registers) and runs them over 4 of the 8 k-steps of every tile:
+  //   G rows {7-q, q} (9 tiles), stack columns {2q, 2q+1} (12 tiles), small Gram of target q (6 tiles);
+  // 18 conflict-free fragment loads feed 27 DMMAs per k-step.  The two pixel halves are summed at the end.
+  {
+    const int warp = rt >> 5, lane = rt & 31;
+    const int g4 = lane >> 2, l4 = lane & 3;
+    const int q = warp & 3, h = warp >> 2;
+    const int ra = 7 - q, rb = q;
+    const bool do_z = q < ntgt;
+    const int s_lo = primary ? 0 : 1;                       // stack rows 0..7 (D) exist for the primary unit only
+    const int s_top = min(6, ntgt + 2);                     // rows >= 9 + 8 ntgt are empty
+    double accG[9][2], accS[12][2], accZ[6][2];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+    for (int t = 0; t < 9; ++t) accG[t][0] = accG[t][1] = 0.0;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) accG[a][b] = 0.0;
+    for (int t = 0; t < 12; ++t) accS[t][0] = accS[t][1] = 0.0;
 #pragma unroll
-  for (int a = 0; a < NSR; ++a)
+    for (int t = 0; t < 6; ++t) accZ[t][0] = accZ[t][1] = 0.0;
+
+    if (tid < 32)
+      for (int t = 0; t < XST - 1 && t < ntiles; ++t) issue_X(t, t);
+    __syncthreads();   // pairs with the coefficient role's prologue barrier
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const int buf = tile & 1;
+      const int xs = tile % XST;
+      // stage (tile + XST - 1) % XST held tile - 1, which every product thread finished before the last barrier
+      if (tile + XST - 1 < ntiles && tid < 32) issue_X(tile + XST - 1, (tile + XST - 1) % XST);
+      mbar_wait(&S.mbarX[xs], (tile / XST) & 1);
+#pragma unroll 2
+      for (int ks = 0; ks < 4; ++ks) {
+        const int prow = 16 * h + 4 * ks + l4;              // pixel row of this lane's fragment elements
+        const double* xr = &S.X[xs][prow][g4];
+        const double* cr = &S.C[buf][prow][g4];
+        double xf[8];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) accS[a][b] = 0.0;
-#pragma unroll
-  for (int a = 0; a < NZ; ++a) accZ[a] = 0.0;
-  // small-Gram outputs owned by this thread: o = rt + 256 a -> (target, row, col) of the packed 17x17 triangle
-  int zmap[NZ];
-#pragma unroll
-  for (int a = 0; a < NZ; ++a) {
-    const int o = rt + AC_ROLE * a;
-    const int tg = o / NSMALL, idx = o % NSMALL;
-    int ra = 0, rem = idx;
-    while (rem >= ZW - ra) {
-      rem -= ZW - ra;
-      ++ra;
-    }
-    zmap[a] = (tg < ntgt) ? ((tg << 16) | (ra << 8) | (ra + rem)) : -1;
-  }
-  // which of this thread's stack rows are live, and where their coefficients sit (offsets inside E / dba)
-  bool live[NSR];
-  int coff[NSR], cstr[NSR];
-  bool from_dba[NSR];
-#pragma unroll
-  for (int a = 0; a < NSR; ++a) {
-    const int row = ty + 16 * a;
-    from_dba[a] = row < 9;
-    live[a] = from_dba[a] ? primary : (row < row_hi);
-    coff[a] = from_dba[a] ? (row < 8 ? 2 + row : 1) : (row - 9);
-    cstr[a] = from_dba[a] ? DPITCH : EPITCH;
-  }
-  if (tid < 32)
-    for (int q = 0; q < XST - 1 && q < ntiles; ++q) issue_X(q, q);
-  __syncthreads();   // pairs with the coefficient role's prologue barrier
-  for (int tile = 0; tile < ntiles; ++tile) {
-    const int buf = tile & 1;
-    const int xs = tile % XST;
-    // stage (tile + XST - 1) % XST held tile - 1, which every product thread finished before the last barrier
-    if (tile + XST - 1 < ntiles && tid < 32) issue_X(tile + XST - 1, (tile + XST - 1) % XST);
-    const int nb = un.pix_begin + tile * TP;
-    const int npx = min(TP, un.pix_end - nb);
-    mbar_wait(&S.mbarX[xs], (tile / XST) & 1);
-    const double* xrow = &S.X[xs][0][0];
-    const double* cbase[NSR];
-#pragma unroll
-    for (int a = 0; a < NSR; ++a)
-      cbase[a] = live[a] ? ((from_dba[a] ? &S.dba[buf][0][0] : &S.E[buf][0][0]) + coff[a]) : &S.zero[0];
-    // operands of pixel 0
-    double4 xb = *reinterpret_cast<const double4*>(xrow + 4 * tx);
-    double4 xa = *reinterpret_cast<const double4*>(xrow + 4 * ty);
-    double Acur = S.dba[buf][0][0];
-    double cf[NSR];
-#pragma unroll
-    for (int a = 0; a < NSR; ++a) cf[a] = cbase[a][0];
-#pragma unroll 4
-    for (int p = 0; p < npx; ++p) {
-      // prefetch pixel p+1 (row TP-1 is re-read harmlessly on the last pixel)
-      const int pn = min(p + 1, TP - 1);
-      const double4 xb_n = *reinterpret_cast<const double4*>(xrow + pn * BA_MAXM + 4 * tx);
-      const double4 xa_n = *reinterpret_cast<const double4*>(xrow + pn * BA_MAXM + 4 * ty);
-      const double A_n = S.dba[buf][pn][0];
-      double cf_n[NSR];
-#pragma unroll
-      for (int a = 0; a < NSR; ++a) cf_n[a] = live[a] ? cbase[a][pn * cstr[a]] : 0.0;
-      const double b4[4] = {xb.x, xb.y, xb.z, xb.w};
-      if (primary) {
-        const double a4[4] = {Acur * xa.x, Acur * xa.y, Acur * xa.z, Acur * xa.w};
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) accG[a][b] += a4[a] * b4[b];
-      }
-#pragma unroll
-      for (int a = 0; a < NSR; ++a) {
-        if (live[a]) {
-#pragma unroll
-          for (int b = 0; b < 4; ++b) accS[a][b] += cf[a] * b4[b];
+        for (int c = 0; c < 8; ++c) xf[c] = xr[8 * c];
+        if (primary) {
+          const double Ap = S.C[buf][prow][C_A];
+          switch (q) {   // warp-uniform
+            case 0: accum_gram_step<0>(accG, xf, Ap); break;
+            case 1: accum_gram_step<1>(accG, xf, Ap); break;
+            case 2: accum_gram_step<2>(accG, xf, Ap); break;
+            default: accum_gram_step<3>(accG, xf, Ap); break;
+          }
+        }
+        switch (q) {
+          case 0: accum_stack_step<0>(accS, xf, cr, s_lo, s_top); break;
+          case 1: accum_stack_step<1>(accS, xf, cr, s_lo, s_top); break;
+          case 2: accum_stack_step<2>(accS, xf, cr, s_lo, s_top); break;
+          default: accum_stack_step<3>(accS, xf, cr, s_lo, s_top); break;
+        }
+        if (do_z) {
+          const double* zr = &S.Z[buf][q][prow][g4];
+          const double z0 = zr[0], z1 = zr[8], z2 = zr[16];
+          dmma884(accZ[0][0], accZ[0][1], z0, z0);   // (0,0)
+          dmma884(accZ[1][0], accZ[1][1], z1, z0);   // (1,0)
+          dmma884(accZ[2][0], accZ[2][1], z1, z1);   // (1,1)
+          dmma884(accZ[3][0], accZ[3][1], z2, z0);   // (2,0)
+          dmma884(accZ[4][0], accZ[4][1], z2, z1);   // (2,1)
+          dmma884(accZ[5][0], accZ[5][1], z2, z2);   // (2,2)
         }
       }
-      xb = xb_n;
-      xa = xa_n;
-      Acur = A_n;
-#pragma unroll
-      for (int a = 0; a < NSR; ++a) cf[a] = cf_n[a];
+      __syncthreads();
     }
-    // small Grams
+
+    // ---------------- combine the two pixel halves (through the idle X ring) and write the unit's partial sums;
+    // the scatter kernels read full G / all stack rows / the packed upper triangle of the 17x17 Grams.
+    double* xch = &S.X[0][0][0];                    // 4 quarters x 27 tiles x 64 doubles = 55 KB < sizeof(S.X)
+    if (h == 1) {
+      double* dst = xch + ((size_t)q * 27) * 64 + 2 * lane;
 #pragma unroll
-    for (int a = 0; a < NZ; ++a) {
-      if (zmap[a] >= 0) {
-        const double* za = &S.Z[buf][zmap[a] >> 16][0][(zmap[a] >> 8) & 0xff];
-        const double* zb = &S.Z[buf][zmap[a] >> 16][0][zmap[a] & 0xff];
-        double sacc = 0.0;
-#pragma unroll 8
-        for (int p = 0; p < npx; ++p) sacc += za[p * ZW] * zb[p * ZW];
-        accZ[a] += sacc;
+      for (int t = 0; t < 9; ++t) *reinterpret_cast<double2*>(dst + t * 64) = make_double2(accG[t][0], accG[t][1]);
+#pragma unroll
+      for (int t = 0; t < 12; ++t) *reinterpret_cast<double2*>(dst + (9 + t) * 64) = make_double2(accS[t][0], accS[t][1]);
+#pragma unroll
+      for (int t = 0; t < 6; ++t) *reinterpret_cast<double2*>(dst + (21 + t) * 64) = make_double2(accZ[t][0], accZ[t][1]);
+    }
+    asm volatile("bar.sync 2, 256;" ::: "memory");   // product role only (the coefficient warps have left)
+    if (h == 0) {
+      const double* src = xch + ((size_t)q * 27) * 64 + 2 * lane;
+      double* out = partial + (size_t)blockIdx.x * PART_STRIDE;
+      double* outS = out + BA_MAXM * BA_MAXM;
+      double* outZ = outS + STACK_ROWS * BA_MAXM;
+      // C fragment: element (8 r + g4, 8 c + 2 l4 + {0,1})
+      if (primary) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const double2 o = *reinterpret_cast<const double2*>(src + t * 64);
+          const double v0 = accG[t][0] + o.x, v1 = accG[t][1] + o.y;
+          // slot t: t <= ra -> tile (ra, t); else tile (rb, t - ra - 1)
+          const int tr = (t <= ra) ? ra : rb, tc = (t <= ra) ? t : (t - ra - 1);
+          const int row = 8 * tr + g4, col = 8 * tc + 2 * l4;
+          out[row * BA_MAXM + col] = v0;
+          out[row * BA_MAXM + col + 1] = v1;
+          if (tr != tc) {
+            out[col * BA_MAXM + row] = v0;
+            out[(col + 1) * BA_MAXM + row] = v1;
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 12; ++t) {
+        const double2 o = *reinterpret_cast<const double2*>(src + (9 + t) * 64);
+        const int sr = t >> 1, cc = 2 * q + (t & 1);
+        const int row = 8 * sr + g4, col = 8 * cc + 2 * l4;
+        const bool livet = (sr >= s_lo) && (sr < s_top);
+        outS[row * BA_MAXM + col] = livet ? accS[t][0] + o.x : 0.0;
+        outS[row * BA_MAXM + col + 1] = livet ? accS[t][1] + o.y : 0.0;
+      }
+      // small Gram of target q: packed upper triangle (a <= b); tile (ta, tb) holds rows 8 ta.., cols 8 tb.. with
+      // ta >= tb, i.e. element (row, col) -> packed index of (col, row) when col <= row
+      {
+        double* oz = outZ + q * SMALL_STRIDE;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+          const double2 o = *reinterpret_cast<const double2*>(src + (21 + t) * 64);
+          const double v[2] = {accZ[t][0] + o.x, accZ[t][1] + o.y};
+          const int zta = (t == 0) ? 0 : (t < 3 ? 1 : 2);          // tiles (0,0) (1,0) (1,1) (2,0) (2,1) (2,2)
+          const int ztb = (t == 2) ? 1 : (t < 4 ? 0 : t - 3);
+          const int row = 8 * zta + g4;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = 8 * ztb + 2 * l4 + e;
+            if (row < ZW && col < ZW && col <= row) oz[tri_index(col, row)] = do_z ? v[e] : 0.0;
+          }
+        }
+        // padding slots of the packed triangle are never read
       }
     }
-    __syncthreads();
-  }
-
-  // ---------------- write the unit's partial sums (the scatter kernels read full G / all stack rows)
-  double* out = partial + (size_t)blockIdx.x * PART_STRIDE;
-  double* outS = out + BA_MAXM * BA_MAXM;
-  if (primary) {
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int b = 0; b < 4; ++b) out[(4 * ty + a) * BA_MAXM + 4 * tx + b] = accG[a][b];
-  }
-#pragma unroll
-  for (int a = 0; a < NSR; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) outS[(ty + 16 * a) * BA_MAXM + 4 * tx + b] = live[a] ? accS[a][b] : 0.0;
-  double* outZ = outS + STACK_ROWS * BA_MAXM;
-#pragma unroll
-  for (int a = 0; a < NZ; ++a) {
-    const int o = rt + AC_ROLE * a;
-    const int tg = o / NSMALL, idx = o % NSMALL;
-    if (tg < TG) outZ[tg * SMALL_STRIDE + idx] = (zmap[a] >= 0) ? accZ[a] : 0.0;
   }
 }
 
