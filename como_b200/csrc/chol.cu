@@ -1,0 +1,577 @@
+// Dense SPD solve  H x = g  (fp64) for the window-BA normal equations: replaces lin_sys.solve_system
+// (como/odom/backend/linear_system.py:101-112: torch.linalg.cholesky_ex + torch.cholesky_solve, i.e. cuSOLVER
+// potrf + two cuBLAS trsv: 1.21 + 0.47 ms at n = 2848 on B200).
+//
+// One persistent kernel factorises the matrix with a LEFT-LOOKING TILED DATAFLOW Cholesky (64 x 64 tiles):
+//   * tiles of the lower triangle are numbered column-major; CTA c owns tiles c, c + grid, ... and processes them
+//     in that order.  Tile (i,k) accumulates  sum_{j<k} L_ij L_kj^T  on the FP64 tensor path (DMMA.8x8x4, operands
+//     staged in shared memory with cp.async, double buffered), subtracts it from A_ik and then either
+//       - i == k: factorises the 64 x 64 block (blocked 8 x 8: warp Cholesky + DMMA trailing update) and inverts it, or
+//       - i  > k: multiplies by L_kk^-T (the same DMMA GEMM with the inverse as operand);
+//   * a tile waits only for the tiles it reads (release/acquire flags in global memory); every dependency points
+//     to a smaller tile number, so with all CTAs resident (grid <= #SMs, 1 CTA per SM) the schedule cannot
+//     deadlock and look-ahead happens by itself: the next diagonal block is factorised while the bulk of the
+//     trailing updates of earlier columns is still running on other SMs;
+//   * the right-hand side rides along as one extra block row (row 0 of tiles (nb, k)): its "panel solve" IS the
+//     forward substitution  y = L^-1 g.
+// A second small kernel does the backward substitution  L^T x = y  column by column (one CTA per block column,
+// flags again), using the inverses of the diagonal blocks that the factorisation left behind.
+// Non-PD input gives NaN (sqrt of a negative pivot), like cholesky_ex(check_errors=False) -- never a trap.
+#include "common.cuh"
+
+namespace como {
+
+constexpr int CT = 64;        // tile size
+constexpr int CPITCH = 68;    // shared-memory pitch (== 4 mod 16: conflict-free DMMA fragment loads)
+constexpr int CH_THREADS = 256;
+
+__device__ __forceinline__ void dmma884c(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// 16-byte async copy global -> shared through L2 only (.cg): tiles are produced by other SMs during this kernel
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire_i32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_i32(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+struct CholView {
+  double* L;        // padded working copy, (64 nb) x (64 nb) row-major: lower triangle of H, identity padding
+  double* aug;      // nb tiles of 64 x 64 (row 0 = right-hand side / y)
+  double* linv;     // nb tiles of 64 x 64: inverses of the diagonal blocks (for the backward substitution)
+  double* l8inv;    // nb x 8 blocks of 8 x 8: inverses of the 8 x 8 diagonal sub-blocks (for the panel solves)
+  int* flags;       // (nb + 1) x nb
+  int n, nb;
+};
+
+__device__ __forceinline__ double* tile_ptr(const CholView& v, int i, int k, int& pitch) {
+  if (i == v.nb) {
+    pitch = CT;
+    return v.aug + (size_t)k * CT * CT;
+  }
+  pitch = v.nb * CT;
+  return v.L + (size_t)i * CT * pitch + (size_t)k * CT;
+}
+
+// global tile -> shared (pitch CPITCH); every tile of the padded copy is complete and 16-byte aligned
+__device__ __forceinline__ void load_tile_async(const CholView& v, int i, int k, double* dst) {
+  int pitch;
+  const double* src = tile_ptr(v, i, k, pitch);
+  for (int e = threadIdx.x; e < CT * CT / 2; e += CH_THREADS) {
+    const int r = e >> 5, c = 2 * (e & 31);
+    cp_async16(dst + r * CPITCH + c, src + (size_t)r * pitch + c);
+  }
+}
+
+// acc (rows 8 warp + g4, cols 8 c + 2 l4 + {0,1}) += A (64 x 64, [row][k]) * B^T (B [col][k]); both in shared memory
+__device__ __forceinline__ void tile_gemm(const double* A, const double* B, double (&acc)[8][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g4 = lane >> 2, l4 = lane & 3;
+  const double* ar = A + (8 * warp + g4) * CPITCH + l4;
+  const double* br = B + g4 * CPITCH + l4;
+#pragma unroll 4
+  for (int ks = 0; ks < CT / 4; ++ks) {
+    const double fa = ar[4 * ks];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dmma884c(acc[c][0], acc[c][1], fa, br[(8 * c) * CPITCH + 4 * ks]);
+  }
+}
+
+__device__ unsigned long long* g_chol_timeline = nullptr;   // optional: 4 timestamps (ns) per tile
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+struct CholSmem {
+  double A[2][CT * CPITCH];
+  double B[2][CT * CPITCH];
+  double T[CT * CPITCH];
+  double X[CT * CPITCH];       // inverse of the diagonal block (built here / operand of the panel solve)
+  double L8inv[8][64];         // scratch
+  int2 cur;
+};
+
+// Packed lower triangle of an 8 x 8 block: element (i, k), k <= i, at i (i + 1) / 2 + k.
+__device__ __forceinline__ constexpr int tri8(int i, int k) { return i * (i + 1) / 2 + k; }
+
+// In-register Cholesky of an 8 x 8 block (every lane of the warp computes the same thing: no shuffles on the
+// pivot chain).  rs[j] = 1 / L[j][j].  Non-positive pivot -> NaN.
+__device__ __forceinline__ void chol8_regs(double (&a)[36], double (&rs)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double r = rsqrt(a[tri8(j, j)]);
+    rs[j] = r;
+#pragma unroll
+    for (int i = j; i < 8; ++i) a[tri8(i, j)] *= r;        // (j,j): d * rsqrt(d) = sqrt(d)
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+      for (int k = j + 1; k <= i; ++k) a[tri8(i, k)] -= a[tri8(i, j)] * a[tri8(k, j)];
+  }
+}
+
+// Inverse of a lower-triangular 8 x 8 block held in registers: x[i][j] = -rs_i sum_{m=j}^{i-1} l[i][m] x[m][j]
+__device__ __forceinline__ void inv8_regs(const double (&l)[36], const double (&rs)[8], double (&x)[36]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    x[tri8(j, j)] = rs[j];
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int m = j; m < i; ++m) sacc += l[tri8(i, m)] * x[tri8(m, j)];
+      x[tri8(i, j)] = -rs[i] * sacc;
+    }
+  }
+}
+
+// C (+)= sign * A * B for small matrices in shared memory (pitch CPITCH) on the tensor path.  A: M x K row-major
+// ([row][k]), B: K x N row-major ([k][col]), C: M x N.  M, N multiples of 8, K multiple of 4.  Tiles are dealt to the
+// 8 warps round-robin starting at `first`; all 256 threads must call it.
+__device__ __forceinline__ void small_gemm(const double* A, const double* B, double* Cm, int M, int N, int K, double sign,
+                                           int first) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g4 = lane >> 2, l4 = lane & 3;
+  const int tn = N / 8, nt = (M / 8) * tn;
+  for (int t = (warp + 8 - (first & 7)) & 7; t < nt; t += 8) {
+    const int tr = t / tn, tc = t % tn;
+    double c0 = 0.0, c1 = 0.0;
+    const double* ar = A + (8 * tr + g4) * CPITCH + l4;
+    const double* br = B + l4 * CPITCH + 8 * tc + g4;
+    for (int k0 = 0; k0 < K; k0 += 4) dmma884c(c0, c1, ar[k0], br[k0 * CPITCH]);
+    double* cp = Cm + (8 * tr + g4) * CPITCH + 8 * tc + 2 * l4;
+    cp[0] = sign * c0;
+    cp[1] = sign * c1;
+  }
+}
+
+// ---- 64 x 64 Cholesky of S.T (lower triangle in place).  256 threads.
+// Blocked by 8: (a) warp 0 factorises the 8 x 8 diagonal block in registers (one rsqrt per pivot) while warp 1
+// inverts the PREVIOUS diagonal block (needed by the panel solves of other tiles, not by this loop), (b) the rows
+// below are solved against the block by substitution (one thread per row), (c) the trailing block is updated on the
+// tensor path.  On return S.L8inv[b] holds the inverse of diagonal block b (8 x 8 row-major, zero above the
+// diagonal) and s_invdiag the reciprocal pivots.
+__device__ void potrf64(CholSmem& S, double* s_invdiag, long long* clk = nullptr) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g4 = lane >> 2, l4 = lane & 3;
+  double* T = S.T;
+  auto invert_block = [&](int blk) {   // whole warp, redundantly in registers
+    const int c0 = 8 * blk;
+    double l8[36], rs8[8], x8[36];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      rs8[i] = s_invdiag[c0 + i];
+#pragma unroll
+      for (int k = 0; k <= i; ++k) l8[tri8(i, k)] = T[(c0 + i) * CPITCH + c0 + k];
+    }
+    inv8_regs(l8, rs8, x8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) S.L8inv[blk][8 * i + k] = (k <= i) ? x8[tri8(i, k <= i ? k : 0)] : 0.0;
+  };
+  for (int jb = 0; jb < 8; ++jb) {
+    const int c0 = 8 * jb;
+    if (clk && tid == 0) clk[4 * jb] = clock64();
+    if (warp == 0) {
+      double a8[36], rs8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int k = 0; k <= i; ++k) a8[tri8(i, k)] = T[(c0 + i) * CPITCH + c0 + k];
+      chol8_regs(a8, rs8);
+      // every lane holds the same result and stores it (same address, same value): no divergent selection
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int k = 0; k <= i; ++k) T[(c0 + i) * CPITCH + c0 + k] = a8[tri8(i, k)];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_invdiag[c0 + j] = rs8[j];
+    } else if (warp == 1 && jb > 0) {
+      invert_block(jb - 1);
+    }
+    __syncthreads();
+    if (clk && tid == 0) clk[4 * jb + 1] = clock64();
+    // (b) rows below: P L8^T = A  ->  p_c = (a_c - sum_{m<c} p_m L8[c][m]) / L8[c][c]
+    {
+      const int r = c0 + 8 + tid;
+      if (r < CT) {
+        double pv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          double sacc = T[r * CPITCH + c0 + c];
+#pragma unroll
+          for (int m = 0; m < 8; ++m)
+            if (m < c) sacc -= pv[m] * T[(c0 + c) * CPITCH + c0 + m];
+          pv[c] = sacc * s_invdiag[c0 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) T[r * CPITCH + c0 + c] = pv[c];
+      }
+    }
+    __syncthreads();
+    if (clk && tid == 0) clk[4 * jb + 2] = clock64();
+    // (c) trailing update T22 -= P P^T on the tensor path: warp w owns row tile jb + 1 + w (lower tiles only)
+    {
+      const int rt = jb + 1 + warp;
+      if (rt < 8) {
+        const double pa0 = -T[(8 * rt + g4) * CPITCH + c0 + l4], pa1 = -T[(8 * rt + g4) * CPITCH + c0 + 4 + l4];
+        for (int ct = jb + 1; ct <= rt; ++ct) {
+          double* cptr = T + (8 * rt + g4) * CPITCH + 8 * ct + 2 * l4;
+          double c0v = cptr[0], c1v = cptr[1];
+          const double pb0 = T[(8 * ct + g4) * CPITCH + c0 + l4], pb1 = T[(8 * ct + g4) * CPITCH + c0 + 4 + l4];
+          dmma884c(c0v, c1v, pa0, pb0);
+          dmma884c(c0v, c1v, pa1, pb1);
+          cptr[0] = c0v;
+          cptr[1] = c1v;
+        }
+      }
+    }
+    __syncthreads();
+    if (clk && tid == 0) clk[4 * jb + 3] = clock64();
+  }
+  if (warp == 1) invert_block(7);
+  __syncthreads();
+  if (clk && tid == 0) clk[32] = clock64();
+}
+
+// ---- inverse of the factor in S.T into S.X from the 8 x 8 inverses, by recursive doubling on the tensor path:
+// X21 = -X22 (L21 X11) for block sizes 8 -> 16 -> 32 (scratch: S.A[0]).  Off the critical path of the factorisation.
+__device__ void inverse64(CholSmem& S, long long* clk = nullptr) {
+  const int tid = threadIdx.x;
+  double* T = S.T;
+  double* X = S.X;
+  for (int e = tid; e < CT * CT; e += CH_THREADS) {
+    const int r = e >> 6, c = e & 63;
+    X[r * CPITCH + c] = ((r >> 3) == (c >> 3)) ? S.L8inv[r >> 3][8 * (r & 7) + (c & 7)] : 0.0;
+  }
+  __syncthreads();
+  if (clk && tid == 0) clk[33] = clock64();
+  double* tmp = S.A[0];
+  for (int bs = 8; bs < CT; bs *= 2) {
+    const int npairs = CT / (2 * bs);
+    for (int pr = 0; pr < npairs; ++pr) {
+      const int base = 2 * bs * pr;
+      small_gemm(T + (base + bs) * CPITCH + base, X + base * CPITCH + base, tmp + (base + bs) * CPITCH + base, bs, bs, bs, 1.0,
+                 pr * (bs * bs / 64));
+    }
+    __syncthreads();
+    for (int pr = 0; pr < npairs; ++pr) {
+      const int base = 2 * bs * pr;
+      small_gemm(X + (base + bs) * CPITCH + base + bs, tmp + (base + bs) * CPITCH + base, X + (base + bs) * CPITCH + base, bs, bs,
+                 bs, -1.0, pr * (bs * bs / 64));
+    }
+    __syncthreads();
+    if (clk && tid == 0) clk[34 + (bs == 8 ? 0 : bs == 16 ? 1 : 2)] = clock64();
+  }
+}
+
+// ---- panel solve  X L^T = T  in place (T: S.T, L: lower factor in S.X, 8 x 8 inverses in S.L8inv), blocked
+// substitution on the tensor path.  Warp w owns rows 8w..8w+7 and never needs another warp's rows: no block barrier.
+//   X[:, cb] = (T[:, cb] - sum_{mb<cb} X[:, mb] L[cb, mb]^T) L8inv_cb^T
+__device__ void trsm64(CholSmem& S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g4 = lane >> 2, l4 = lane & 3;
+  double* Tw = S.T + (8 * warp) * CPITCH;
+  const double* L = S.X;
+  for (int cb = 0; cb < 8; ++cb) {
+    double c0 = 0.0, c1 = 0.0;
+    for (int kk = 0; kk < 8 * cb; kk += 4)
+      dmma884c(c0, c1, Tw[g4 * CPITCH + kk + l4], L[(8 * cb + g4) * CPITCH + kk + l4]);
+    double* cp = Tw + g4 * CPITCH + 8 * cb + 2 * l4;
+    cp[0] -= c0;
+    cp[1] -= c1;
+    __syncwarp();
+    double x0 = 0.0, x1 = 0.0;
+    const double* li = &S.L8inv[cb][0];
+    dmma884c(x0, x1, Tw[g4 * CPITCH + 8 * cb + l4], li[8 * g4 + l4]);
+    dmma884c(x0, x1, Tw[g4 * CPITCH + 8 * cb + 4 + l4], li[8 * g4 + 4 + l4]);
+    __syncwarp();
+    cp[0] = x0;
+    cp[1] = x1;
+    __syncwarp();
+  }
+}
+
+// debug probe: factorise one 64 x 64 tile (row-major, pitch 64) and record clock64 stamps of the phases
+__global__ void __launch_bounds__(CH_THREADS, 1) chol_probe_kernel(double* tile, long long* clk) {
+  extern __shared__ __align__(16) unsigned char craw[];
+  CholSmem& S = *reinterpret_cast<CholSmem*>(craw);
+  for (int e = threadIdx.x; e < CT * CT; e += CH_THREADS) S.T[(e >> 6) * CPITCH + (e & 63)] = tile[e];
+  __syncthreads();
+  __shared__ double s_invdiag[CT];
+  potrf64(S, s_invdiag, clk);
+  inverse64(S, clk);
+  for (int e = threadIdx.x; e < CT * CT; e += CH_THREADS) tile[e] = S.X[(e >> 6) * CPITCH + (e & 63)];
+}
+
+// padded working copy: lower triangle of H (tiles on or below the diagonal, complete tiles), identity on the padding
+__global__ void __launch_bounds__(256)
+chol_copy_kernel(CholView v, const double* __restrict__ H) {
+  const int i = blockIdx.y, k = blockIdx.x;
+  if (k > i) return;
+  const int ld = v.nb * CT;
+  for (int e = threadIdx.x; e < CT * CT; e += 256) {
+    const int r = i * CT + (e >> 6), c = k * CT + (e & 63);
+    double a;
+    if (r < v.n && c < v.n) a = H[(size_t)r * v.n + c];
+    else a = (r == c) ? 1.0 : 0.0;
+    v.L[(size_t)r * ld + c] = a;
+  }
+}
+
+__global__ void chol_prep_kernel(CholView v, const double* __restrict__ g, int2* __restrict__ table) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (int e = tid; e < (v.nb + 1) * v.nb; e += stride) v.flags[e] = 0;
+  for (int e = tid; e < v.nb * CT * CT; e += stride) {
+    const int k = e / (CT * CT), r = (e / CT) % CT, c = e % CT;
+    const int col = k * CT + c;
+    v.aug[e] = (r == 0 && col < v.n) ? g[col] : 0.0;
+  }
+  if (tid == 0) {
+    int t = 0;
+    for (int k = 0; k < v.nb; ++k)
+      for (int i = k; i <= v.nb; ++i) table[t++] = make_int2(i, k);
+  }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1)
+chol_factor_kernel(CholView v, const int2* __restrict__ table, int ntiles) {
+  extern __shared__ __align__(16) unsigned char craw[];
+  CholSmem& S = *reinterpret_cast<CholSmem*>(craw);
+  __shared__ double s_invdiag[CT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g4 = lane >> 2, l4 = lane & 3;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int2 ik = table[t];
+    const int i = ik.x, k = ik.y;
+    unsigned long long* tl = g_chol_timeline ? g_chol_timeline + 4 * (size_t)t : nullptr;
+    if (tl && tid == 0) tl[0] = gtime();
+    double acc[8][2];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c][0] = acc[c][1] = 0.0;
+    // the tile's own entries (A_ik) are read up front: they do not depend on anything
+    int pitch;
+    double* gt = tile_ptr(v, i, k, pitch);
+    double2 own[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      own[c] = *reinterpret_cast<const double2*>(gt + (size_t)(8 * warp + g4) * pitch + 8 * c + 2 * l4);
+    auto stage = [&](int j, int buf) {
+      if (tid == 0) {
+        while (ld_acquire_i32(v.flags + i * v.nb + j) == 0) {
+        }
+        if (i != k)
+          while (ld_acquire_i32(v.flags + k * v.nb + j) == 0) {
+          }
+      }
+      __syncthreads();
+      load_tile_async(v, i, j, S.A[buf]);
+      if (i != k) load_tile_async(v, k, j, S.B[buf]);
+      cp_async_commit();
+    };
+    if (k > 0) stage(0, 0);
+    for (int j = 0; j < k; ++j) {
+      const int buf = j & 1;
+      if (j + 1 < k) {
+        stage(j + 1, buf ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      tile_gemm(S.A[buf], (i != k) ? S.B[buf] : S.A[buf], acc);
+      __syncthreads();
+    }
+    if (tl && tid == 0) tl[1] = gtime();
+    // val = A_ik - acc
+    {
+      const int r = 8 * warp + g4;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int col = 8 * c + 2 * l4;
+        S.T[r * CPITCH + col] = own[c].x - acc[c][0];
+        S.T[r * CPITCH + col + 1] = own[c].y - acc[c][1];
+      }
+    }
+    __syncthreads();
+    if (i == k) {
+      potrf64(S, s_invdiag);
+      for (int e = tid; e < CT * CT; e += CH_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        gt[(size_t)r * pitch + c] = (c <= r) ? S.T[r * CPITCH + c] : 0.0;
+      }
+      for (int e = tid; e < 8 * 64; e += CH_THREADS) v.l8inv[(size_t)k * 512 + e] = S.L8inv[e >> 6][e & 63];
+    } else {
+      if (tid == 0)
+        while (ld_acquire_i32(v.flags + k * v.nb + k) == 0) {
+        }
+      if (tl && tid == 0) tl[2] = gtime();
+      __syncthreads();
+      {
+        int lp;
+        const double* src = tile_ptr(v, k, k, lp);
+        for (int e = tid; e < CT * CT / 2; e += CH_THREADS) {
+          const int r = e >> 5, c = 2 * (e & 31);
+          cp_async16(S.X + r * CPITCH + c, src + (size_t)r * lp + c);
+        }
+        const double* s8 = v.l8inv + (size_t)k * 512;
+        for (int e = tid; e < 256; e += CH_THREADS) cp_async16(&S.L8inv[0][0] + 2 * e, s8 + 2 * e);
+        cp_async_commit();
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      trsm64(S);
+      __syncthreads();
+      for (int e = tid; e < CT * CT / 2; e += CH_THREADS) {
+        const int r = e >> 5, c = 2 * (e & 31);
+        *reinterpret_cast<double2*>(gt + (size_t)r * pitch + c) = *reinterpret_cast<const double2*>(S.T + r * CPITCH + c);
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_i32(v.flags + i * v.nb + k, 1);
+    if (tl && tid == 0) tl[3] = gtime();
+    if (i == k) {
+      // off the critical path: the 64 x 64 inverse of the diagonal block, used by the backward substitution
+      inverse64(S);
+      for (int e = tid; e < CT * CT; e += CH_THREADS) v.linv[(size_t)k * CT * CT + e] = S.X[(e >> 6) * CPITCH + (e & 63)];
+      __syncthreads();
+    }
+  }
+}
+
+// Backward substitution L^T x = y.  CTA k owns block column k: s = sum_{i>k} L_ik^T x_i as the x_i arrive,
+// x_k = Linv_k^T (y_k - s).
+__global__ void __launch_bounds__(CH_THREADS)
+chol_backsolve_kernel(CholView v, double* __restrict__ x, int* __restrict__ xflags) {
+  __shared__ double s_part[4][CT];
+  __shared__ double s_x[CT];
+  const int k = v.nb - 1 - blockIdx.x;   // late columns first (they are needed first)
+  const int tid = threadIdx.x, c = tid & 63, part = tid >> 6;
+  const int ld = v.nb * CT;
+  double s = 0.0;
+  for (int i = v.nb - 1; i > k; --i) {
+    double l[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) l[q] = v.L[(size_t)(i * CT + 16 * part + q) * ld + k * CT + c];
+    if (tid == 0)
+      while (ld_acquire_i32(xflags + i) == 0) {
+      }
+    __syncthreads();
+    if (tid < CT) s_x[tid] = (i * CT + tid < v.n) ? __ldcg(x + i * CT + tid) : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s += l[q] * s_x[16 * part + q];
+    __syncthreads();
+  }
+  s_part[part][c] = s;
+  __syncthreads();
+  if (tid < CT) {
+    const double tot = s_part[0][tid] + s_part[1][tid] + s_part[2][tid] + s_part[3][tid];
+    s_x[tid] = v.aug[(size_t)k * CT * CT + tid] - tot;   // y_k - s
+  }
+  __syncthreads();
+  double p = 0.0;
+  {
+    const double* li = v.linv + (size_t)k * CT * CT;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int r = 16 * part + q;
+      p += li[r * CT + c] * s_x[r];
+    }
+  }
+  __syncthreads();
+  s_part[part][c] = p;
+  __syncthreads();
+  if (tid < CT && k * CT + tid < v.n) x[k * CT + tid] = s_part[0][tid] + s_part[1][tid] + s_part[2][tid] + s_part[3][tid];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) st_release_i32(xflags + k, 1);
+}
+
+}  // namespace como
+
+using namespace como;
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// debug only (not part of the public header): timeline buffer of 4 x ntiles u64, or NULL to switch off
+extern "C" int como_b200_chol_debug_timeline(unsigned long long* buf) {
+  return cudaMemcpyToSymbol(g_chol_timeline, &buf, sizeof(buf)) == cudaSuccess ? 0 : -2;
+}
+
+extern "C" int como_b200_chol_debug_probe(double* tile, long long* clk) {
+  cudaFuncSetAttribute(chol_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem));
+  chol_probe_kernel<<<1, CH_THREADS, sizeof(CholSmem)>>>(tile, clk);
+  return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
+}
+
+extern "C" size_t como_b200_chol_solve_workspace_bytes(int32_t n) {
+  const size_t nb = (n + CT - 1) / CT;
+  return align256(sizeof(int) * ((nb + 1) * nb + nb)) + align256(sizeof(int2) * (nb * (nb + 3) / 2 + 8)) +
+         align256(sizeof(double) * nb * CT * CT) * 2 + align256(sizeof(double) * nb * 512) +
+         align256(sizeof(double) * nb * CT * nb * CT) + 256;
+}
+
+extern "C" int como_b200_chol_solve(const double* H, const double* g, int32_t n, double* x, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  COMO_REQUIRE(H && g && x && workspace, "chol_solve: null pointer argument");
+  COMO_REQUIRE(n >= 1, "chol_solve: bad size");
+  if (workspace_bytes < como_b200_chol_solve_workspace_bytes(n)) {
+    set_last_error("chol_solve: workspace too small");
+    return COMO_B200_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nb = (n + CT - 1) / CT;
+  unsigned char* w = (unsigned char*)workspace;
+  CholView v;
+  v.n = n;
+  v.nb = nb;
+  v.flags = (int*)w;
+  int* xflags = v.flags + (nb + 1) * nb;
+  w += align256(sizeof(int) * ((nb + 1) * nb + nb));
+  int2* table = (int2*)w;
+  w += align256(sizeof(int2) * (nb * (nb + 3) / 2 + 8));
+  v.aug = (double*)w;
+  w += align256(sizeof(double) * nb * CT * CT);
+  v.linv = (double*)w;
+  w += align256(sizeof(double) * nb * CT * CT);
+  v.l8inv = (double*)w;
+  w += align256(sizeof(double) * nb * 512);
+  v.L = (double*)w;
+  COMO_REQUIRE(nb <= sm_count(), "chol_solve: n = %d too large for the resident-CTA schedule", n);
+  const int ntiles = nb * (nb + 1) / 2 + nb;   // lower triangle + the right-hand-side row
+  chol_copy_kernel<<<dim3(nb, nb), 256, 0, st>>>(v, H);
+  chol_prep_kernel<<<64, 256, 0, st>>>(v, g, table);
+  cudaMemsetAsync(xflags, 0, sizeof(int) * nb, st);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem));
+    attr = true;
+  }
+  int grid = sm_count();
+  if (grid > ntiles) grid = ntiles;
+  chol_factor_kernel<<<grid, CH_THREADS, sizeof(CholSmem), st>>>(v, table, ntiles);
+  int rc = check_launch("chol_factor");
+  if (rc) return rc;
+  chol_backsolve_kernel<<<nb, CH_THREADS, 0, st>>>(v, x, xflags);
+  return check_launch("chol_backsolve");
+}

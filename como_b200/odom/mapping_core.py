@@ -195,11 +195,33 @@ def _buf(cache, name, shape, dtype, dev):
 _OVERLAP = os.environ.get("COMO_B200_BA_OVERLAP", "1") != "0"
 
 
+_SOLVER = os.environ.get("COMO_B200_SOLVER", "tiled")   # "torch": cuSOLVER potrf + cuBLAS trsv (comparison only)
+_solve_ws = {}
+
+
 def solve_system(H, g):
-    """Drop-in for lin_sys.solve_system (como/odom/backend/linear_system.py:101-112): dense Cholesky,
-    never raises on a non-PD matrix."""
-    Lc, _ = torch.linalg.cholesky_ex(H, upper=False, check_errors=False)
-    return torch.cholesky_solve(g[:, None], Lc, upper=False)
+    """Drop-in for lin_sys.solve_system (como/odom/backend/linear_system.py:101-112): dense Cholesky solve of the
+    SPD normal equations, never raises on a non-PD matrix (NaN instead).  Runs the tiled dataflow Cholesky of
+    csrc/chol.cu (factorisation + both substitutions); H is left untouched.  Returns delta (dim, 1)."""
+    dev = _lib.require_cuda(H, g)
+    if H.dtype != F64 or g.dtype != F64:
+        raise RuntimeError("como_b200 solve_system runs in float64 (mapping.dtype: double)")
+    if _SOLVER == "torch":
+        Lc, _ = torch.linalg.cholesky_ex(H, upper=False, check_errors=False)
+        return torch.cholesky_solve(g.reshape(-1, 1), Lc, upper=False)
+    n = H.shape[0]
+    Hc = H if H.is_contiguous() else H.contiguous()
+    gc = g.reshape(-1).contiguous()
+    x = torch.empty(n, 1, dtype=F64, device=dev)
+    key = (dev.index, n)
+    ws = _solve_ws.get(key)
+    if ws is None:
+        _solve_ws.clear()
+        ws = _solve_ws[key] = torch.empty(int(_lib.chol_solve_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.chol_solve(_lib.ptr(Hc), _lib.ptr(gc), n, _lib.ptr(x), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(st, "como_b200_chol_solve")
+    return x
 
 
 def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return_debug=False):

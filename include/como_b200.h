@@ -205,6 +205,13 @@ int como_b200_kmat_predictor(const double* cov_img, int32_t B, int32_t H, int32_
                              const double* E_m, const double* Kmm_inv, int32_t M, double scale, double* Knm_Kmminv,
                              void* stream);
 
+/* lin_sys.solve_system (como/odom/backend/linear_system.py:101-112): x = H^-1 g for the SPD normal equations,
+ * H (n,n) row-major fp64 (only the lower triangle is read, H is not modified), g (n), x (n).  Tiled dataflow
+ * Cholesky + fused forward substitution + backward substitution (csrc/chol.cu).  Non-PD input gives NaN. */
+size_t como_b200_chol_solve_workspace_bytes(int32_t n);
+int como_b200_chol_solve(const double* H, const double* g, int32_t n, double* x, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* Keyframe-creation path: calc_kernel_matrices + get_predictor at arbitrary test points
  * (como/depth_cov/core/distill_depth.py:8-48) and the normal equations of distill_depth /
  * distill_conditional_depth_with_scale_prior (distill_depth.py:51-82, 126-153; lstsq_chol utils/lin_alg.py:82-87).
