@@ -195,6 +195,17 @@ def _buf(cache, name, shape, dtype, dev):
 _OVERLAP = os.environ.get("COMO_B200_BA_OVERLAP", "1") != "0"
 
 
+def _host_scalars(cache, name, t, pick, n):
+    """Host copy of a few scalars of a (rarely changing) device tensor, cached on (storage, version): reading them
+    every iteration would synchronise the host with the stream and leave the GPU idle between iterations."""
+    key = (t.data_ptr(), t._version, tuple(t.shape))
+    hit = cache.get(name)
+    if hit is None or hit[0] != key:
+        vals = pick(t.detach().to("cpu", F64))
+        hit = cache[name] = (key, (C.c_double * n)(*[float(v) for v in vals]))
+    return hit[1]
+
+
 _SOLVER = os.environ.get("COMO_B200_SOLVER", "tiled")   # "torch": cuSOLVER potrf + cuBLAS trsv (comparison only)
 _solve_ws = {}
 
@@ -243,8 +254,7 @@ def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return
         K, L, M, N, H, W = kp.K, kp.L, kp.M, kp.N, kp.H, kp.W
         R = pp.R
         stream = _lib.stream_ptr(dev)
-        Kmat = s.intrinsics[0].detach().to("cpu", F64)
-        intr4 = (C.c_double * 4)(float(Kmat[0, 0]), float(Kmat[1, 1]), float(Kmat[0, 2]), float(Kmat[1, 2]))
+        intr4 = _host_scalars(cache, "intr4", s.intrinsics, lambda Kh: (Kh[0, 0, 0], Kh[0, 1, 1], Kh[0, 0, 2], Kh[0, 1, 2]), 4)
         if R > 0:
             if not s.recent_poses.is_contiguous():
                 s.recent_poses = s.recent_poses.contiguous()
@@ -356,7 +366,8 @@ def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return
         sig4 = (C.c_double * 4)(1e-2, float(sg["pose_prior"]), float(sg["scale_prior"]), float(sg["mean_depth_prior"]))
         full = bool(s.window_full)
         anchors = s.P_m_anchors.contiguous() if full else None
-        scale_anchor = 0.0 if full else float(torch.as_tensor(s.init_scale_anchor).reshape(-1)[0])
+        scale_anchor = 0.0 if full else _host_scalars(cache, "scale_anchor", torch.as_tensor(s.init_scale_anchor),
+                                                      lambda a: (a.reshape(-1)[0],), 1)[0]
         obs = s.obs_ref_mask.contiguous().view(torch.uint8)
         st = _lib.ba_priors(
             _lib.ptr(scaf), _lib.ptr(dz_dP), _lib.ptr(kp.LtL), _lib.ptr(med_new), _lib.ptr(obs), _lib.ptr(s.pm_first_obs),
