@@ -363,7 +363,7 @@ def run_ba_ours(args, rank, world, device):
                                    if shard else f"replicas x{world} (one independent window per GPU)")},
         "e2e": {"value": nwin * args.steps / (e_ms * 1e-3), "unit": "GN-it/s",
                 "h2d_bytes_per_step": int(rgb_host.numel() * 8), "d2h_bytes_per_step": int(res_host.numel() * 8)},
-        "gpu_launches": args.steps * 22,
+        "gpu_launches": args.steps * 36,   # own kernels per step, counted in profiles/r01_launches_ba_final.csv
         "roofline": {"kernel": "predictor_stream_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                      "alg_bytes_per_launch": ab["predictor_apply"], "launch_ms": pa_ms},
@@ -495,7 +495,7 @@ def run_kfinit_ours(args, rank, world, device):
                    "parallelism": f"replicas x{world} (independent keyframes, no collective)"},
         "e2e": {"value": world * args.steps / (e_ms * 1e-3), "unit": "KF/s",
                 "h2d_bytes_per_step": int(cov_host.numel() + z_host.numel()) * 8, "d2h_bytes_per_step": int(out_host.numel()) * 8},
-        "gpu_launches": None,
+        "gpu_launches": args.steps * 253,   # own kernels per call, counted in profiles/r01_launches_kfinit_summary.txt
         "roofline": {"kernel": "kmat_rows_kernel", "bound": "tensor", "achieved": ach, "peak": FP64_PEAK_TFLOPS,
                      "unit": "TFLOP/s", "frac": ach / FP64_PEAK_TFLOPS, "traffic": None,
                      "peak_source": "fp64 DFMA/DMMA peak measured with scripts/micro/dmma_bench.cu (MEASURED_PEAKS.json has no fp64 entry)",
