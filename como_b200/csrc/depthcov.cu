@@ -116,17 +116,17 @@ struct SamplerState {   // per batch element, in global memory
 
 // step A (1 CTA per batch): commit `next` as anchor number i=count: coords/E, k_ni against the previous
 // anchors, Cholesky row.  Mirrors greedy_loop lines 252-274 of samplers.py.
-__global__ void sampler_commit_kernel(SamplerState* __restrict__ st, const float* __restrict__ dom_xy,
-                                      const float* __restrict__ dom_E, int d, float* __restrict__ sel_xy,
-                                      float* __restrict__ sel_E, long long* __restrict__ sel_idx, float* __restrict__ L,
-                                      int n, float signal_var, float fixed_var, int has_fixed, float max_stdev_thresh,
-                                      int terminate_early) {
-  const int b = blockIdx.x;
-  SamplerState& s = st[b];
+__device__ __forceinline__ void sampler_commit_body(int b, SamplerState* st, const float* dom_xy,
+                                                    const float* dom_E, int d, float* sel_xy,
+                                                    float* sel_E, long long* sel_idx,
+                                                    float* L, int n, float signal_var, float fixed_var,
+                                                    int has_fixed, float max_stdev_thresh, int terminate_early) {
+  volatile SamplerState& s = st[b];
   __shared__ float k_ni[128];
   const int i = s.count;
   if (s.done || i >= n) return;
   if (terminate_early && s.next_stdev < max_stdev_thresh) {   // batch size 1 in every reference call site
+    __syncthreads();            // every thread has read the state before it changes
     if (threadIdx.x == 0) s.done = 1;
     return;
   }
@@ -165,20 +165,29 @@ __global__ void sampler_commit_kernel(SamplerState* __restrict__ st, const float
   }
 }
 
+__global__ void sampler_commit_kernel(SamplerState* __restrict__ st, const float* __restrict__ dom_xy,
+                                      const float* __restrict__ dom_E, int d, float* __restrict__ sel_xy,
+                                      float* __restrict__ sel_E, long long* __restrict__ sel_idx, float* __restrict__ L,
+                                      int n, float signal_var, float fixed_var, int has_fixed, float max_stdev_thresh,
+                                      int terminate_early) {
+  sampler_commit_body(blockIdx.x, st, dom_xy, dom_E, d, sel_xy, sel_E, sel_idx, L, n, signal_var, fixed_var, has_fixed,
+                      max_stdev_thresh, terminate_early);
+}
+
 // step B (grid over the domain): k_id against the new anchor, new obs_info row, variance downdate, distance
 // mask update, block-level argmax of stdev*mask (first index wins ties) -> per-block candidates.
 constexpr int SB_THREADS = 256;
-__global__ void __launch_bounds__(SB_THREADS)
-sampler_domain_kernel(const SamplerState* __restrict__ st, const float* __restrict__ dom_xy,
-                      const float* __restrict__ dom_E, int d, const float* __restrict__ sel_xy,
-                      const float* __restrict__ sel_E, const float* __restrict__ L, int n, float* __restrict__ obs_info,
-                      float* __restrict__ var, uint8_t* __restrict__ dist_ok, float signal_var, float dist_thresh_sq,
-                      float* __restrict__ cand_val, int* __restrict__ cand_idx) {
-  const int b = blockIdx.y;
-  const SamplerState s = st[b];
-  const int i = s.count;   // row being appended
-  const bool live = !(s.done || i >= n);
-  const int j = blockIdx.x * SB_THREADS + threadIdx.x;
+__device__ __forceinline__ void sampler_domain_body(int b, int blk, int nblk, const SamplerState* st,
+                                                    const float* dom_xy, const float* dom_E, int d,
+                                                    const float* sel_xy, const float* sel_E,
+                                                    const float* L, int n, float* obs_info,
+                                                    float* var, uint8_t* dist_ok, float signal_var,
+                                                    float dist_thresh_sq, float* cand_val,
+                                                    int* cand_idx) {
+  const volatile SamplerState* vs = st + b;   // re-read every call: the fused small-domain kernel updates it in place
+  const int i = vs->count;   // row being appended
+  const bool live = !(vs->done || i >= n);
+  const int j = blk * SB_THREADS + threadIdx.x;
   float best = -1.0f;
   int besti = 0x7fffffff;
   if (j < d) {
@@ -228,16 +237,25 @@ sampler_domain_kernel(const SamplerState* __restrict__ st, const float* __restri
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    cand_val[(size_t)b * gridDim.x + blockIdx.x] = sv[0];
-    cand_idx[(size_t)b * gridDim.x + blockIdx.x] = si[0];
+    cand_val[(size_t)b * nblk + blk] = sv[0];
+    cand_idx[(size_t)b * nblk + blk] = si[0];
   }
 }
 
+__global__ void __launch_bounds__(SB_THREADS)
+sampler_domain_kernel(const SamplerState* __restrict__ st, const float* __restrict__ dom_xy,
+                      const float* __restrict__ dom_E, int d, const float* __restrict__ sel_xy,
+                      const float* __restrict__ sel_E, const float* __restrict__ L, int n, float* __restrict__ obs_info,
+                      float* __restrict__ var, uint8_t* __restrict__ dist_ok, float signal_var, float dist_thresh_sq,
+                      float* __restrict__ cand_val, int* __restrict__ cand_idx) {
+  sampler_domain_body(blockIdx.y, blockIdx.x, gridDim.x, st, dom_xy, dom_E, d, sel_xy, sel_E, L, n, obs_info, var, dist_ok,
+                      signal_var, dist_thresh_sq, cand_val, cand_idx);
+}
+
 // step C (1 CTA per batch): final argmax over block candidates -> next index; advance the count.
-__global__ void sampler_pick_kernel(SamplerState* __restrict__ st, const float* __restrict__ cand_val,
-                                    const int* __restrict__ cand_idx, int nblocks, const float* __restrict__ var, int d,
-                                    int n, int advance) {
-  const int b = blockIdx.x;
+__device__ __forceinline__ void sampler_pick_body(int b, SamplerState* st, const float* cand_val,
+                                                  const int* cand_idx, int nblocks,
+                                                  const float* var, int d, int n, int advance) {
   __shared__ float sv[256];
   __shared__ int si[256];
   float best = -1.0f;
@@ -265,15 +283,65 @@ __global__ void sampler_pick_kernel(SamplerState* __restrict__ st, const float* 
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    SamplerState& s = st[b];
+    volatile SamplerState& s = st[b];
     const bool live = !(s.done || s.count >= n);
-    if (advance && live) s.count += 1;
+    if (advance && live) s.count = s.count + 1;
     s.next = si[0];
     // the reference reports gp_stdev at the chosen index (without the distance mask)
     float sd = sqrtf(var[(size_t)b * d + si[0]]);
     if (sd != sd) sd = 0.0f;
     s.next_stdev = sd + 1e-10f;
   }
+}
+
+__global__ void sampler_pick_kernel(SamplerState* __restrict__ st, const float* __restrict__ cand_val,
+                                    const int* __restrict__ cand_idx, int nblocks, const float* __restrict__ var, int d,
+                                    int n, int advance) {
+  sampler_pick_body(blockIdx.x, st, cand_val, cand_idx, nblocks, var, d, n, advance);
+}
+
+// Small domains (d <= 2048, e.g. the re-selection among <= 64 tracked anchors in track_and_init): the whole greedy
+// loop in ONE launch, one CTA per batch element, the same three steps separated by block barriers instead of
+// kernel boundaries (3 (n - m) + 2 launches otherwise, each ~10 us of fixed cost for a few hundred flops).
+constexpr int SAMPLER_SMALL_D = 8 * SB_THREADS;
+__global__ void __launch_bounds__(SB_THREADS)
+sampler_small_kernel(SamplerState* st, const float* dom_xy, const float* dom_E, int d, int n, int m, float* sel_xy,
+                     float* sel_E, long long* sel_idx, float* L, float* obs_info, float* var, uint8_t* dist_ok,
+                     float signal_var, float fixed_var, int has_fixed, float dist_thresh_sq, float max_stdev_thresh,
+                     int terminate_early, float* cand_val, int* cand_idx, int* count_out) {
+  const int b = blockIdx.x;
+  const int nblk = (d + SB_THREADS - 1) / SB_THREADS;
+  volatile SamplerState* vs = st + b;
+  if (threadIdx.x == 0) {
+    vs->count = n;   // "not live": the first domain pass only evaluates the arg max
+    vs->next = 0;
+    vs->next_stdev = 0.0f;
+    vs->done = 0;
+  }
+  __syncthreads();
+  for (int blk = 0; blk < nblk; ++blk) {
+    sampler_domain_body(b, blk, nblk, st, dom_xy, dom_E, d, sel_xy, sel_E, L, n, obs_info, var, dist_ok, signal_var,
+                        dist_thresh_sq, cand_val, cand_idx);
+    __syncthreads();
+  }
+  sampler_pick_body(b, st, cand_val, cand_idx, nblk, var, d, n, 0);
+  __syncthreads();
+  if (threadIdx.x == 0) vs->count = m;
+  __syncthreads();
+  for (int i = m; i < n; ++i) {
+    sampler_commit_body(b, st, dom_xy, dom_E, d, sel_xy, sel_E, sel_idx, L, n, signal_var, fixed_var, has_fixed,
+                        max_stdev_thresh, terminate_early);
+    __syncthreads();
+    if (vs->done) break;
+    for (int blk = 0; blk < nblk; ++blk) {
+      sampler_domain_body(b, blk, nblk, st, dom_xy, dom_E, d, sel_xy, sel_E, L, n, obs_info, var, dist_ok, signal_var,
+                          dist_thresh_sq, cand_val, cand_idx);
+      __syncthreads();
+    }
+    sampler_pick_body(b, st, cand_val, cand_idx, nblk, var, d, n, 1);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) count_out[b] = vs->count;
 }
 
 }  // namespace como
@@ -335,6 +403,12 @@ extern "C" int como_b200_sampler_greedy(const float* dom_xy, const float* dom_E,
   SamplerState* state = (SamplerState*)ws;
   float* cand_val = (float*)(ws + 256 + (size_t)B * sizeof(SamplerState));
   int* cand_idx = (int*)(cand_val + (size_t)B * nblk);
+  if (d <= SAMPLER_SMALL_D) {
+    sampler_small_kernel<<<B, SB_THREADS, 0, st>>>(state, dom_xy, dom_E, d, n, m, sel_xy, sel_E, (long long*)sel_idx, L, obs_info,
+                                                   var, dist_ok, signal_var, fixed_var, has_fixed, dist_thresh * dist_thresh,
+                                                   max_stdev_thresh, terminate_early, cand_val, cand_idx, count_out);
+    return check_launch("sampler_greedy");
+  }
   // state: count = m, not done; the first domain pass below only evaluates the arg max (row m is not live yet)
   SamplerState h;
   h.count = n;  // "not live": makes the first domain pass a pure argmax evaluation
