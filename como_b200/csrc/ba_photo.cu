@@ -17,10 +17,11 @@
 //   predictor rows (512 B each, one coalesced request per row) and forms logz_n and q_n = Kt dlogz/dTwc
 //   with warp shuffles; stage 2 maps lanes to pixels and loops over the keyframe's targets: project,
 //   bilinear gather of [I,gx,gy], residual.  Writes r (contiguous, for the median) and dI/dPc.
-// Pass B (ba_accum_kernel): work unit = (reference keyframe, pixel slice, group of <= 8 targets).
+// Pass B (ba_accum_kernel): work unit = (reference keyframe, pixel slice, group of <= 4 targets).
 //   Predictor rows of a 32-pixel tile are staged into shared memory with 1-D bulk async copies
-//   (cp.async.bulk + mbarrier, double buffered); per-(pixel,target) Jacobians are rebuilt from the
-//   stored residual data; the Gram / stack products run as register-tiled FMAs over the tile.
+//   (cp.async.bulk + mbarrier, 4-deep ring); 4 coefficient warps rebuild the per-(pixel,target) Jacobians
+//   of tile t+1 from the stored residual data while 8 product warps run the Gram / stack / small-Gram
+//   products of tile t on the FP64 tensor path (mma.sync m8n8k4 f64 = DMMA.8x8x4, pixel index as K).
 #include "ba_common.cuh"
 
 namespace como {
@@ -214,8 +215,8 @@ __device__ __forceinline__ void accum_stack_step(double (&accS)[12][2], const do
   }
 }
 
-// Warp-specialised: the coefficient warps (8-15) rebuild the per-(target,pixel) Jacobians of tile t+1 while
-// the product warps (0-7) run the register-tiled products of tile t; one CTA-wide barrier per tile.
+// Warp-specialised: the coefficient warps (8-11) rebuild the per-(target,pixel) Jacobians of tile t+1 while
+// the product warps (0-7) run the tensor-path products of tile t; one CTA-wide barrier per tile.
 __global__ void __launch_bounds__(AC_THREADS, 1)
 ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coords, const double* __restrict__ scaf,
                 const BAFrame* __restrict__ frames, const int32_t* __restrict__ ref_ptr,
