@@ -330,9 +330,7 @@ def run_ba_ours(args, rank, world, device):
 
     def e2e_step():
         rgb = rgb_host.to(device, non_blocking=True)
-        gray = synth._gray(rgb)
-        gx, gy = synth._scharr(gray)
-        s.recent_img_and_grads[0].copy_(torch.cat((gray, gx, gy), dim=1)[0])
+        s.recent_img_and_grads[0].copy_(MC.get_img_and_grads(rgb)[0])   # fused gray + Scharr kernel
         step()
         res_host[: K * 16].copy_(s.kf_poses.reshape(-1), non_blocking=True)
         res_host[K * 16:(K + R) * 16].copy_(s.recent_poses.reshape(-1), non_blocking=True)
@@ -365,7 +363,10 @@ def run_ba_ours(args, rank, world, device):
                 "h2d_bytes_per_step": int(rgb_host.numel() * 8), "d2h_bytes_per_step": int(res_host.numel() * 8)},
         "gpu_launches": args.steps * 36,   # own kernels per step, counted in profiles/r01_launches_ba_final.csv
         "roofline": {"kernel": "predictor_stream_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": ach / peak,
+                     # dram__bytes_read + write of one launch at this exact shape (ncu --set full,
+                     # profiles/r01_predictor_stream_full.txt): 5.034 GB + 0.081 GB; other shapes: not captured
+                     "traffic": 5115372864 if (K, H, W, M) == (32, 480, 640, 64) else None, "peak_source": peak_src,
                      "alg_bytes_per_launch": ab["predictor_apply"], "launch_ms": pa_ms},
         "clocks": clocks,
     }

@@ -95,6 +95,7 @@ sample_depth_gradmag = _sig("como_b200_sample_depth_gradmag", C.c_int, [VP, I32,
 
 gray_pyramid = _sig("como_b200_gray_pyramid", C.c_int, [VP, I32, I32, I32, C.POINTER(C.c_void_p), VP])
 image_gradients = _sig("como_b200_image_gradients", C.c_int, [VP, I32, I32, VP, VP, VP])
+img_and_grads_f64 = _sig("como_b200_img_and_grads_f64", C.c_int, [VP, I32, I32, VP, VP])
 kf_reference_level = _sig("como_b200_kf_reference_level", C.c_int,
                           [VP, VP, VP, VP, I32, I32, I32, I32, I32, C.POINTER(F32), VP, F32, F32, VP, VP, VP, VP, VP, VP])
 reproj_depth = _sig("como_b200_reproj_depth", C.c_int, [VP, I32, VP, C.POINTER(F32), I32, I32, VP, VP, VP])
@@ -112,7 +113,7 @@ DECLARED_SYMBOLS = [
     "como_b200_chol_solve_workspace_bytes", "como_b200_chol_solve",
     "como_b200_kmat_rows", "como_b200_weighted_gram", "como_b200_rows_residual",
     "como_b200_reproject_dense", "como_b200_sample_depth_gradmag",
-    "como_b200_gray_pyramid", "como_b200_image_gradients", "como_b200_kf_reference_level", "como_b200_reproj_depth",
+    "como_b200_gray_pyramid", "como_b200_image_gradients", "como_b200_img_and_grads_f64", "como_b200_kf_reference_level", "como_b200_reproj_depth",
 ]
 
 

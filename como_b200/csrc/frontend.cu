@@ -52,6 +52,28 @@ __global__ void scharr_kernel(const float* __restrict__ in, int h, int w, float*
   gy[(size_t)y * w + x] = k3 * (v[2][0] - v[0][0]) + k10 * (v[2][1] - v[0][1]) + k3 * (v[2][2] - v[0][2]);
 }
 
+// Mapping.get_img_and_grads (como/odom/Mapping.py:368-376) in ONE pass: rgb (3,H,W) f64 -> [I, gx, gy] (3,H,W) f64,
+// the layout the BA gather kernels read.  I = 0.2989 R + 0.587 G + 0.114 B (torchvision rgb_to_grayscale), Scharr
+// with reflect padding (utils/image_processing.py:8-45); the 3x3 gray neighbourhood is rebuilt from RGB on the fly.
+__global__ void img_and_grads_f64_kernel(const double* __restrict__ rgb, int h, int w, double* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w || y >= h) return;
+  const size_t hw = (size_t)h * w;
+  double v[3][3];
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx) {
+      const size_t o = (size_t)reflect_idx(y + dy, h) * w + reflect_idx(x + dx, w);
+      v[dy + 1][dx + 1] = 0.2989 * rgb[o] + 0.587 * rgb[hw + o] + 0.114 * rgb[2 * hw + o];
+    }
+  const double k3 = 3.0 / 32.0, k10 = 10.0 / 32.0;
+  const size_t o = (size_t)y * w + x;
+  out[o] = v[1][1];
+  out[hw + o] = k3 * (v[0][2] - v[0][0]) + k10 * (v[1][2] - v[1][0]) + k3 * (v[2][2] - v[2][0]);
+  out[2 * hw + o] = k3 * (v[2][0] - v[0][0]) + k10 * (v[2][1] - v[0][1]) + k3 * (v[2][2] - v[0][2]);
+}
+
 // One level of Tracking.update_kf_reference for one keyframe b: all pixels of the level image.
 // rel (3x4 row-major) maps keyframe b's camera frame into the last keyframe's frame.
 __global__ void kf_reference_kernel(const float* __restrict__ img, const float* __restrict__ gx, const float* __restrict__ gy,
@@ -149,6 +171,13 @@ extern "C" int como_b200_image_gradients(const float* img, int32_t h, int32_t w,
   dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
   scharr_kernel<<<grd, blk, 0, (cudaStream_t)stream>>>(img, h, w, gx, gy);
   return check_launch("image_gradients");
+}
+
+extern "C" int como_b200_img_and_grads_f64(const double* rgb, int32_t h, int32_t w, double* img_and_grads, void* stream) {
+  COMO_REQUIRE(rgb && img_and_grads && h >= 2 && w >= 2, "img_and_grads_f64: bad arguments");
+  dim3 blk(32, 8), grd((w + 31) / 32, (h + 7) / 8);
+  img_and_grads_f64_kernel<<<grd, blk, 0, (cudaStream_t)stream>>>(rgb, h, w, img_and_grads);
+  return check_launch("img_and_grads_f64");
 }
 
 extern "C" int como_b200_kf_reference_level(const float* img, const float* gx, const float* gy, const float* depth_full,

@@ -393,6 +393,21 @@ def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return
     return getattr(s, "converged", False)
 
 
+def get_img_and_grads(rgb):
+    """Drop-in for Mapping.get_img_and_grads (como/odom/Mapping.py:368-376, color "gray"): rgb (1,3,H,W) CUDA tensor ->
+    (1,3,H,W) float64 [I, gx, gy] in one fused pass (gray + Scharr)."""
+    dev = _lib.require_cuda(rgb)
+    if rgb.dim() != 4 or rgb.shape[0] != 1 or rgb.shape[1] != 3:
+        raise RuntimeError(f"get_img_and_grads expects rgb of shape (1,3,H,W), got {tuple(rgb.shape)}")
+    src = rgb.to(F64).contiguous()
+    H, W = int(rgb.shape[2]), int(rgb.shape[3])
+    out = torch.empty(1, 3, H, W, dtype=F64, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.img_and_grads_f64(_lib.ptr(src), H, W, _lib.ptr(out), _lib.stream_ptr(dev))
+        _lib.check(st, "como_b200_img_and_grads_f64")
+    return out
+
+
 def store_vars(s, pm, logzm, Knm_Kmminv):
     """Drop-in for Mapping.store_vars (como/odom/Mapping.py:749-758): dense depth of every keyframe from the
     predictor (one streaming pass over Knm_Kmminv) and the exact per-keyframe median depth."""

@@ -8,7 +8,7 @@ What is replaced (reference name -> como_b200 implementation):
   sys.modules["como_backends"]                                  -> como_b200.como_backends
   como.depth_cov.core.samplers.sample_sparse_coords             -> como_b200.depth_cov.core.samplers.sample_sparse_coords
   como.odom.frontend.photo_tracking.photo_tracking_pyr / precalc_jacobians (also as imported by como.odom.Tracking)
-  como.odom.Mapping.Mapping.iterate / store_vars / prep_predictor
+  como.odom.Mapping.Mapping.iterate / store_vars / prep_predictor / get_img_and_grads
   como.odom.backend.linear_system.solve_system
   como.odom.frontend.corr.track_and_init (also as imported by como.odom.Mapping) and
   como.depth_cov.core.distill_depth.distill_depth_from_scratch / distill_conditional_depth_from_scratch
@@ -65,9 +65,15 @@ def install():
     for name in ("distill_depth_from_scratch", "distill_conditional_depth_from_scratch"):
         setattr(ref_dd, name, getattr(b_dd, name))
         setattr(ref_corr, name, getattr(b_dd, name))
+    def get_img_and_grads(self, rgb):
+        if self.cfg["color"] != "gray":
+            raise NotImplementedError("como_b200 implements color: gray only")
+        return mc.get_img_and_grads(rgb.to(self.dtype)).to(self.dtype)
+
+    ref_mapping.Mapping.get_img_and_grads = get_img_and_grads
     ref_mapping.Mapping.iterate = iterate
     ref_mapping.Mapping.store_vars = store_vars
     ref_mapping.Mapping.prep_predictor = prep_predictor
     return {"patched": ["como_backends", "sample_sparse_coords", "photo_tracking_pyr", "precalc_jacobians",
-                        "Mapping.iterate", "Mapping.store_vars", "Mapping.prep_predictor", "solve_system",
+                        "Mapping.iterate", "Mapping.store_vars", "Mapping.prep_predictor", "Mapping.get_img_and_grads", "solve_system",
                         "track_and_init", "distill_depth_from_scratch", "distill_conditional_depth_from_scratch"]}

@@ -250,6 +250,10 @@ int como_b200_gray_pyramid(const float* rgb, int32_t H, int32_t W, int32_t num_l
                            void* stream);
 /* ImageGradientModule (utils/image_processing.py:8-44): Scharr/32, reflect padding. */
 int como_b200_image_gradients(const float* img, int32_t h, int32_t w, float* gx, float* gy, void* stream);
+
+/* Mapping.get_img_and_grads (como/odom/Mapping.py:368-376), color "gray": rgb (3,H,W) f64 -> [I, gx, gy] (3,H,W)
+ * f64 in one pass (gray = 0.2989 R + 0.587 G + 0.114 B, Scharr with reflect padding). */
+int como_b200_img_and_grads_f64(const double* rgb, int32_t h, int32_t w, double* img_and_grads, void* stream);
 /* One pyramid level of Tracking.update_kf_reference (Tracking.py:243-314) for one keyframe: nearest depth
  * (stride `sub` into the full-resolution depth), back-projection, rel (3x4, DEVICE) into the last keyframe,
  * +-`border` px / depth mask, precalc_jacobians.  Outputs in the reference layout: vals (n), grads (n,2),

@@ -135,3 +135,18 @@ def test_ba_iterate_without_one_way_frames_vs_oracle():
     assert rel(dbg["g"], o["g"]) < 1e-6
     assert rel(s.kf_poses, sc["kf_poses"]) < 1e-5
     assert rel(s.P_m, sc["P_m"]) < 1e-5
+
+
+def test_img_and_grads_f64_vs_torch():
+    """Fused gray + Scharr (Mapping.get_img_and_grads) against the plain torch ops of the reference, odd sizes."""
+    from como_b200.odom.mapping_core import get_img_and_grads
+    for (H, W) in ((2, 2), (31, 47), (96, 128)):
+        g = torch.Generator().manual_seed(H)
+        rgb = torch.rand(1, 3, H, W, dtype=F64, generator=g)
+        gray = 0.2989 * rgb[:, 0:1] + 0.587 * rgb[:, 1:2] + 0.114 * rgb[:, 2:3]
+        kx = torch.tensor([[-3.0, 0, 3], [-10, 0, 10], [-3, 0, 3]], dtype=F64) / 32.0
+        ky = kx.t().contiguous()
+        xp = torch.nn.functional.pad(gray, (1, 1, 1, 1), mode="reflect")
+        ref = torch.cat((gray, torch.nn.functional.conv2d(xp, kx[None, None]), torch.nn.functional.conv2d(xp, ky[None, None])), 1)
+        out = get_img_and_grads(rgb.cuda())
+        np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=0, atol=1e-14)
