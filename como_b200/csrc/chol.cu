@@ -569,9 +569,28 @@ extern "C" int como_b200_chol_solve(const double* H, const double* g, int32_t n,
   }
   int grid = sm_count();
   if (grid > ntiles) grid = ntiles;
-  chol_factor_kernel<<<grid, CH_THREADS, sizeof(CholSmem), st>>>(v, table, ntiles);
-  int rc = check_launch("chol_factor");
-  if (rc) return rc;
-  chol_backsolve_kernel<<<nb, CH_THREADS, 0, st>>>(v, x, xflags);
-  return check_launch("chol_backsolve");
+  // Both kernels spin on flags written by other CTAs of the same grid: launched cooperatively so that the runtime
+  // refuses the launch (instead of letting it hang) if the CTAs cannot all be resident.
+  {
+    int nt = ntiles;
+    const int2* tb = table;
+    void* args[] = {(void*)&v, (void*)&tb, (void*)&nt};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)chol_factor_kernel, dim3(grid), dim3(CH_THREADS), args,
+                                                sizeof(CholSmem), st);
+    if (e != cudaSuccess) {
+      set_last_error("chol_factor: cooperative launch failed: %s", cudaGetErrorString(e));
+      return COMO_B200_ELAUNCH;
+    }
+  }
+  {
+    double* xp = x;
+    int* xf = xflags;
+    void* args[] = {(void*)&v, (void*)&xp, (void*)&xf};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)chol_backsolve_kernel, dim3(nb), dim3(CH_THREADS), args, 0, st);
+    if (e != cudaSuccess) {
+      set_last_error("chol_backsolve: cooperative launch failed: %s", cudaGetErrorString(e));
+      return COMO_B200_ELAUNCH;
+    }
+  }
+  return check_launch("chol_solve");
 }
