@@ -345,10 +345,16 @@ __global__ void chol_prep_kernel(CholView v, const double* __restrict__ g, int2*
     const int col = k * CT + c;
     v.aug[e] = (r == 0 && col < v.n) ? g[col] : 0.0;
   }
-  if (tid == 0) {
-    int t = 0;
-    for (int k = 0; k < v.nb; ++k)
-      for (int i = k; i <= v.nb; ++i) table[t++] = make_int2(i, k);
+  // column-major tile list: column k holds rows k..nb (nb = right-hand-side row), nb - k + 1 entries starting at
+  // k (nb + 1) - k (k - 1) / 2; every thread locates its own entries
+  const int ntiles = v.nb * (v.nb + 1) / 2 + v.nb;
+  for (int t = tid; t < ntiles; t += stride) {
+    int k = 0, off = 0;
+    while (off + (v.nb - k + 1) <= t) {
+      off += v.nb - k + 1;
+      ++k;
+    }
+    table[t] = make_int2(k + (t - off), k);
   }
 }
 
@@ -467,6 +473,13 @@ chol_backsolve_kernel(CholView v, double* __restrict__ x, int* __restrict__ xfla
   const int k = v.nb - 1 - blockIdx.x;   // late columns first (they are needed first)
   const int tid = threadIdx.x, c = tid & 63, part = tid >> 6;
   const int ld = v.nb * CT;
+  // the inverse of this column's diagonal block is needed at the very end of the chain: fetch it now
+  double linv_pref[16];
+  {
+    const double* li = v.linv + (size_t)k * CT * CT;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) linv_pref[q] = li[(16 * part + q) * CT + c];
+  }
   double s = 0.0;
   for (int i = v.nb - 1; i > k; --i) {
     double l[16];
@@ -491,12 +504,8 @@ chol_backsolve_kernel(CholView v, double* __restrict__ x, int* __restrict__ xfla
   __syncthreads();
   double p = 0.0;
   {
-    const double* li = v.linv + (size_t)k * CT * CT;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-      const int r = 16 * part + q;
-      p += li[r * CT + c] * s_x[r];
-    }
+    for (int q = 0; q < 16; ++q) p += linv_pref[q] * s_x[16 * part + q];
   }
   __syncthreads();
   s_part[part][c] = p;
