@@ -54,39 +54,37 @@ ba_residual_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ c
   __syncthreads();
   const int n0 = (blockIdx.x * (RA_THREADS / 32) + wid) * 32;
   if (n0 >= d.N) return;
-  const int m0 = 2 * lane;
-  const bool act = m0 < d.M;
-  double lv[7][2];
+  // ---- stage 1: 32 rows x 7 dot products as one (32 x 64) x (64 x 8) product on the FP64 tensor path.  The B
+  // fragments (logz_m and the six dlogz/dTwc columns, column 7 = 0) are constant for the keyframe and live in 16
+  // registers; A fragments come straight from HBM: for a fixed k-step the four lanes of a quad read one 32-byte
+  // sector of a predictor row, and every row is consumed completely over the 16 k-steps.  (This replaced 32
+  // double2 loads + 56 FMAs + a 31-step double-shuffle butterfly per 4 rows.)
+  const int g4 = lane >> 2, l4 = lane & 3;
+  double bfrag[16];
 #pragma unroll
-  for (int v = 0; v < 7; ++v) {
-    lv[v][0] = s_vec[v][m0 < BA_MAXM ? m0 : 0];
-    lv[v][1] = s_vec[v][m0 + 1 < BA_MAXM ? m0 + 1 : 0];
-  }
-  // ---- stage 1: 32 rows, 7 dot products each.  Four rows at a time: 4 x 8 partial products per lane are
-  // summed across the warp with one transposed butterfly (31 double shuffles for 28 dot products); lane
-  // 8*row+q ends with dot product q of that row and parks it in shared memory for stage 2.
+  for (int ks = 0; ks < 16; ++ks) bfrag[ks] = (g4 < 7) ? s_vec[g4][4 * ks + l4] : 0.0;
   __shared__ double s_dot[RA_THREADS / 32][32][8];
   const int32_t* crd = coords + 2 * ((size_t)i * d.N);
-  for (int j0 = 0; j0 < 32; j0 += 4) {
-    double2 row[4];
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int n = n0 + j0 + jj;
-      row[jj] = make_double2(0.0, 0.0);
-      if (n < d.N && act) {
-        const int r = crd[2 * n], c = crd[2 * n + 1];
-        row[jj] = *reinterpret_cast<const double2*>(Knm + (((size_t)i * d.H + r) * d.W + c) * d.M + m0);
-      }
+  for (int rt = 0; rt < 4; ++rt) {
+    const int n = n0 + 8 * rt + g4;
+    const bool rowok = n < d.N;
+    const double* row = Knm;
+    if (rowok) {
+      const int r = crd[2 * n], c = crd[2 * n + 1];
+      row = Knm + (((size_t)i * d.H + r) * d.W + c) * d.M;
     }
-    double v[32];
+    double a[16];
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
+    for (int ks = 0; ks < 16; ++ks) a[ks] = (rowok && 4 * ks + l4 < d.M) ? __ldg(row + 4 * ks + l4) : 0.0;
+    double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-      for (int q = 0; q < 7; ++q) v[jj * 8 + q] = row[jj].x * lv[q][0] + row[jj].y * lv[q][1];
-      v[jj * 8 + 7] = 0.0;
-    }
-    const double tot = warp_transpose_sum32(v);
-    s_dot[wid][j0 + (lane >> 3)][lane & 7] = tot;
+    for (int ks = 0; ks < 16; ++ks)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0), "+d"(c1)
+                   : "d"(a[ks]), "d"(bfrag[ks]));
+    s_dot[wid][8 * rt + g4][2 * l4] = c0;
+    s_dot[wid][8 * rt + g4][2 * l4 + 1] = c1;
   }
   __syncwarp();
   double mine[7];

@@ -209,13 +209,16 @@ def test_full_resolution_k8_window_vs_oracle():
     o = BO.iterate(sc, cfg)
     dbg = MC.iterate(s, cfg, return_debug=True)
     np.testing.assert_array_equal(dbg["coords_n"].cpu().numpy().astype(np.int64), o["coords_n"].numpy())
-    assert rel(dbg["H"], o["H"]) < 1e-6
-    assert rel(dbg["g"], o["g"]) < 1e-6
-    assert rel(s.kf_poses, sc["kf_poses"]) < 1e-5
-    assert rel(s.P_m, sc["P_m"]) < 1e-5
-    # the linear solve: residual of the normal equations in fp64
+    eH, eg = rel(dbg["H"], o["H"]), rel(dbg["g"], o["g"])
+    ep, eP = rel(s.kf_poses, sc["kf_poses"]), rel(s.P_m, sc["P_m"])
+    assert eH < 1e-6 and eg < 1e-6, (eH, eg)
+    assert ep < 1e-5 and eP < 1e-5, (ep, eP)
+    # the linear solve: residual of the normal equations in fp64 (backward error of the tiled Cholesky)
     Hs = torch.tril(dbg["H"]) + torch.tril(dbg["H"], -1).T
-    r = (Hs @ dbg["delta"].reshape(-1, 1) - dbg["g"].reshape(-1, 1)).abs().max() / dbg["g"].abs().max()
-    assert float(r) < 1e-9
+    x = dbg["delta"].reshape(-1, 1)
+    r = float((Hs @ x - dbg["g"].reshape(-1, 1)).abs().max() / (Hs.abs().max() * x.abs().max()))
+    assert r < 1e-12, r
+    # same state again: fp64 atomics reorder the sums of H (1e-16 relative), the ill-conditioned system amplifies that
     dbg2 = MC.iterate(s2, cfg, return_debug=True)
-    assert rel(dbg2["delta"], dbg["delta"]) < 1e-9
+    eH2, ed2 = rel(dbg2["H"], dbg["H"]), rel(dbg2["delta"], dbg["delta"])
+    assert eH2 < 1e-12 and ed2 < 1e-6, (eH2, ed2)
