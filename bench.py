@@ -598,7 +598,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ba_window", choices=["ba_window", "track640", "kf_init"])
-    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=74,
+                    help="track640: independent sequences per launch (74 -> 2 CTAs per sequence on 148 SMs)")
     ap.add_argument("--kf", type=int, default=BA_K)
     ap.add_argument("--oneway", type=int, default=BA_R)
     ap.add_argument("--shard", type=int, default=0, help="1: shard the pair blocks of ONE window over the GPUs")
