@@ -457,6 +457,81 @@ def gen_kfinit(name, H, W, NKF, M, iters=2):
           "size %.2f MB" % (os.path.getsize(os.path.join(GOLD, name + ".npz")) / 1e6))
 
 
+def gen_sfm(name, H, W, M, shift_px=2.5):
+    """Two-frame SfM bootstrap golden: the reference's TwoFrameSfm (como/odom/frontend/TwoFrameSfm.py,
+    two_frame_sfm.py) initialised on frame 0 and aligned against a translated frame 1.  Captured: everything
+    setup_reference produced (test coordinates in the reference's random pixel order, values, predictor pyramids,
+    intrinsics pyramid, prior linearisation), the target pyramid, the first normal equations of every level and the
+    per-level results."""
+    ref_harness.load_reference()
+    import como.odom.Mapping as MP
+    import como.odom.frontend.two_frame_sfm as TF2
+
+    MP.init_gpu = lambda d: None
+    cfg = copy.deepcopy(ref_cfg()["mapping"])
+    cfg["device"] = "cpu"
+    cfg["model_path"] = os.path.join(ref_harness.REF, "models", "scannet.ckpt")
+    cfg["sampling"]["max_num_coords"] = M
+    f = 525.0 * W / 640
+    K = torch.tensor([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]])
+    tex = synth.make_rgb(H, W, seed=1, cell=8, extra_w=16).double()
+    torch.manual_seed(0)
+    m = MP.Mapping(cfg, K)
+    m.setup()
+    sfm = m.two_frame_sfm
+    rgb0 = tex[..., 0:W].clone()
+    x1 = int(shift_px)
+    a = shift_px - x1
+    rgb1 = ((1 - a) * tex[..., x1:x1 + W] + a * tex[..., x1 + 1:x1 + 1 + W]).clone()
+    sfm.handle_frame(rgb0, 1.0)
+    cap = {"levels": [], "solve": []}
+    orig_level, orig_solve = TF2.two_frame_sfm, TF2.solve_delta
+
+    def level_hook(*a, **k):
+        cap["solve"].append([])
+        r = orig_level(*a, **k)
+        cap["levels"].append([_np(x).copy() for x in r])
+        return r
+
+    def solve_hook(Hm, g):
+        d = orig_solve(Hm, g)
+        cap["solve"][-1].append((_np(Hm).copy(), _np(g).copy(), _np(d).copy()))
+        return d
+
+    TF2.two_frame_sfm, TF2.solve_delta = level_hook, solve_hook
+    try:
+        img_and_grads1 = sfm.get_img_gradient_pyr(rgb1)
+        res = sfm.align_frame([x.clone() for x in img_and_grads1])
+    finally:
+        TF2.two_frame_sfm, TF2.solve_delta = orig_level, orig_solve
+    L = len(sfm.vals_pyr)
+    out = {"H": H, "W": W, "M": M, "levels": L, "gp_scale": float(m.model.get_scale(-1)),
+           "cov_params_img": _np(sfm.cov_params_img), "coords_m": _np(sfm.coords_m),
+           "dr_prior_dd": _np(sfm.dr_prior_dd), "H_prior_d_d": _np(sfm.H_prior_d_d),
+           "T_init": _np(sfm.T_curr_kf), "sparse_log_depth_init": _np(sfm.sparse_log_depth),
+           "sigma_photo": float(cfg["sigmas"]["photo"])}
+    for k, v in cfg["init"].items():
+        out["init_" + k] = v
+    for l in range(L):
+        out[f"l{l}_test_coords"] = _np(sfm.test_coords_pyr[l])
+        out[f"l{l}_vals"] = _np(sfm.vals_pyr[l])
+        out[f"l{l}_Knm_Kmminv"] = _np(sfm.Knm_Kmminv_pyr[l])
+        out[f"l{l}_intrinsics"] = _np(sfm.intrinsics_pyr[l])
+        out[f"l{l}_img_and_grads_ref"] = _np(sfm.img_and_grads[l])
+        out[f"l{l}_img_and_grads_j"] = _np(img_and_grads1[l])
+        Tl, dl, affl, cj, dj, mld = cap["levels"][l]
+        out[f"l{l}_T"], out[f"l{l}_sparse_log_depth"], out[f"l{l}_mean_log_depth"] = Tl, dl, mld
+        out[f"l{l}_num_valid"] = cj.shape[1]
+        out[f"l{l}_iters"] = len(cap["solve"][l])
+        out[f"l{l}_H0"], out[f"l{l}_g0"], out[f"l{l}_delta0"] = cap["solve"][l][0]
+    out["T_final"], out["sparse_log_depth_final"] = _np(res[0]), _np(res[1])
+    out["depth_final_sorted"] = np.sort(_np(res[4]).reshape(-1))
+    out["mean_log_depth_final"] = _np(res[5])
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "levels", L, "iters", [out[f"l{l}_iters"] for l in range(L)], "valid", [out[f"l{l}_num_valid"] for l in range(L)],
+          "t", res[0][0, :3, 3].tolist(), "size %.2f MB" % (os.path.getsize(os.path.join(GOLD, name + ".npz")) / 1e6))
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     os.makedirs(GOLD, exist_ok=True)
@@ -471,6 +546,8 @@ def main():
         gen_ba("ba_k4_full", 48, 64, 5, 3, 16, 4)
     if what in ("kfinit", "all"):
         gen_kfinit("kfinit_64x48", 48, 64, 4, 16)
+    if what in ("sfm", "all"):
+        gen_sfm("sfm_64x48", 48, 64, 16)
 
 
 if __name__ == "__main__":
