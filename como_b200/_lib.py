@@ -89,6 +89,9 @@ chol_solve = _sig("como_b200_chol_solve", C.c_int, [VP, VP, I32, VP, VP, C.c_siz
 kmat_rows = _sig("como_b200_kmat_rows", C.c_int, [VP, I32, I32, I32, VP, VP, VP, I32, F64, VP, VP, I64, VP, VP, VP, VP])
 weighted_gram = _sig("como_b200_weighted_gram", C.c_int, [VP, VP, VP, VP, I64, I32, F64, F64, VP, VP, VP, VP])
 rows_residual = _sig("como_b200_rows_residual", C.c_int, [VP, VP, VP, VP, I64, I32, VP, VP, VP])
+sfm_linearize = _sig("como_b200_sfm_linearize", C.c_int,
+                     [VP, VP, VP, VP, VP, I32, I32, I64, I32, C.POINTER(F64), C.POINTER(F64), VP, VP, VP, VP, VP])
+sfm_accumulate = _sig("como_b200_sfm_accumulate", C.c_int, [VP, VP, VP, I64, I32, VP, VP, VP, VP])
 reproject_dense = _sig("como_b200_reproject_dense", C.c_int,
                        [VP, I32, I32, C.POINTER(F64), C.POINTER(F64), F64, VP, VP, VP, VP, VP])
 sample_depth_gradmag = _sig("como_b200_sample_depth_gradmag", C.c_int, [VP, I32, I32, VP, VP, I32, VP, VP, VP])
@@ -112,7 +115,7 @@ DECLARED_SYMBOLS = [
     "como_b200_sampler_workspace_bytes", "como_b200_sampler_greedy", "como_b200_kmat_kmm", "como_b200_kmat_predictor",
     "como_b200_chol_solve_workspace_bytes", "como_b200_chol_solve",
     "como_b200_kmat_rows", "como_b200_weighted_gram", "como_b200_rows_residual",
-    "como_b200_reproject_dense", "como_b200_sample_depth_gradmag",
+    "como_b200_reproject_dense", "como_b200_sample_depth_gradmag", "como_b200_sfm_linearize", "como_b200_sfm_accumulate",
     "como_b200_gray_pyramid", "como_b200_image_gradients", "como_b200_img_and_grads_f64", "como_b200_kf_reference_level", "como_b200_reproj_depth",
 ]
 

@@ -12,7 +12,9 @@ What is replaced (reference name -> como_b200 implementation):
   como.odom.backend.linear_system.solve_system
   como.odom.frontend.corr.track_and_init (also as imported by como.odom.Mapping) and
   como.depth_cov.core.distill_depth.distill_depth_from_scratch / distill_conditional_depth_from_scratch
-Everything else (two-frame initialisation, UNet, orchestration) keeps running the reference's own Python on the
+  como.odom.frontend.two_frame_sfm.two_frame_sfm_pyr / two_frame_sfm / setup_reference (also as imported by
+  como.odom.frontend.TwoFrameSfm)
+Everything else (UNet, orchestration) keeps running the reference's own Python on the
 same device.  Requires tracking.dtype float / mapping.dtype double, color gray.
 """
 import sys
@@ -71,9 +73,19 @@ def install():
         return mc.get_img_and_grads(rgb.to(self.dtype)).to(self.dtype)
 
     ref_mapping.Mapping.get_img_and_grads = get_img_and_grads
+    import como.odom.frontend.two_frame_sfm as ref_sfm
+    import como.odom.frontend.TwoFrameSfm as ref_sfm_cls
+
+    from como_b200.odom.frontend import two_frame_sfm as b_sfm
+
+    for name in ("two_frame_sfm_pyr", "two_frame_sfm", "setup_reference"):
+        setattr(ref_sfm, name, getattr(b_sfm, name))
+    ref_sfm_cls.two_frame_sfm_pyr = b_sfm.two_frame_sfm_pyr
+    ref_sfm_cls.setup_reference = b_sfm.setup_reference
     ref_mapping.Mapping.iterate = iterate
     ref_mapping.Mapping.store_vars = store_vars
     ref_mapping.Mapping.prep_predictor = prep_predictor
     return {"patched": ["como_backends", "sample_sparse_coords", "photo_tracking_pyr", "precalc_jacobians",
                         "Mapping.iterate", "Mapping.store_vars", "Mapping.prep_predictor", "Mapping.get_img_and_grads", "solve_system",
-                        "track_and_init", "distill_depth_from_scratch", "distill_conditional_depth_from_scratch"]}
+                        "track_and_init", "distill_depth_from_scratch", "distill_conditional_depth_from_scratch",
+                        "two_frame_sfm_pyr", "setup_reference"]}

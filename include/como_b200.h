@@ -229,6 +229,22 @@ int como_b200_weighted_gram(const double* rows, const double* y, const double* v
                             void* stream);
 int como_b200_rows_residual(const double* rows, const double* x, const double* y, const uint8_t* mask, int64_t n,
                             int32_t M, double* res, double* stats3, void* stream);
+/* Two-frame SfM bootstrap (como/odom/frontend/two_frame_sfm.py:180-392), one Gauss-Newton iteration of
+ * the (6 + M) system [T_ji | sparse log depths]:
+ * sfm_linearize: Knm (N,M) predictor rows of the reference pixels, d (M) sparse log depths, coords (N,2) int64
+ *   [row,col], vals (N) reference intensities, img_and_grads (3,H,W) of the other frame, T_ji12 / intr4 HOST ->
+ *   rec (N,8) = [r (NaN if invalid), dI/dT (6), beta = dI/dP_i . P_i], absr (N) = rec[:,0] (input of the median),
+ *   proj (N,3) = [u, v, Z_j], stats2 = [sum_n logz_n, number of valid pixels].
+ * sfm_accumulate: sigma (DEVICE scalar, 1.4826 median |r|) -> G (M,M) = sum s beta^2 k k^T, St7 (7,M): rows 0..5 =
+ *   sum s beta dI/dT k^T, row 6 = sum s beta r k^T, small28 = [upper triangle of sum s dI/dT^T dI/dT (21),
+ *   sum s dI/dT r (6), sum w (r/sigma)^2], s = huber(r/sigma)/sigma^2. */
+int como_b200_sfm_linearize(const double* Knm, const double* d, const int64_t* coords, const double* vals,
+                            const double* img_and_grads, int32_t H, int32_t W, int64_t N, int32_t M,
+                            const double* T_ji12, const double* intr4, double* rec, double* absr, double* proj,
+                            double* stats2, void* stream);
+int como_b200_sfm_accumulate(const double* Knm, const double* rec, const double* sigma, int64_t N, int32_t M, double* G,
+                             double* St7, double* small28, void* stream);
+
 /* track_and_init helpers (como/odom/frontend/corr.py:37-43, 17-29, 80-96, 116-152).
  * reproject_dense: z_img (H,W) of the last keyframe, T_ji12 HOST row-major 3x4, intr4 HOST [fx,fy,cx,cy] ->
  *   coords_j (H*W,2) [row,col], logz_j, z_j (H*W), mask (H*W) = inside [1, dim-1) and z_j > min_depth.

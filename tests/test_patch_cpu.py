@@ -27,6 +27,8 @@ def test_install_rebinds_reference_names():
         assert sys.modules["como_backends"].__name__ == "como_b200.como_backends"
         assert "Mapping.iterate" in info["patched"]
         assert RM.track_and_init.__module__ == "como_b200.odom.frontend.corr"
+        import como.odom.frontend.TwoFrameSfm as RSC
+        assert RSC.two_frame_sfm_pyr.__module__ == "como_b200.odom.frontend.two_frame_sfm"
         import como.odom.frontend.corr as RC
         assert RC.distill_depth_from_scratch.__module__ == "como_b200.depth_cov.core.distill_depth"
         # no CPU fallback: the patched operators refuse CPU tensors loudly
