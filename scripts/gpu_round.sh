@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-for b in 37 74; do
-timeout 400 python bench.py --workload track640 --batch $b --steps 10 --warmup 3 > gpurun_out/bench_track_b$b.json 2> gpurun_out/bench_track_b$b.err; python -c "import json; d=json.loads(open('gpurun_out/bench_track_b$b.json').read()); print($b, d['ms_per_step'], d['value'], d['e2e']['value'], d['roofline']['frac'])" || tail -3 gpurun_out/bench_track_b$b.err
-done
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+timeout 600 python bench.py > gpurun_out/bench_ba_n1.json 2> gpurun_out/bench_ba_n1.err; python -c "import json; d=json.loads(open('gpurun_out/bench_ba_n1.json').read()); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['finite'], d['clocks']['reasons'])"
