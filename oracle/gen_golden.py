@@ -546,8 +546,12 @@ def main():
         gen_ba("ba_k4_full", 48, 64, 5, 3, 16, 4)
     if what in ("kfinit", "all"):
         gen_kfinit("kfinit_64x48", 48, 64, 4, 16)
+    if what in ("kfinit2", "all"):
+        gen_kfinit("kfinit_96x72", 72, 96, 3, 24)     # second shape: pins the oracle only (tests/test_oracle_kfinit.py)
     if what in ("sfm", "all"):
         gen_sfm("sfm_64x48", 48, 64, 16)
+    if what in ("sfm2", "all"):
+        gen_sfm("sfm_96x72", 72, 96, 24, shift_px=3.25)   # second shape: pins the oracle only (tests/test_oracle_sfm.py)
 
 
 if __name__ == "__main__":

@@ -16,9 +16,10 @@ def _case(g, ci):
     return pre, ins, corr, samp
 
 
-@pytest.mark.parametrize("ci", [0, 1, 2])
-def test_track_and_init_oracle(golden_dir, ci):
-    g = np.load(os.path.join(golden_dir, "kfinit_64x48.npz"), allow_pickle=True)
+@pytest.mark.parametrize("name,ci", [("kfinit_64x48", 0), ("kfinit_64x48", 1), ("kfinit_64x48", 2), ("kfinit_96x72", 0),
+                                     ("kfinit_96x72", 1)])
+def test_track_and_init_oracle(golden_dir, name, ci):
+    g = np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=True)
     pre, ins, corr, samp = _case(g, ci)
     dbg = {}
     c2, z2, mask, call, zall = KO.track_and_init(*ins, float(g["gp_scale"]), corr, samp, debug=dbg)

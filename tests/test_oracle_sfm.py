@@ -2,13 +2,14 @@
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import sfm_oracle as SO
 
 
-def load(golden_dir):
-    g = np.load(os.path.join(golden_dir, "sfm_64x48.npz"), allow_pickle=True)
+def load(golden_dir, name="sfm_64x48"):
+    g = np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=True)
     L = int(g["levels"])
     t = lambda k: torch.from_numpy(g[k])
     coords = [t(f"l{l}_test_coords")[0] for l in range(L)]
@@ -20,8 +21,9 @@ def load(golden_dir):
     return g, L, coords, vals, Knm, imgs, Ks, init
 
 
-def test_two_frame_sfm_oracle_vs_reference(golden_dir):
-    g, L, coords, vals, Knm, imgs, Ks, init = load(golden_dir)
+@pytest.mark.parametrize("name", ["sfm_64x48", "sfm_96x72"])
+def test_two_frame_sfm_oracle_vs_reference(golden_dir, name):
+    g, L, coords, vals, Knm, imgs, Ks, init = load(golden_dir, name)
     traces = []
     T, d, mld, pjv, zv, iters = SO.two_frame_sfm_pyr(
         torch.from_numpy(g["T_init"])[0], torch.from_numpy(g["sparse_log_depth_init"])[0], coords, vals, Knm, imgs, Ks,
