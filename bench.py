@@ -161,6 +161,11 @@ def run_track_ours(args, rank, world, device):
     peak, peak_src = measured_peaks()
     ach = alg_bytes / (kernel_ms * 1e-3) / 1e9
 
+    if args.no_e2e:
+        return {"value": its / (ms_max * 1e-3), "ms_per_step": ms_max / args.steps, "n_gpus": world,
+                "config": {"workload": "track640", "problems_per_gpu": B, "tuning_only": True},
+                "roofline": {"achieved": ach, "peak": peak, "frac": ach / peak, "alg_bytes_per_launch": alg_bytes,
+                             "launch_ms": kernel_ms}}, cases
     # e2e through the public API: B `Tracking` objects (one per sequence), each step every tracker handles one new
     # frame: pinned host RGB -> device, gray pyramid, tracking, reprojection statistics, keyframe decision (the
     # reference's handle_frame), pose read back to the host.
@@ -603,6 +608,7 @@ def main():
     ap.add_argument("--kf", type=int, default=BA_K)
     ap.add_argument("--oneway", type=int, default=BA_R)
     ap.add_argument("--shard", type=int, default=0, help="1: shard the pair blocks of ONE window over the GPUs")
+    ap.add_argument("--no-e2e", type=int, default=0, help="1: kernel-only sweep (tuning; no e2e / cpu_baseline legs)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -678,7 +684,7 @@ def main():
     if args.workload == "track640":
         res, cases = run_track_ours(args, rank, world, device)
         if rank == 0:
-            res["cpu_baseline"] = cpu_track_baseline(cases) if world == 1 else None
+            res["cpu_baseline"] = cpu_track_baseline(cases) if (world == 1 and not args.no_e2e) else None
             print(json.dumps(res))
     elif args.workload == "kf_init":
         res, case = run_kfinit_ours(args, rank, world, device)

@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcomo_b200.so")
 MAX_LEVELS = 8
-TRACK_STAT_STRIDE = 8
+TRACK_STAT_STRIDE = 32
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -47,6 +47,7 @@ track_pyr = _sig(
     "como_b200_track_pyr", C.c_int,
     [C.POINTER(TrackLevel), C.c_int32, C.c_int32, C.POINTER(TrackTerm), C.c_void_p, C.c_void_p, C.c_void_p,
      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p])
+track_debug_candidate_cap = _sig("como_b200_track_debug_candidate_cap", None, [C.c_int32])
 precalc_jacobians = _sig(
     "como_b200_precalc_jacobians", C.c_int,
     [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.c_void_p, C.c_void_p])
@@ -106,6 +107,7 @@ reproj_depth = _sig("como_b200_reproj_depth", C.c_int, [VP, I32, VP, C.POINTER(F
 # every symbol include/como_b200.h declares (checked by tests/test_abi.py without a GPU)
 DECLARED_SYMBOLS = [
     "como_b200_abi_version", "como_b200_last_error", "como_b200_track_workspace_bytes", "como_b200_track_pyr",
+    "como_b200_track_debug_candidate_cap",
     "como_b200_precalc_jacobians", "como_b200_median_workspace_bytes", "como_b200_median_f64", "como_b200_median_f32",
     "como_b200_subselect_pixels", "como_b200_ba_scaffold", "como_b200_predictor_apply", "como_b200_predictor_colsum",
     "como_b200_ba_frames_bytes", "como_b200_ba_partial_doubles", "como_b200_ba_unit_ints", "como_b200_ba_target_group",

@@ -5,32 +5,61 @@
 //   como/odom/frontend/photo_tracking.py:10-42,77-185, como/geometry/camera.py:57-68,
 //   como/odom/frontend/photo_utils.py:9-31, como/odom/backend/robust_loss.py:9-16.
 //
-// Per GN iteration a group of G co-resident CTAs runs five phases separated by four group barriers:
-//   1  warp + bilinear gather + residual r (kept in L2-resident scratch), 11-bit radix histogram of |r|
-//   2  pick bucket of the lower-median rank, histogram of the next 11 bits of the candidates
-//   3  same for the last 9 bits  -> exact median -> sigma_r = 1.4826 med
-//   4  Huber weights, J^T W J / J^T W r / error: registers -> warp shuffle -> CTA -> per-CTA partial row
-//   5  every CTA sums the partial rows in a fixed order (bitwise identical everywhere), solves the
-//      8x8 system (Cholesky), applies T <- T Exp(-d), a -= d6, b -= d7 and evaluates termination.
-// HBM traffic per pixel-iteration: P 12 B + I_ref 4 B + J 32 B + target 4 B (the 52 B of BASELINE.md).
+// Layout of the launch: grid (G, B) -- G co-resident CTAs share one of B independent problems.  A CTA is
+// 8 consumer warps + 1 producer warp.  The producer warp streams the CTA's slice of the operands through a
+// ring of shared-memory stages with the TMA unit (cp.async.bulk + mbarrier, SASS UBLKCP), always as far
+// ahead as the ring allows, so the HBM stream never waits for the reductions:
+//   pass-1 tiles: P (12 B/px) + I_ref (4 B/px) + mask (1 B/px)      1024 px per stage
+//   pass-2 tiles: J (32 B/px) + I_ref (4 B/px)                       512 px per stage
+// Per GN iteration (3 group barriers on the common path):
+//   pass 1   warp + bilinear gather (4 taps through the read-only path, the target image is L1/L2 resident)
+//            + residual r; r stays in shared memory when the slice fits (else an L2-resident scratch);
+//            2048-bin histogram of |r| with 1/64-octave bins over [2^-16, 2^16)          -> barrier
+//   median   the bin holding the lower-median rank is compacted (a few hundred candidates), barrier,
+//            every CTA selects the exact order statistic locally -> sigma = 1.4826 med.  Bins too
+//            crowded for the candidate list are narrowed by further 11-bit histogram passes (exact for
+//            any input, e.g. identical frames where every |r| is 0).
+//   pass 2   Huber weights, J^T W J / J^T W r / error: registers -> warp shuffle -> CTA -> per-CTA row -> barrier
+//   solve    every CTA sums the rows in a fixed order (bitwise identical everywhere, run to run), solves the
+//            8x8 system (Cholesky), applies T <- T Exp(-d), a -= d6, b -= d7 and evaluates termination.
+// HBM traffic per pixel-iteration: P 12 + I_ref 4 (+4 re-read in pass 2) + mask 1 + J 32 + target 4 B
+// (algorithmic: the 52 B of BASELINE.md).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
 
 namespace como {
 
-constexpr int TRK_THREADS = 512;
-constexpr int TRK_WARPS = TRK_THREADS / 32;
-constexpr int NACC = 45;        // 36 (upper triangle of 8x8) + 8 (gradient) + 1 (robust error)
+constexpr int CONS_WARPS = 8;
+constexpr int CONS_THREADS = CONS_WARPS * 32;
+constexpr int TRK_THREADS = CONS_THREADS + 32;  // + producer warp
+constexpr int T1 = 1024;                        // pixels per pass-1 stage
+constexpr int T2 = 512;                         // pixels per pass-2 stage
+constexpr int STAGE_BYTES = 18432;              // max(T1*(12+4+1), T2*(32+4))
+constexpr int T1_VALS_OFF = T1 * 12, T1_MASK_OFF = T1 * 16;
+constexpr int T2_VALS_OFF = T2 * 32;
+constexpr int STAGES = 3;
+constexpr int CHUNK_ALIGN = 256;  // slice starts: 16-byte aligned in every operand array
+constexpr int NACC = 45;          // 36 (upper triangle of 8x8) + 8 (gradient) + 1 (robust error)
 constexpr int NACC_PAD = 48;
-constexpr int HIST_BINS = 2048;  // bits [30:20], [19:9] -> 2048 bins; [8:0] -> 512 bins
+constexpr int HIST_BINS = 2048;
+constexpr int MAX_PASSES = 4;     // first histogram + at most 3 narrowing passes cover the 31-bit key
+constexpr int CAND_CAP = 2048;
 constexpr float HUBER_K = 1.345f;
+// first-pass bins: 0 = [0, KEY_LO), 1..2046 = 2^17 key codes each (1/64 octave), 2047 = [KEY_HI, 2^31)
+constexpr unsigned KEY_HI = 0x47800000u;                 // 2^16
+constexpr unsigned KEY_LO = KEY_HI - 2046u * 0x20000u;   // ~2^-16
+constexpr int MAX_GROUP = 1024;
 
 struct TrackCtl {
   unsigned barrier;
-  unsigned pad[31];
-  unsigned hist[2][3][HIST_BINS];
+  unsigned pad0[31];
+  unsigned cand_count[2];
+  unsigned pad1[30];
+  unsigned hist[2][MAX_PASSES][HIST_BINS];
+  unsigned cand[2][CAND_CAP];
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -39,72 +68,184 @@ struct TrackLayout {
   size_t levels_bytes, ctl_off, partials_off, resid_off, per_problem;
 };
 
-static TrackLayout track_layout(int max_n, int num_problems, int max_group) {
+static TrackLayout track_layout(int max_n, int num_problems) {
   TrackLayout L;
   L.levels_bytes = align_up((size_t)num_problems * COMO_B200_MAX_LEVELS * sizeof(como_b200_track_level_t), 256);
   L.ctl_off = 0;
   L.partials_off = align_up(sizeof(TrackCtl), 256);
-  L.resid_off = L.partials_off + align_up((size_t)max_group * NACC_PAD * sizeof(double), 256);
+  L.resid_off = L.partials_off + align_up((size_t)MAX_GROUP * NACC_PAD * sizeof(double), 256);
   L.per_problem = L.resid_off + align_up((size_t)max_n * sizeof(float), 256);
   return L;
 }
 
-// Find the bin holding 0-based rank k in a global histogram (read through L2), block-wide.
-// Returns (via shared) the bin, the rank inside the bin, and the total count.
-__device__ __forceinline__ void select_bin(const unsigned* __restrict__ gh, int nbins, unsigned k,
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CONS_THREADS) : "memory"); }
+
+// group barrier among the consumer threads of the G CTAs of one problem
+__device__ __forceinline__ void consumer_group_barrier(unsigned* counter, unsigned& epoch, unsigned group_size) {
+  __threadfence();
+  consumer_sync();
+  epoch += 1;
+  if (group_size > 1 && threadIdx.x == 0) {
+    red_release_add_u32(counter, 1u);
+    const unsigned target = epoch * group_size;
+    while (ld_acquire_u32(counter) < target) {
+    }
+  }
+  consumer_sync();
+}
+
+__device__ __forceinline__ unsigned first_bin(unsigned key) {
+  if (key < KEY_LO) return 0u;
+  const unsigned b = ((key - KEY_LO) >> 17) + 1u;
+  return b > 2047u ? 2047u : b;
+}
+
+__device__ __forceinline__ int clog2(unsigned w) { return w <= 1u ? 0 : 32 - __clz(w - 1u); }
+
+// Consumer-block search of the bin holding 0-based rank k in a 2048-bin histogram (shared, or global read
+// through L2).  k_is_median: k = (total-1)/2 (torch.median's lower median).  s_out: [bin, rank in bin, count in bin, total].
+__device__ __forceinline__ void select_bin(const unsigned* hist, bool global, unsigned k, bool k_is_median,
                                            unsigned* s_warp, unsigned* s_out) {
   const int tid = threadIdx.x;
-  const int per = nbins / TRK_THREADS;  // 4 or 1
-  unsigned c[4] = {0, 0, 0, 0};
-  unsigned local = 0;
-  for (int j = 0; j < per; ++j) {
-    c[j] = __ldcg(gh + tid * per + j);
-    local += c[j];
-  }
-  // inclusive scan over threads
-  unsigned incl = local;
   const int lane = tid & 31, wid = tid >> 5;
+  unsigned c[8];
+  if (global) {
+    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(hist) + 2 * tid);
+    const uint4 b = __ldcg(reinterpret_cast<const uint4*>(hist) + 2 * tid + 1);
+    c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+  } else {
+    const uint4 a = reinterpret_cast<const uint4*>(hist)[2 * tid];
+    const uint4 b = reinterpret_cast<const uint4*>(hist)[2 * tid + 1];
+    c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+  }
+  unsigned local = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) local += c[j];
+  unsigned incl = local;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
+  consumer_sync();  // previous readers of s_warp / s_out are done
   if (lane == 31) s_warp[wid] = incl;
-  __syncthreads();
-  unsigned base = 0;
-  for (int w2 = 0; w2 < wid; ++w2) base += s_warp[w2];
+  consumer_sync();
+  unsigned base = 0, total = 0;
+#pragma unroll
+  for (int w2 = 0; w2 < CONS_WARPS; ++w2) {
+    const unsigned v = s_warp[w2];
+    if (w2 < wid) base += v;
+    total += v;
+  }
   incl += base;
   const unsigned excl = incl - local;
-  if (tid == TRK_THREADS - 1) s_out[2] = incl;  // total
+  if (k_is_median) k = total > 0 ? (total - 1u) / 2u : 0u;
+  if (tid == 0) {
+    s_out[3] = total;
+    if (total == 0) s_out[0] = s_out[1] = s_out[2] = 0u;
+  }
   if (k >= excl && k < incl) {
     unsigned run = excl;
-    for (int j = 0; j < per; ++j) {
-      if (k < run + c[j]) {
-        s_out[0] = tid * per + j;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (k >= run && k < run + c[j]) {
+        s_out[0] = tid * 8 + j;
         s_out[1] = k - run;
-        break;
+        s_out[2] = c[j];
       }
       run += c[j];
     }
   }
-  __syncthreads();
+  consumer_sync();
 }
 
-__device__ __forceinline__ void flush_hist(unsigned* s_hist, unsigned* gh, int nbins) {
-  __syncthreads();
-  for (int b = threadIdx.x; b < nbins; b += TRK_THREADS) {
+// add the CTA histogram into the problem's global one and leave the shared copy zeroed
+__device__ __forceinline__ void flush_hist(unsigned* s_hist, unsigned* gh, bool single) {
+  consumer_sync();
+  for (int b = threadIdx.x; b < HIST_BINS; b += CONS_THREADS) {
     const unsigned v = s_hist[b];
-    if (v) atomicAdd(gh + b, v);
+    if (v) {
+      if (single) gh[b] = v;
+      else atomicAdd(gh + b, v);
+    }
     s_hist[b] = 0;
   }
-  __syncthreads();
 }
 
-__global__ void __launch_bounds__(TRK_THREADS, 1)
+struct SliceInfo {
+  int begin, len;
+};
+
+__device__ __forceinline__ SliceInfo slice_of(int N, int G, int c) {
+  int chunk = (N + G - 1) / G;
+  chunk = (chunk + CHUNK_ALIGN - 1) / CHUNK_ALIGN * CHUNK_ALIGN;
+  SliceInfo s;
+  s.begin = min(N, c * chunk);
+  s.len = min(N, s.begin + chunk) - s.begin;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// producer warp: one tile = wait for the stage to be released, tail elements by plain stores, then
+// one arrive.expect_tx + up to three bulk copies
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void produce_tile1(uint8_t* stage, unsigned long long* full, unsigned long long* empty,
+                                              unsigned n, const como_b200_track_level_t& lv, int i0, int cnt) {
+  const int lane = threadIdx.x & 31;
+  mbar_wait(empty, ((n / STAGES) & 1u) ^ 1u);
+  const int bulk = cnt & ~15;
+  const float* P = lv.P + 3 * (size_t)i0;
+  const float* V = lv.vals + i0;
+  for (int j = bulk + lane; j < cnt; j += 32) {
+    float* sp = reinterpret_cast<float*>(stage) + 3 * j;
+    sp[0] = P[3 * j];
+    sp[1] = P[3 * j + 1];
+    sp[2] = P[3 * j + 2];
+    reinterpret_cast<float*>(stage + T1_VALS_OFF)[j] = V[j];
+    if (lv.mask) (stage + T1_MASK_OFF)[j] = lv.mask[i0 + j];
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const unsigned bytes = (unsigned)bulk * (lv.mask ? 17u : 16u);
+    if (bytes) {
+      mbar_expect_tx(full, bytes);
+      bulk_g2s(stage, P, (unsigned)bulk * 12u, full);
+      bulk_g2s(stage + T1_VALS_OFF, V, (unsigned)bulk * 4u, full);
+      if (lv.mask) bulk_g2s(stage + T1_MASK_OFF, lv.mask + i0, (unsigned)bulk, full);
+    } else {
+      mbar_arrive(full);
+    }
+  }
+}
+
+__device__ __forceinline__ void produce_tile2(uint8_t* stage, unsigned long long* full, unsigned long long* empty,
+                                              unsigned n, const como_b200_track_level_t& lv, int i0, int cnt) {
+  const int lane = threadIdx.x & 31;
+  mbar_wait(empty, ((n / STAGES) & 1u) ^ 1u);
+  const int bulk = cnt & ~3;
+  const float* J = lv.J + 8 * (size_t)i0;
+  const float* V = lv.vals + i0;
+  for (int j = bulk + (lane >> 3); j < cnt; j += 4) {
+    reinterpret_cast<float*>(stage)[8 * j + (lane & 7)] = J[8 * j + (lane & 7)];
+    if ((lane & 7) == 0) reinterpret_cast<float*>(stage + T2_VALS_OFF)[j] = V[j];
+  }
+  __syncwarp();
+  if (lane == 0) {
+    if (bulk) {
+      mbar_expect_tx(full, (unsigned)bulk * 36u);
+      bulk_g2s(stage, J, (unsigned)bulk * 32u, full);
+      bulk_g2s(stage + T2_VALS_OFF, V, (unsigned)bulk * 4u, full);
+    } else {
+      mbar_arrive(full);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TRK_THREADS, 2)
 track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num_levels,
                  como_b200_track_term_t term, float* __restrict__ T_io, float* __restrict__ aff_io,
                  float* __restrict__ stats, int* __restrict__ num_iters, uint8_t* __restrict__ ws,
-                 TrackLayout lay) {
+                 TrackLayout lay, int r_cap, int cand_cap) {
   const int G = gridDim.x;
   const int c = blockIdx.x;
   const int prob = blockIdx.y;
@@ -114,51 +255,98 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
   uint8_t* base = ws + lay.levels_bytes + (size_t)prob * lay.per_problem;
   TrackCtl* ctl = reinterpret_cast<TrackCtl*>(base + lay.ctl_off);
   double* partials = reinterpret_cast<double*>(base + lay.partials_off);
-  float* resid = reinterpret_cast<float*>(base + lay.resid_off);
+  float* g_resid = reinterpret_cast<float*>(base + lay.resid_off);
   const como_b200_track_level_t* levels = levels_all + (size_t)prob * COMO_B200_MAX_LEVELS;
 
-  __shared__ unsigned s_hist[HIST_BINS];
-  __shared__ double s_red[TRK_WARPS][NACC_PAD];
+  extern __shared__ __align__(128) uint8_t dsm[];
+  uint8_t* ring = dsm;
+  float* s_r = reinterpret_cast<float*>(dsm + STAGES * STAGE_BYTES);
+
+  __shared__ __align__(16) unsigned s_hist[HIST_BINS];
+  __shared__ __align__(16) unsigned s_cand[CAND_CAP];
+  __shared__ double s_red[CONS_WARPS][NACC_PAD];
   __shared__ double s_acc[NACC_PAD];
+  __shared__ double s_chol[64];
+  __shared__ double s_delta[8];
+  __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES];
   __shared__ float s_T[16];
   __shared__ float s_aff[2];
   __shared__ float s_Pm[12];
   __shared__ float s_ea;
-  __shared__ unsigned s_warp[TRK_WARPS];
-  __shared__ unsigned s_sel[3];
-  __shared__ int s_done;
-  __shared__ double s_chol[64];
-  __shared__ double s_delta[8];
+  __shared__ unsigned s_warp[CONS_WARPS];
+  __shared__ unsigned s_sel[4];
+  __shared__ unsigned s_cnt, s_base;
+  __shared__ int s_done[2];
 
   for (int b = tid; b < HIST_BINS; b += TRK_THREADS) s_hist[b] = 0;
   if (tid < 16) s_T[tid] = T_io[prob * 16 + tid];
   if (tid < 2) s_aff[tid] = aff_io[prob * 2 + tid];
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], CONS_WARPS);
+    }
+    s_cnt = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   __syncthreads();
 
+  // ============================================================================================
+  // producer warp
+  // ============================================================================================
+  if (wid == CONS_WARPS) {
+    unsigned n = 0;
+    int pit = 0;
+    for (int l = 0; l < num_levels; ++l) {
+      const como_b200_track_level_t lv = levels[l];
+      if (lv.n <= 0) continue;
+      const SliceInfo sl = slice_of(lv.n, G, c);
+      for (;; ++pit) {
+        for (int t0 = 0; t0 < sl.len; t0 += T1, ++n) {
+          const unsigned s = n % STAGES;
+          produce_tile1(ring + s * STAGE_BYTES, &full_bar[s], &empty_bar[s], n, lv, sl.begin + t0, min(T1, sl.len - t0));
+        }
+        for (int t0 = 0; t0 < sl.len; t0 += T2, ++n) {
+          const unsigned s = n % STAGES;
+          produce_tile2(ring + s * STAGE_BYTES, &full_bar[s], &empty_bar[s], n, lv, sl.begin + t0, min(T2, sl.len - t0));
+        }
+        __syncthreads();  // the consumers' verdict for this iteration (flag double-buffered by iteration parity)
+        if (s_done[pit & 1]) {
+          ++pit;
+          break;
+        }
+      }
+    }
+    return;
+  }
+
+  // ============================================================================================
+  // consumer warps
+  // ============================================================================================
   unsigned epoch = 0;
+  unsigned n = 0;  // tile counter, mirrors the producer's
   int total_iter = 0;
   const int stats_cap = num_levels * term.max_iter;
+  const bool single = (G == 1);
 
   for (int l = 0; l < num_levels; ++l) {
     const como_b200_track_level_t lv = levels[l];
     const int N = lv.n;
+    if (N <= 0) continue;
     const int w = lv.w, h = lv.h;
-    int chunk = (N + G - 1) / G;
-    chunk = (chunk + 31) & ~31;
-    const int i_begin = min(N, c * chunk);
-    const int i_end = min(N, i_begin + chunk);
+    const SliceInfo sl = slice_of(N, G, c);
     const float Ax = 1.0f / (float)w, Ay = 1.0f / (float)h;
     const float wf = (float)w, hf = (float)h;
     const float xmax = (float)(w - 1), ymax = (float)(h - 1);
+    float* g_r = g_resid + sl.begin;  // residual of slice pixel j: s_r[j] if j < r_cap else g_r[j]
 
     double mse_prev = INFINITY;
     int it = 0;
-    bool level_done = (N <= 0);
+    bool level_done = false;
     while (!level_done) {
       const int par = total_iter & 1;
-      unsigned* gh0 = ctl->hist[par][0];
-      unsigned* gh1 = ctl->hist[par][1];
-      unsigned* gh2 = ctl->hist[par][2];
+      unsigned* gh = &ctl->hist[par][0][0];
 
       // ---- per-iteration constants: Pmat = K * T[0:3,:], e^{-a}
       if (tid < 12) {
@@ -167,32 +355,41 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
                     lv.K[r * 3 + 2] * s_T[2 * 4 + cc];
       }
       if (tid == 12) s_ea = expf(-s_aff[0]);
-      __syncthreads();
+      consumer_sync();
       const float p00 = s_Pm[0], p01 = s_Pm[1], p02 = s_Pm[2], p03 = s_Pm[3];
       const float p10 = s_Pm[4], p11 = s_Pm[5], p12 = s_Pm[6], p13 = s_Pm[7];
       const float p20 = s_Pm[8], p21 = s_Pm[9], p22 = s_Pm[10], p23 = s_Pm[11];
       const float ea = s_ea, bb = s_aff[1];
 
-      // ---- phase 1: warp, gather, residual, first radix histogram.  Four pixels per thread and trip so that
-      // the operand loads, and then the 16 bilinear taps, are all in flight together (memory-level parallelism).
-      constexpr int PB = 4;
-      for (int i0 = i_begin + tid; i0 < i_end; i0 += TRK_THREADS * PB) {
+      // ---- pass 1: warp, gather, residual, first histogram.  Four pixels per thread and tile so that the
+      // 16 bilinear taps are all in flight together.
+      constexpr int PB = T1 / CONS_THREADS;
+      for (int t0 = 0; t0 < sl.len; t0 += T1, ++n) {
+        const unsigned s = n % STAGES;
+        const uint8_t* stage = ring + s * STAGE_BYTES;
+        const int cnt = min(T1, sl.len - t0);
+        mbar_wait(&full_bar[s], (n / STAGES) & 1u);
+        const float* sP = reinterpret_cast<const float*>(stage);
+        const float* sV = reinterpret_cast<const float*>(stage + T1_VALS_OFF);
+        const uint8_t* sM = stage + T1_MASK_OFF;
         float X[PB], Y[PB], Z[PB], vref[PB];
         bool use[PB];
 #pragma unroll
         for (int k = 0; k < PB; ++k) {
-          const int i = i0 + k * TRK_THREADS;
-          use[k] = (i < i_end) && (lv.mask ? (lv.mask[i] != 0) : true);
+          const int j = tid + k * CONS_THREADS;
+          use[k] = (j < cnt) && (lv.mask ? (sM[j] != 0) : true);
           X[k] = Y[k] = 0.0f;
           Z[k] = 1.0f;
           vref[k] = 0.0f;
           if (use[k]) {
-            X[k] = lv.P[3 * i + 0];
-            Y[k] = lv.P[3 * i + 1];
-            Z[k] = lv.P[3 * i + 2];
-            vref[k] = lv.vals[i];
+            X[k] = sP[3 * j + 0];
+            Y[k] = sP[3 * j + 1];
+            Z[k] = sP[3 * j + 2];
+            vref[k] = sV[j];
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);  // operands are in registers: release the stage early
         float w00[PB], w01[PB], w10[PB], w11[PB];
         const float* t00[PB];
         int dxs[PB], dys[PB];
@@ -237,8 +434,8 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         }
 #pragma unroll
         for (int k = 0; k < PB; ++k) {
-          const int i = i0 + k * TRK_THREADS;
-          if (i < i_end) {
+          const int j = tid + k * CONS_THREADS;
+          if (j < cnt) {
             float r = __int_as_float(0x7fc00000);
             if (valid[k]) {
               float v = v00[k] * w00[k];
@@ -247,81 +444,135 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
               v += v11[k] * w11[k];
               const float tmp = ea * v;
               r = (tmp + bb) - vref[k];
-              const unsigned key = __float_as_uint(fabsf(r));
-              atomicAdd(&s_hist[key >> 20], 1u);
+              atomicAdd(&s_hist[first_bin(__float_as_uint(fabsf(r)))], 1u);
             }
-            resid[i] = r;
+            const int js = t0 + j;
+            if (js < r_cap) s_r[js] = r;
+            else __stcg(g_r + js, r);
           }
         }
       }
-      flush_hist(s_hist, gh0, HIST_BINS);
-      group_barrier(&ctl->barrier, epoch, G);
+      flush_hist(s_hist, gh, single);
+      consumer_group_barrier(&ctl->barrier, epoch, G);
 
-      // ---- phase 2
-      // rank of the lower median among nvalid values: (nvalid-1)/2  (torch.median semantics)
-      select_bin(gh0, HIST_BINS, 0xffffffffu, s_warp, s_sel);  // first call only to get the total
-      const unsigned nvalid = s_sel[2];
-      __syncthreads();
-      unsigned key_prefix = 0;
+      // ---- exact lower median of |r| over the whole problem
+      select_bin(gh, true, 0u, true, s_warp, s_sel);
+      const unsigned nvalid = s_sel[3];
       float sigma = __int_as_float(0x7fc00000);
       if (nvalid > 0) {
-        const unsigned k0 = (nvalid - 1) / 2;
-        select_bin(gh0, HIST_BINS, k0, s_warp, s_sel);
-        const unsigned b0 = s_sel[0], k1 = s_sel[1];
-        __syncthreads();
-        for (int i = i_begin + tid; i < i_end; i += TRK_THREADS) {
-          const float r = resid[i];
-          if (r == r) {
-            const unsigned key = __float_as_uint(fabsf(r));
-            if ((key >> 20) == b0) atomicAdd(&s_hist[(key >> 9) & 2047u], 1u);
-          }
+        unsigned bin = s_sel[0], krank = s_sel[1], cnt_in = s_sel[2];
+        unsigned klo, khi;
+        if (bin == 0u) {
+          klo = 0u;
+          khi = KEY_LO;
+        } else if (bin == 2047u) {
+          klo = KEY_HI;
+          khi = 0x80000000u;
+        } else {
+          klo = KEY_LO + ((bin - 1u) << 17);
+          khi = klo + 0x20000u;
         }
-        flush_hist(s_hist, gh1, HIST_BINS);
-        group_barrier(&ctl->barrier, epoch, G);
-        // ---- phase 3
-        select_bin(gh1, HIST_BINS, k1, s_warp, s_sel);
-        const unsigned b1 = s_sel[0], k2 = s_sel[1];
-        __syncthreads();
-        const unsigned pre = (b0 << 11) | b1;
-        for (int i = i_begin + tid; i < i_end; i += TRK_THREADS) {
-          const float r = resid[i];
-          if (r == r) {
-            const unsigned key = __float_as_uint(fabsf(r));
-            if ((key >> 9) == pre) atomicAdd(&s_hist[key & 511u], 1u);
+        int pass = 0;
+        while (khi - klo > 1u) {
+          if (cnt_in <= (unsigned)cand_cap) {
+            // compact this CTA's candidates, append them to the problem's list, then select locally
+            for (int j = tid; j < sl.len; j += CONS_THREADS) {
+              const float r = (j < r_cap) ? s_r[j] : __ldcg(g_r + j);
+              if (r == r) {
+                const unsigned key = __float_as_uint(fabsf(r));
+                if (key >= klo && key < khi) s_cand[atomicAdd(&s_cnt, 1u)] = key;
+              }
+            }
+            consumer_sync();
+            const unsigned mine = s_cnt;
+            if (!single) {
+              if (tid == 0) s_base = atomicAdd(&ctl->cand_count[par], mine);
+              consumer_sync();
+              const unsigned gb = s_base;
+              for (unsigned j = tid; j < mine; j += CONS_THREADS) __stcg(&ctl->cand[par][gb + j], s_cand[j]);
+              consumer_group_barrier(&ctl->barrier, epoch, G);
+              for (unsigned j = tid; j < cnt_in; j += CONS_THREADS) s_cand[j] = __ldcg(&ctl->cand[par][j]);
+            }
+            if (tid == 0) s_cnt = 0;
+            consumer_sync();
+            while (khi - klo > 1u) {
+              const int sh = max(0, clog2(khi - klo) - 11);
+              for (unsigned j = tid; j < cnt_in; j += CONS_THREADS) {
+                const unsigned key = s_cand[j];
+                if (key >= klo && key < khi) atomicAdd(&s_hist[(key - klo) >> sh], 1u);
+              }
+              consumer_sync();
+              select_bin(s_hist, false, krank, false, s_warp, s_sel);
+              const unsigned b2 = s_sel[0];
+              krank = s_sel[1];
+              for (int b = tid; b < HIST_BINS; b += CONS_THREADS) s_hist[b] = 0;
+              consumer_sync();
+              klo += b2 << sh;
+              khi = min(khi, klo + (1u << sh));
+            }
+            break;
           }
+          // crowded bin: narrow it with another histogram pass over the problem
+          ++pass;
+          const int sh = max(0, clog2(khi - klo) - 11);
+          for (int j = tid; j < sl.len; j += CONS_THREADS) {
+            const float r = (j < r_cap) ? s_r[j] : __ldcg(g_r + j);
+            if (r == r) {
+              const unsigned key = __float_as_uint(fabsf(r));
+              if (key >= klo && key < khi) atomicAdd(&s_hist[(key - klo) >> sh], 1u);
+            }
+          }
+          flush_hist(s_hist, gh + pass * HIST_BINS, single);
+          consumer_group_barrier(&ctl->barrier, epoch, G);
+          select_bin(gh + pass * HIST_BINS, true, krank, false, s_warp, s_sel);
+          const unsigned b2 = s_sel[0];
+          krank = s_sel[1];
+          cnt_in = s_sel[2];
+          klo += b2 << sh;
+          khi = min(khi, klo + (1u << sh));
         }
-        flush_hist(s_hist, gh2, 512);
-        group_barrier(&ctl->barrier, epoch, G);
-        select_bin(gh2, 512, k2, s_warp, s_sel);
-        key_prefix = (pre << 9) | s_sel[0];
-        __syncthreads();
-        sigma = 1.4826f * __uint_as_float(key_prefix);
-      } else {
-        group_barrier(&ctl->barrier, epoch, G);
-        group_barrier(&ctl->barrier, epoch, G);
+        consumer_sync();
+        sigma = 1.4826f * __uint_as_float(klo);
       }
 
-      // ---- phase 4: robust weights + normal equations
+      // ---- pass 2: robust weights + normal equations
       float acc[NACC];
 #pragma unroll
       for (int k = 0; k < NACC; ++k) acc[k] = 0.0f;
       const float inv_sigma = 1.0f / sigma;
-      for (int i0 = i_begin + tid; i0 < i_end; i0 += 2 * TRK_THREADS) {
-        float rr[2], vv[2];
+      const int hsel = (tid >> 2) & 1;  // which half of the 32-byte J row this lane reads first (bank spreading)
+      for (int t0 = 0; t0 < sl.len; t0 += T2, ++n) {
+        const unsigned s = n % STAGES;
+        const uint8_t* stage = ring + s * STAGE_BYTES;
+        const int cnt = min(T2, sl.len - t0);
+        float rr[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int j = tid + k * CONS_THREADS;
+          const int js = t0 + j;
+          rr[k] = __int_as_float(0x7fc00000);
+          if (j < cnt) rr[k] = (js < r_cap) ? s_r[js] : __ldcg(g_r + js);
+        }
+        mbar_wait(&full_bar[s], (n / STAGES) & 1u);
+        const float4* sJ = reinterpret_cast<const float4*>(stage);
+        const float* sV = reinterpret_cast<const float*>(stage + T2_VALS_OFF);
+        float vv[2];
         float4 ja[2], jb[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          const int i = i0 + k * TRK_THREADS;
-          rr[k] = __int_as_float(0x7fc00000);
+          const int j = tid + k * CONS_THREADS;
           vv[k] = 0.0f;
           ja[k] = jb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i < i_end) {
-            rr[k] = resid[i];
-            vv[k] = lv.vals[i];
-            ja[k] = *reinterpret_cast<const float4*>(lv.J + 8 * (size_t)i);
-            jb[k] = *reinterpret_cast<const float4*>(lv.J + 8 * (size_t)i + 4);
+          if (j < cnt) {
+            vv[k] = sV[j];
+            const float4 q0 = sJ[2 * j + hsel];
+            const float4 q1 = sJ[2 * j + (hsel ^ 1)];
+            ja[k] = hsel ? q1 : q0;
+            jb[k] = hsel ? q0 : q1;
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const float r = rr[k];
@@ -348,34 +599,33 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         const float s = warp_sum(acc[k]);
         if (lane == 0) s_red[wid][k] = (double)s;
       }
-      __syncthreads();
+      consumer_sync();
       if (tid < NACC) {
         double s = 0.0;
 #pragma unroll
-        for (int w2 = 0; w2 < TRK_WARPS; ++w2) s += s_red[w2][tid];
-        __stcg(partials + (size_t)c * NACC_PAD + tid, s);
+        for (int w2 = 0; w2 < CONS_WARPS; ++w2) s += s_red[w2][tid];
+        if (single) s_acc[tid] = s;
+        else __stcg(partials + (size_t)c * NACC_PAD + tid, s);
       }
-      // zero the other parity's histograms for the next iteration (nobody reads them any more)
+      // zero the other parity's histograms / candidate counter for the next iteration (nobody reads them any more)
       {
         unsigned* nz = &ctl->hist[par ^ 1][0][0];
-        for (int b = c * TRK_THREADS + tid; b < 3 * HIST_BINS; b += G * TRK_THREADS) nz[b] = 0u;
+        for (int b = c * CONS_THREADS + tid; b < MAX_PASSES * HIST_BINS; b += G * CONS_THREADS) nz[b] = 0u;
+        if (c == 0 && tid == 0) ctl->cand_count[par ^ 1] = 0u;
       }
-      __threadfence();
-      group_barrier(&ctl->barrier, epoch, G);
+      consumer_group_barrier(&ctl->barrier, epoch, G);
 
-      // ---- phase 5: deterministic cross-CTA sum, solve, update, termination (identical in every CTA)
-      if (tid < NACC_PAD * 8) {
-        const int k = tid >> 3, s8 = tid & 7;
+      // ---- deterministic cross-CTA sum, solve, update, termination (identical in every CTA)
+      if (!single) {
+        const int k = tid >> 2, s4 = tid & 3;
         double s = 0.0;
         if (k < NACC)
-          for (int cc = s8; cc < G; cc += 8) s += __ldcg(partials + (size_t)cc * NACC_PAD + k);
-        // fixed-order combine of the 8 strided partial sums
+          for (int cc = s4; cc < G; cc += 4) s += __ldcg(partials + (size_t)cc * NACC_PAD + k);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (s8 == 0 && k < NACC) s_acc[k] = s;
+        if (s4 == 0 && k < NACC) s_acc[k] = s;
+        consumer_sync();
       }
-      __syncthreads();
       if (wid == 0) {
         // 8x8 solve by one warp: lane i < 8 owns row i (packed upper triangle -> full row)
         double row[8];
@@ -398,6 +648,25 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         __syncwarp();
         if (lane == 0) {
           const double mse = s_acc[44] / (double)nvalid;
+          const double dn = sqrt(dn2), gnorm = sqrt(gn2);
+          const double rel = fabs((mse_prev - mse) / mse_prev);  // NaN on the first iteration -> false
+          const bool done = (it + 1 >= term.max_iter) || (dn < (double)term.delta_norm) ||
+                            (rel < (double)term.rel_tol) || (gnorm < (double)term.grad_norm) || (nvalid == 0);
+          if (c == 0 && stats != nullptr && total_iter < stats_cap) {
+            float* st = stats + ((size_t)prob * stats_cap + total_iter) * COMO_B200_TRACK_STAT_STRIDE;
+            st[0] = (float)l;
+            st[1] = (float)mse;
+            st[2] = (float)gnorm;
+            st[3] = (float)dn;
+            st[4] = sigma;
+            st[5] = (float)nvalid;
+            st[6] = done ? 1.0f : 0.0f;
+            st[7] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) st[8 + k] = s_T[k];  // the iterate this record was evaluated at
+            st[24] = s_aff[0];
+            st[25] = s_aff[1];
+          }
           // T <- T * Exp(-delta[0:6]); COMO tangent [omega, v] -> lietorch [tau=v, phi=omega]
           const double tau[3] = {-s_delta[3], -s_delta[4], -s_delta[5]};
           const double phi[3] = {-s_delta[0], -s_delta[1], -s_delta[2]};
@@ -417,31 +686,15 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
           for (int k = 0; k < 16; ++k) s_T[k] = Tn[k];
           s_aff[0] = (float)((double)s_aff[0] - s_delta[6]);
           s_aff[1] = (float)((double)s_aff[1] - s_delta[7]);
-          const double dn = sqrt(dn2), gnorm = sqrt(gn2);
-          const double rel = fabs((mse_prev - mse) / mse_prev);  // NaN on the first iteration -> false
-          const bool done = (it + 1 >= term.max_iter) || (dn < (double)term.delta_norm) ||
-                            (rel < (double)term.rel_tol) || (gnorm < (double)term.grad_norm) || (nvalid == 0);
-          s_done = done ? 1 : 0;
+          s_done[total_iter & 1] = done ? 1 : 0;
           s_acc[45] = mse;
-          if (c == 0 && stats != nullptr && total_iter < stats_cap) {
-            float* st = stats + ((size_t)prob * stats_cap + total_iter) * COMO_B200_TRACK_STAT_STRIDE;
-            st[0] = (float)l;
-            st[1] = (float)mse;
-            st[2] = (float)gnorm;
-            st[3] = (float)dn;
-            st[4] = sigma;
-            st[5] = (float)nvalid;
-            st[6] = done ? 1.0f : 0.0f;
-            st[7] = 0.0f;
-          }
         }
       }
-      __syncthreads();
+      __syncthreads();  // with the producer warp: s_done is this iteration's verdict
       mse_prev = s_acc[45];
-      level_done = (s_done != 0);
+      level_done = (s_done[total_iter & 1] != 0);
       ++it;
       ++total_iter;
-      __syncthreads();
     }
   }
   if (c == 0) {
@@ -451,12 +704,59 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
   }
 }
 
-static int track_max_group(int num_problems) {
-  int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, track_pyr_kernel, TRK_THREADS, 0);
-  const int total = per_sm * sm_count();
-  return total / (num_problems > 0 ? num_problems : 1);
+struct TrackLaunchCfg {
+  int G, r_cap;
+  size_t dyn_smem;
+};
+
+// Launch shape: G CTAs per problem, 1 or 2 CTAs per SM.  One CTA per SM (the residual slice stays in shared
+// memory) while the problems fit that way; two per SM for larger batches so that one CTA streams while the
+// other sits in a reduction.  COMO_B200_TRACK_G / COMO_B200_TRACK_OCC override (tuning only).
+static int track_config(int num_problems, int max_n, TrackLaunchCfg* cfg) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int smem_sm = 0, smem_optin = 0;
+  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, track_pyr_kernel) != cudaSuccess) return -1;
+  const int sms = sm_count();
+  const int g_want = max_n > 0 ? (max_n + 2047) / 2048 : 1;
+  const char* e_occ = getenv("COMO_B200_TRACK_OCC");
+  const char* e_g = getenv("COMO_B200_TRACK_G");
+  int occ = ((long long)num_problems * (g_want < 8 ? g_want : 8) > sms) ? 2 : 1;
+  if (e_occ) occ = atoi(e_occ) >= 2 ? 2 : 1;
+  for (;; occ = 1) {
+    const int per_cta = (occ == 1) ? smem_optin : (smem_sm / 2 - 1024);
+    long long dyn = (long long)per_cta - (long long)fa.sharedSizeBytes;
+    if (dyn > smem_optin - (int)fa.sharedSizeBytes) dyn = smem_optin - (int)fa.sharedSizeBytes;
+    long long r_bytes = dyn - (long long)STAGES * STAGE_BYTES;
+    if (r_bytes < 0) {
+      if (occ == 2) continue;
+      return -1;
+    }
+    int r_cap = (int)(r_bytes / 4) / CHUNK_ALIGN * CHUNK_ALIGN;
+    size_t dyn_smem = (size_t)STAGES * STAGE_BYTES + (size_t)r_cap * 4;
+    cudaFuncSetAttribute(track_pyr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, track_pyr_kernel, TRK_THREADS, dyn_smem);
+    if (per_sm > occ) per_sm = occ;
+    const int cap = per_sm * sms / (num_problems > 0 ? num_problems : 1);
+    if (cap < 1) {
+      if (occ == 2) continue;
+      return 0;
+    }
+    int G = g_want < cap ? g_want : cap;
+    if (e_g && atoi(e_g) >= 1) G = atoi(e_g) < cap ? atoi(e_g) : cap;
+    if (G > MAX_GROUP) G = MAX_GROUP;
+    cfg->G = G;
+    cfg->r_cap = r_cap;
+    cfg->dyn_smem = dyn_smem;
+    return G;
+  }
 }
+
+static int g_track_cand_cap = CAND_CAP;
 
 // ---------------------------------------------------------------------------------------------
 // precalc_jacobians: dI/dxi = gradI * dpi/dP * [-P^ | I]; cols 6,7 = [I_ref, 1].
@@ -493,8 +793,12 @@ using namespace como;
 
 extern "C" size_t como_b200_track_workspace_bytes(int32_t max_n, int32_t num_problems) {
   if (max_n < 0 || num_problems <= 0) return 0;
-  const TrackLayout L = track_layout(max_n, num_problems, 1024);
+  const TrackLayout L = track_layout(max_n, num_problems);
   return L.levels_bytes + (size_t)num_problems * L.per_problem;
+}
+
+extern "C" void como_b200_track_debug_candidate_cap(int32_t cap) {
+  g_track_cand_cap = cap < 0 ? 0 : (cap > CAND_CAP ? CAND_CAP : cap);
 }
 
 extern "C" int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_t num_levels,
@@ -513,15 +817,14 @@ extern "C" int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_
       const como_b200_track_level_t& lv = levels[p * num_levels + l];
       COMO_REQUIRE(lv.n >= 0 && lv.w >= 3 && lv.h >= 3, "track_pyr: bad level shape n=%d w=%d h=%d", lv.n, lv.w, lv.h);
       COMO_REQUIRE(lv.n == 0 || (lv.vals && lv.P && lv.J && lv.img), "track_pyr: null level pointer");
-      COMO_REQUIRE(((uintptr_t)lv.J & 15) == 0, "track_pyr: J must be 16-byte aligned");
+      COMO_REQUIRE((((uintptr_t)lv.J | (uintptr_t)lv.P | (uintptr_t)lv.vals | (uintptr_t)lv.mask) & 15) == 0,
+                   "track_pyr: vals, P, J and mask must be 16-byte aligned");
       if (lv.n > max_n) max_n = lv.n;
     }
-  const int max_group = track_max_group(num_problems);
-  COMO_REQUIRE(max_group >= 1, "track_pyr: %d problems exceed the co-resident CTA capacity", num_problems);
-  int G = (max_n + 2 * TRK_THREADS - 1) / (2 * TRK_THREADS);
-  if (G < 1) G = 1;
-  if (G > max_group) G = max_group;
-  const TrackLayout L = track_layout(max_n, num_problems, 1024);
+  TrackLaunchCfg cfg;
+  const int G = track_config(num_problems, max_n, &cfg);
+  COMO_REQUIRE(G >= 1, "track_pyr: %d problems exceed the co-resident CTA capacity", num_problems);
+  const TrackLayout L = track_layout(max_n, num_problems);
   const size_t need = L.levels_bytes + (size_t)num_problems * L.per_problem;
   if (workspace_bytes < need) {
     set_last_error("track_pyr: workspace %zu < required %zu", workspace_bytes, need);
@@ -529,21 +832,32 @@ extern "C" int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_
   }
   uint8_t* ws = (uint8_t*)workspace;
   // level descriptors -> device (padded to MAX_LEVELS per problem) through a small ring of pinned
-  // staging slots, each guarded by an event so the host never blocks on the stream
+  // staging slots per device, each guarded by an event so the host never blocks on the stream
   {
     constexpr int SLOTS = 8;
+    constexpr int MAX_DEV = 16;
     struct Slot {
       como_b200_track_level_t* buf = nullptr;
       size_t cap = 0;
       cudaEvent_t ev = nullptr;
     };
-    static thread_local Slot ring[SLOTS];
-    static thread_local int next = 0;
-    Slot& sl = ring[next];
-    next = (next + 1) % SLOTS;
+    static thread_local Slot ring[MAX_DEV][SLOTS];
+    static thread_local int next[MAX_DEV] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    COMO_REQUIRE(dev >= 0 && dev < MAX_DEV, "track_pyr: device index %d not supported", dev);
+    Slot& sl = ring[dev][next[dev]];
+    next[dev] = (next[dev] + 1) % SLOTS;
     const size_t cnt = (size_t)num_problems * COMO_B200_MAX_LEVELS;
-    if (sl.ev == nullptr) cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming);
-    else cudaEventSynchronize(sl.ev);
+    if (sl.ev == nullptr) {
+      if (cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming) != cudaSuccess) {
+        sl.ev = nullptr;
+        set_last_error("track_pyr: event creation failed");
+        return COMO_B200_ELAUNCH;
+      }
+    } else {
+      cudaEventSynchronize(sl.ev);
+    }
     if (sl.cap < cnt) {
       if (sl.buf) cudaFreeHost(sl.buf);
       if (cudaMallocHost((void**)&sl.buf, cnt * sizeof(como_b200_track_level_t)) != cudaSuccess) {
@@ -557,8 +871,11 @@ extern "C" int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_
     memset(sl.buf, 0, cnt * sizeof(como_b200_track_level_t));
     for (int p = 0; p < num_problems; ++p)
       for (int l = 0; l < num_levels; ++l) sl.buf[p * COMO_B200_MAX_LEVELS + l] = levels[p * num_levels + l];
-    cudaMemcpyAsync(ws, sl.buf, cnt * sizeof(como_b200_track_level_t), cudaMemcpyHostToDevice, stream);
-    cudaEventRecord(sl.ev, stream);
+    if (cudaMemcpyAsync(ws, sl.buf, cnt * sizeof(como_b200_track_level_t), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
+        cudaEventRecord(sl.ev, stream) != cudaSuccess) {
+      set_last_error("track_pyr: descriptor upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return COMO_B200_ELAUNCH;
+    }
   }
   for (int p = 0; p < num_problems; ++p)
     cudaMemsetAsync(ws + L.levels_bytes + (size_t)p * L.per_problem, 0, sizeof(TrackCtl), stream);
@@ -566,10 +883,11 @@ extern "C" int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_
   const como_b200_track_level_t* d_levels = (const como_b200_track_level_t*)ws;
   como_b200_track_term_t t = *term;
   TrackLayout lay = L;
-  void* args[] = {(void*)&d_levels, (void*)&num_levels, (void*)&t,   (void*)&T,  (void*)&aff,
-                  (void*)&stats,    (void*)&num_iters,  (void*)&ws,  (void*)&lay};
+  int r_cap = cfg.r_cap, cand_cap = g_track_cand_cap;
+  void* args[] = {(void*)&d_levels, (void*)&num_levels, (void*)&t,  (void*)&T,   (void*)&aff,   (void*)&stats,
+                  (void*)&num_iters, (void*)&ws,        (void*)&lay, (void*)&r_cap, (void*)&cand_cap};
   dim3 grid(G, num_problems), block(TRK_THREADS);
-  cudaError_t e = cudaLaunchCooperativeKernel((void*)track_pyr_kernel, grid, block, args, 0, stream);
+  cudaError_t e = cudaLaunchCooperativeKernel((void*)track_pyr_kernel, grid, block, args, cfg.dyn_smem, stream);
   if (e != cudaSuccess) {
     set_last_error("track_pyr: cooperative launch failed: %s", cudaGetErrorString(e));
     return COMO_B200_ELAUNCH;

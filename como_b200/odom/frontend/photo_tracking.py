@@ -4,6 +4,7 @@ same names, argument order and meaning, same return values -- computed by the sm
 csrc/track.cu through the C ABI.  Tensors must live on a CUDA device; there is no CPU path.
 """
 import ctypes as C
+import weakref
 
 import torch
 
@@ -15,19 +16,19 @@ last_num_iters = None
 
 
 def _k9_list(K):
-    """3x3 intrinsics -> 9 python floats.  Device tensors are read back once and cached by (storage, version):
+    """3x3 intrinsics -> 9 python floats.  Device tensors are read back once and cached per tensor OBJECT
+    (weak reference + version counter; never by address -- the caching allocator reuses addresses):
     a device->host copy per level and call would otherwise dominate the launch."""
     if not isinstance(K, torch.Tensor):
         return [float(v) for row in K for v in (row if hasattr(row, "__len__") else [row])]
     if not K.is_cuda:
         return K.detach().to(torch.float32).reshape(-1).tolist()
-    key = (K.data_ptr(), K._version, K.device.index)
-    v = _k9_cache.get(key)
-    if v is None:
-        if len(_k9_cache) > 4096:
-            _k9_cache.clear()
-        v = K.detach().to("cpu", torch.float32).reshape(-1).tolist()
-        _k9_cache[key] = v
+    key = id(K)
+    ent = _k9_cache.get(key)
+    if ent is not None and ent[0]() is K and ent[1] == K._version:
+        return ent[2]
+    v = K.detach().to("cpu", torch.float32).reshape(-1).tolist()
+    _k9_cache[key] = (weakref.ref(K, lambda _r, key=key: _k9_cache.pop(key, None)), K._version, v)
     return v
 
 
@@ -40,6 +41,12 @@ def _workspace(nbytes, device):
     return ws
 
 
+def _aligned(t):
+    """contiguous, and 16-byte aligned (the kernel streams the operands with bulk async copies)"""
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
 def _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, keep):
     num_levels = len(vals_i)
     arr = (_lib.TrackLevel * num_levels)()
@@ -48,12 +55,13 @@ def _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, keep):
         v = vals_i[l]
         if v.shape[-1] != 1:
             raise NotImplementedError("como_b200 tracking supports tracking.color: gray (C=1) only")
-        v = v.reshape(-1).contiguous().float()
-        P = Pi[l].reshape(-1, 3).contiguous().float()
-        J = dI_dT[l].reshape(-1, 8).contiguous().float()
+        v = _aligned(v.reshape(-1).float())
+        P = _aligned(Pi[l].reshape(-1, 3).float())
+        J = _aligned(dI_dT[l].reshape(-1, 8).float())
         m = masks[l].reshape(-1).contiguous()
         if m.dtype != torch.uint8:
             m = m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
+        m = _aligned(m)
         img = img_j[l]
         if img.shape[0] != 1 or img.shape[1] != 1:
             raise NotImplementedError("como_b200 tracking expects img_j[l] of shape (1,1,h,w)")
@@ -75,7 +83,7 @@ def photo_tracking_pyr(Tji_init, aff_init, vals_i, Pi, dI_dT, masks, intrinsics,
     """Coarse-to-fine inverse-compositional tracking; inputs are per-level lists (coarsest first).
 
     Like the reference, `photo_sigma` is accepted and ignored (the scale is 1.4826 * median |r|,
-    photo_tracking.py:132-138).  Returns (Tji (1,4,4), aff (1,2,1)) [, stats (iters, 8)].
+    photo_tracking.py:132-138).  Returns (Tji (1,4,4), aff (1,2,1)) [, stats (iters, 32): see COMO_B200_TRACK_STAT_STRIDE].
     """
     dev = _lib.require_cuda(Tji_init, aff_init, *vals_i, *Pi, *dI_dT, *masks, *img_j)
     num_levels = len(vals_i)
@@ -110,7 +118,7 @@ def photo_tracking_pyr_batch(Tji_init, aff_init, problems, term_criteria, return
 
     Tji_init (B,4,4), aff_init (B,2,1); problems: list of B tuples
     (vals_i, Pi, dI_dT, masks, intrinsics, img_j), each as for photo_tracking_pyr (same num_levels).
-    Returns Tji (B,4,4), aff (B,2,1) [, stats (B, L*max_iter, 8), num_iters (B,)]."""
+    Returns Tji (B,4,4), aff (B,2,1) [, stats (B, L*max_iter, 32), num_iters (B,)]."""
     B = len(problems)
     num_levels = len(problems[0][0])
     dev = _lib.require_cuda(Tji_init, aff_init)

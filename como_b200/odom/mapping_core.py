@@ -8,6 +8,7 @@ There is no CPU path.
 """
 import ctypes as C
 import os
+import weakref
 import math
 
 import torch
@@ -196,14 +197,14 @@ _OVERLAP = os.environ.get("COMO_B200_BA_OVERLAP", "1") != "0"
 
 
 def _host_scalars(cache, name, t, pick, n):
-    """Host copy of a few scalars of a (rarely changing) device tensor, cached on (storage, version): reading them
-    every iteration would synchronise the host with the stream and leave the GPU idle between iterations."""
-    key = (t.data_ptr(), t._version, tuple(t.shape))
+    """Host copy of a few scalars of a (rarely changing) device tensor, cached per tensor OBJECT (weak reference +
+    version counter, never the raw address: the caching allocator reuses addresses): reading them every iteration
+    would synchronise the host with the stream and leave the GPU idle between iterations."""
     hit = cache.get(name)
-    if hit is None or hit[0] != key:
+    if hit is None or hit[0]() is not t or hit[1] != t._version:
         vals = pick(t.detach().to("cpu", F64))
-        hit = cache[name] = (key, (C.c_double * n)(*[float(v) for v in vals]))
-    return hit[1]
+        hit = cache[name] = (weakref.ref(t), t._version, (C.c_double * n)(*[float(v) for v in vals]))
+    return hit[2]
 
 
 _SOLVER = os.environ.get("COMO_B200_SOLVER", "tiled")   # "torch": cuSOLVER potrf + cuBLAS trsv (comparison only)

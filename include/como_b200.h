@@ -38,6 +38,7 @@ const char* como_b200_last_error(void);
  * torch ops under them (geometry/camera.py:57-68, frontend/photo_utils.py:9-31, lietorch SE3.exp).
  * One persistent cooperative launch runs the whole coarse-to-fine loop incl. termination tests.
  * ------------------------------------------------------------------------------------------ */
+/* vals, P, J and mask must be 16-byte aligned (they are streamed with bulk async copies). */
 typedef struct {
   const float* vals;   /* (n)     reference intensities I_i            [photo_tracking.py:24 vals_i]  */
   const float* P;      /* (n,3)   reference points in the KF frame     [Pi]                           */
@@ -55,9 +56,11 @@ typedef struct {
   float grad_norm;     /* term_criteria["grad_norm"]  */
 } como_b200_track_term_t;
 
-/* per-iteration record written to `stats` (8 floats per iteration, iteration-major) */
-#define COMO_B200_TRACK_STAT_STRIDE 8
-/* [0]=level [1]=mean_sq_err [2]=grad_norm [3]=delta_norm [4]=sigma_r [5]=num_valid [6]=done [7]=reserved */
+/* per-iteration record written to `stats` (32 floats per iteration, iteration-major) */
+#define COMO_B200_TRACK_STAT_STRIDE 32
+/* [0]=level [1]=mean_sq_err [2]=grad_norm [3]=delta_norm [4]=sigma_r [5]=num_valid [6]=done [7]=reserved
+ * [8..23]=Tji (row-major 4x4) and [24..25]=[a,b] this iteration was linearised at (tracking_iter's inputs,
+ * photo_tracking.py:117) -- lets a checker replay every iteration from identical inputs; [26..31]=reserved */
 
 size_t como_b200_track_workspace_bytes(int32_t max_n, int32_t num_problems);
 
@@ -67,6 +70,9 @@ size_t como_b200_track_workspace_bytes(int32_t max_n, int32_t num_problems);
 int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_t num_levels, int32_t num_problems,
                         const como_b200_track_term_t* term, float* T, float* aff, float* stats,
                         int32_t* num_iters, void* workspace, size_t workspace_bytes, void* stream);
+/* Test hook: largest median-bin population that is finished through the candidate list (default 2048);
+ * 0 forces the histogram-narrowing path for every iteration.  Both paths return the same exact order statistic. */
+void como_b200_track_debug_candidate_cap(int32_t cap);
 
 /* Replaces precalc_jacobians (como/odom/frontend/photo_tracking.py:46-74), C = 1.
  * grads (n,2) [gx,gy]; P (n,3); vals (n); K 9 floats (host); out J (n,8). */

@@ -448,6 +448,71 @@ def state_from_golden(g, prefix="in_"):
     return s
 
 
+def img_and_grads(rgb):
+    """Mapping.get_img_and_grads, color "gray" (como/odom/Mapping.py:368-376): torchvision rgb_to_grayscale
+    (0.2989 R + 0.587 G + 0.114 B) and the Scharr/32 gradients with reflect padding
+    (como/utils/image_processing.py:8-44).  rgb (1,3,H,W) float64 -> (1,3,H,W) [I, gx, gy]."""
+    img = (0.2989 * rgb[:, 0:1] + 0.587 * rgb[:, 1:2] + 0.114 * rgb[:, 2:3]).to(rgb.dtype)
+    kx = torch.tensor([[-3.0, 0.0, 3.0], [-10.0, 0.0, 10.0], [-3.0, 0.0, 3.0]], dtype=rgb.dtype) * (1.0 / 32.0)
+    ky = torch.tensor([[-3.0, -10.0, -3.0], [0.0, 0.0, 0.0], [3.0, 10.0, 3.0]], dtype=rgb.dtype) * (1.0 / 32.0)
+    xp = torch.nn.functional.pad(img, (1, 1, 1, 1), mode="reflect")
+    gx = torch.nn.functional.conv2d(xp, kx.view(1, 1, 3, 3))
+    gy = torch.nn.functional.conv2d(xp, ky.view(1, 1, 3, 3))
+    return torch.cat((img, gx, gy), dim=1)
+
+
+def state_from_compact_golden(g, img_fn=None, slab_fn=None):
+    """State dict from a compact golden (gen_golden.gen_ba_compact): the image stacks are regenerated from the stored
+    texture + frame offsets (`img_fn(rgb) -> (1,3,H,W)`, default: the restatement above) and the dense predictor slab
+    from the stored covariance images, anchors and the reference's own K_mm^-1 (`slab_fn(cov (K,4,H,W) f64,
+    coords_m (K,M,2), Kmm_inv (K,M,M), scale) -> (K,H,W,M)`, default: oracle/depthcov_oracle.py), after which the rows
+    at the sampled pixels are replaced by the reference's exact rows.  Returns (state, report) -- report holds the
+    agreement of the regenerated parts with the stored checksums."""
+    from oracle import depthcov_oracle as DO
+
+    s = state_from_golden(g)
+    W = int(g["W"])
+    tex = torch.from_numpy(g["tex"])
+    img_fn = img_fn or img_and_grads
+    frames = lambda xs: torch.cat([img_fn(tex[..., int(x0):int(x0) + W].clone()).to("cpu") for x0 in xs], 0)
+    s["kf_img_and_grads"] = frames(g["kf_x0"])
+    s["recent_img_and_grads"] = frames(g["recent_x0"])
+    cov = torch.from_numpy(g["in_cov_params_img_f32"]).double()
+    s["cov_params_img"] = cov
+    s.pop("cov_params_img_f32", None)
+    if slab_fn is None:
+        def slab_fn(cov, cm, Kinv, scale):
+            K, _, H, Wc = cov.shape
+            cmn = DO._normalize(cm.double(), (H, Wc))
+            E_m = DO._interp_cov(cov, cmn)
+            rr, cc = torch.meshgrid(torch.arange(H), torch.arange(Wc), indexing="ij")
+            cn = DO._normalize(torch.stack((rr.reshape(-1), cc.reshape(-1)), 1)[None].double(), (H, Wc))
+            out = []
+            for k in range(K):
+                E_n = DO._interp_cov(cov[k:k + 1], cn)
+                out.append((DO.cov_python(cn, E_n, cmn[k:k + 1], E_m[k:k + 1], scale) @ Kinv[k:k + 1]).reshape(1, H, Wc, -1))
+            return torch.cat(out, 0)
+    # the predictor was built at the first-observation pixels; state stores them as (x, y), prep_predictor takes (row, col)
+    coords_m = s["pm_first_obs"].flip(-1).contiguous()
+    slab = slab_fn(cov, coords_m, s["Kmm_inv"], float(g["gp_scale"])).to("cpu").clone()
+    rows = torch.from_numpy(g["in_Knm_rows"])
+    cn = torch.from_numpy(g["coords_n"])
+    kidx = torch.arange(slab.shape[0])[:, None]
+    mine = slab[kidx, cn[..., 0], cn[..., 1]]
+    rep = dict(
+        img0=float((s["kf_img_and_grads"][0] - torch.from_numpy(g["chk_kf_img_and_grads_0"])).abs().max()),
+        img_sum=float((s["kf_img_and_grads"].sum((2, 3)) - torch.from_numpy(g["chk_kf_img_and_grads_sum"])).abs().max()),
+        rec_sum=float((s["recent_img_and_grads"].sum((2, 3)) - torch.from_numpy(g["chk_recent_img_and_grads_sum"])).abs().max()),
+        rows=float((mine - rows).abs().max() / rows.abs().max()),
+        colsum=float((slab.sum((1, 2)) - torch.from_numpy(g["chk_Knm_colsum"])).abs().max()
+                     / torch.from_numpy(g["chk_Knm_colsum"]).abs().max()))
+    slab[kidx, cn[..., 0], cn[..., 1]] = rows
+    s["Knm_Kmminv"] = slab
+    s.pop("Knm_rows", None)
+    s["depth_imgs"] = torch.zeros(slab.shape[0], 1, slab.shape[1], slab.shape[2], dtype=torch.float64)
+    return s, rep
+
+
 def cfg_from_golden(g):
     return dict(
         photo_construction=dict(nonmax_suppression_window=4, pairwise_batch_size=int(g["photo_cfg_batch"])),

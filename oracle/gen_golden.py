@@ -160,9 +160,12 @@ def build_reference_window(H, W, NKF, NOW, M, cfg_num_kf, step=3.0):
     K = torch.tensor([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]])
     tex = synth.make_rgb(H, W, seed=0, cell=8, extra_w=int(step * (NKF + 2)) + 8).double()
 
+    x0_log = []
+
     def frame(k):
         dx = k * step
         x0 = int(dx)
+        x0_log.append(x0)
         rgb = tex[..., x0:x0 + W].clone()
         T = torch.eye(4, dtype=torch.double)[None]
         T[0, 0, 3] = dx * Z / f
@@ -205,6 +208,10 @@ def build_reference_window(H, W, NKF, NOW, M, cfg_num_kf, step=3.0):
     m.recent_img_and_grads = m.recent_img_and_grads[order]
     m.recent_poses = m.recent_poses[order]
     m.recent_aff_params = m.recent_aff_params[order]
+    # bookkeeping for the compact goldens (frames are slices of one texture)
+    m._golden_tex = tex
+    m._golden_kf_x0 = x0_log[:NKF][-nwin:]
+    m._golden_recent_x0 = [x0_log[NKF + i] for i in order]
     return m, cfg
 
 
@@ -299,6 +306,91 @@ def gen_ba(name, H, W, NKF, NOW, M, cfg_num_kf, iters=3):
     print(name, "K", m.kf_poses.shape[0], "R", m.recent_poses.shape[0], "L", m.P_m.shape[0], "dim", out["H0"].shape,
           "pairs", len(pr[0]), len(pr[2]), "full", m.window_full, "errs", [out[f"it{i}_total_err"] for i in range(iters)],
           "size %.1f MB" % (sz / 1e6))
+
+
+def gen_ba_compact(name, H, W, NKF, NOW, M, cfg_num_kf):
+    """One Mapping.iterate of the reference on a window at the network resolution with M = 64 anchors (BASELINE
+    configs 3/4 shape, shrunk in pixels only).  Compact: instead of the (K,H,W,M) predictor slab, the kf/recent
+    image stacks and the dense depth images, it stores what they are made from (covariance images + anchors,
+    the texture + frame offsets) plus the slab rows at the sampled pixels, and checksums/subsamples of the rest."""
+    ref_harness.load_reference()
+    import como.odom.backend.linear_system as LS
+    import como.odom.Mapping as MP
+
+    m, cfg = build_reference_window(H, W, NKF, NOW, M, cfg_num_kf)
+    out = {"H": H, "W": W, "M": M, "cfg_num_kf": cfg_num_kf, "iters": 1, "compact": True}
+    out["photo_cfg_batch"] = cfg["photo_construction"]["pairwise_batch_size"]
+    out["sigma_mean_depth_prior"] = cfg["sigmas"]["mean_depth_prior"]
+    out["sigma_scale_prior"] = cfg["sigmas"]["scale_prior"]
+    out["sigma_pose_prior"] = cfg["sigmas"]["pose_prior"]
+    tmp = {}
+    snapshot_mapping(m, "in_", tmp)
+    heavy = ("in_Knm_Kmminv", "in_kf_img_and_grads", "in_recent_img_and_grads", "in_depth_imgs", "in_cov_params_img")
+    for k, v in tmp.items():
+        if k not in heavy:
+            out[k] = v
+    cov = tmp["in_cov_params_img"]
+    assert np.array_equal(cov.astype(np.float32).astype(np.float64), cov), "covariance images are not float32 values"
+    out["in_cov_params_img_f32"] = cov.astype(np.float32)
+    out["tex"] = _np(m._golden_tex)
+    out["kf_x0"] = np.array(m._golden_kf_x0)
+    out["recent_x0"] = np.array(m._golden_recent_x0)
+    kfi, rci = tmp["in_kf_img_and_grads"], tmp["in_recent_img_and_grads"]
+    out["chk_kf_img_and_grads_sum"] = kfi.sum(axis=(2, 3))
+    out["chk_recent_img_and_grads_sum"] = rci.sum(axis=(2, 3))
+    out["chk_kf_img_and_grads_0"] = kfi[0]                  # one full keyframe: pins the regenerated stack
+    out["gp_scale"] = float(m.model.get_scale(-1))
+    slab = tmp["in_Knm_Kmminv"]
+    cap = {}
+    orig_solve, orig_cps, orig_sub = LS.solve_system, MP.create_photo_system, MP.subselect_pixels
+
+    def solve_hook(Hm, g):
+        d = orig_solve(Hm, g)
+        cap["H"], cap["g"], cap["delta"] = _np(Hm), _np(g), _np(d)
+        return d
+
+    def cps_hook(*a, **k):
+        r = orig_cps(*a, **k)
+        cap["photo_err"] = float(r[0])
+        cap["H_photo"], cap["g_photo"] = _np(a[15]), _np(a[16])
+        cap["pairs"] = (list(r[1][0]), list(r[1][1]), list(r[2][0]), list(r[2][1]))
+        return r
+
+    def sub_hook(*a, **k):
+        r = orig_sub(*a, **k)
+        cap["coords_n"] = _np(r[0])
+        return r
+
+    LS.solve_system = solve_hook
+    MP.lin_sys.solve_system = solve_hook
+    MP.create_photo_system = cps_hook
+    MP.subselect_pixels = sub_hook
+    try:
+        m.iterate()
+    finally:
+        LS.solve_system = orig_solve
+        MP.lin_sys.solve_system = orig_solve
+        MP.create_photo_system = orig_cps
+        MP.subselect_pixels = orig_sub
+    cn = cap["coords_n"]                                    # (K,N,2) [row, col]
+    Kw = slab.shape[0]
+    out["in_Knm_rows"] = np.stack([slab[k, cn[k, :, 0], cn[k, :, 1]] for k in range(Kw)])   # (K,N,M)
+    out["chk_Knm_colsum"] = slab.sum(axis=(1, 2))          # (K,M): pins the regenerated dense slab
+    out["coords_n"] = cn
+    for k in ("H", "g", "delta", "H_photo", "g_photo"):
+        out[k + "0" if not k.endswith("photo") else k.replace("_photo", "0_photo")] = cap[k]
+    out["it0_photo_err"] = cap["photo_err"]
+    out["it0_total_err"] = float(m.total_err_prev)
+    for k in ("kf_poses", "kf_aff_params", "recent_poses", "recent_aff_params", "P_m", "median_depths"):
+        out["it0_" + k] = _np(getattr(m, k))
+    out["it0_depth_imgs_sub8"] = _np(m.depth_imgs)[:, :, ::8, ::8]
+    pr = cap["pairs"]
+    out["kf_ref_ids"], out["kf_target_ids"] = np.array(pr[0]), np.array(pr[1])
+    out["one_way_kf_ids"], out["one_way_target_ids"] = np.array(pr[2]), np.array(pr[3])
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    sz = os.path.getsize(os.path.join(GOLD, name + ".npz"))
+    print(name, "K", m.kf_poses.shape[0], "R", m.recent_poses.shape[0], "L", m.P_m.shape[0], "dim", out["H0"].shape,
+          "pairs", len(pr[0]), len(pr[2]), "full", m.window_full, "err", out["it0_total_err"], "size %.1f MB" % (sz / 1e6))
 
 
 def synth_cov_image(H, W, seed):
@@ -544,6 +636,8 @@ def main():
     if what in ("ba", "all"):
         gen_ba("ba_k4_notfull", 48, 64, 4, 3, 16, 5)
         gen_ba("ba_k4_full", 48, 64, 5, 3, 16, 4)
+    if what in ("ba_compact", "all"):
+        gen_ba_compact("ba_k8_m64_256x192", 192, 256, 8, 6, 64, 9)
     if what in ("kfinit", "all"):
         gen_kfinit("kfinit_64x48", 48, 64, 4, 16)
     if what in ("kfinit2", "all"):

@@ -17,3 +17,9 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def pytest_collection_modifyitems(config, items):
+    """The long full-resolution parity tests run last: the driver runs the suite with -x, and an early stop in one
+    of them must not hide the short tests of the other rows."""
+    items.sort(key=lambda it: 1 if ("full_size" in it.name or "full_case" in getattr(it, "fixturenames", ())) else 0)

@@ -222,3 +222,78 @@ def test_full_resolution_k8_window_vs_oracle():
     dbg2 = MC.iterate(s2, cfg, return_debug=True)
     eH2, ed2 = rel(dbg2["H"], dbg["H"]), rel(dbg2["delta"], dbg["delta"])
     assert eH2 < 1e-12 and ed2 < 1e-6, (eH2, ed2)
+
+
+def test_full_resolution_k32_headline_window_vs_oracle():
+    """The HEADLINE configuration (bench.py ba_window: 640x480, K = 32 keyframes, R = 24 one-way frames, M = 64,
+    110 pairs, dim 2848): one iteration of the CUDA path against the oracle on identical state."""
+    from como_b200 import synth
+    from como_b200.odom import mapping_core as MC
+
+    s = synth.make_ba_window(32, 24, 480, 640, M=64, seed=0)
+    cfg = synth.ba_cfg()
+    sc = state_to_cpu_dict(s)
+    o = BO.iterate(sc, cfg)
+    dbg = MC.iterate(s, cfg, return_debug=True)
+    np.testing.assert_array_equal(dbg["coords_n"].cpu().numpy().astype(np.int64), o["coords_n"].numpy())
+    assert dbg["pairs"][0] == o["pairs"][0] and dbg["pairs"][1] == o["pairs"][1]
+    assert dbg["pairs"][2] == o["pairs"][2] and dbg["pairs"][3] == o["pairs"][3]
+    assert rel(dbg["sigma"], torch.tensor(o["sigmas"])) < 1e-6
+    assert abs(float(dbg["err"][0]) - o["photo_err"]) <= 1e-6 * o["photo_err"]      # residual norm (bound 1e-4)
+    eH, eg = rel(dbg["H"], o["H"]), rel(dbg["g"], o["g"])
+    assert eH < 1e-6 and eg < 1e-6, (eH, eg)
+    ep, er, eP = rel(s.kf_poses, sc["kf_poses"]), rel(s.recent_poses, sc["recent_poses"]), rel(s.P_m, sc["P_m"])
+    assert ep < 1e-5 and er < 1e-5 and eP < 1e-5, (ep, er, eP)                        # SE(3) log bound is 1e-3
+    assert rel(s.median_depths, sc["median_depths"]) < 1e-7
+
+
+def test_reference_golden_k8_m64_256x192(golden_dir):
+    """Reference-generated golden at the network resolution with the BASELINE anchor count (K = 8, R = 6, M = 64,
+    built through the reference's own init_keyframe / add_keyframe / add_one_way_frame).  The compact fixture is
+    expanded with the PRODUCT kernels -- gray + Scharr stack (must reproduce the reference's to 1e-13) and the dense
+    predictor slab K_nm K_mm^-1 (must reproduce the reference's rows at the sampled pixels to 1e-9) -- and then one
+    Mapping.iterate is compared with what the reference computed."""
+    from como_b200 import _lib
+    from como_b200.odom import mapping_core as MC
+
+    g = np.load(os.path.join(golden_dir, "ba_k8_m64_256x192.npz"))
+
+    def slab_fn(cov, cm, Kinv, scale):
+        cov, cm, Kinv = cov.cuda().contiguous(), cm.cuda().double().contiguous(), Kinv.cuda().contiguous()
+        B, _, H, W = cov.shape
+        M = cm.shape[1]
+        E_m = torch.empty(B, M, 4, dtype=torch.float64, device="cuda")
+        K_mm = torch.empty(B, M, M, dtype=torch.float64, device="cuda")
+        out = torch.empty(B, H, W, M, dtype=torch.float64, device="cuda")
+        st = _lib.stream_ptr()
+        _lib.check(_lib.kmat_kmm(_lib.ptr(cov), B, H, W, _lib.ptr(cm), M, scale, 1e-6, _lib.ptr(E_m), _lib.ptr(K_mm), st), "kmm")
+        _lib.check(_lib.kmat_predictor(_lib.ptr(cov), B, H, W, _lib.ptr(cm), _lib.ptr(E_m), _lib.ptr(Kinv), M, scale,
+                                       _lib.ptr(out), st), "kmat_predictor")
+        # the K_mm the kernel builds must invert to the reference's K_mm^-1
+        resid = (K_mm @ Kinv - torch.eye(M, dtype=torch.float64, device="cuda")).abs().max()
+        assert float(resid) < 1e-6, float(resid)
+        return out
+
+    sd, rep = BO.state_from_compact_golden(g, img_fn=lambda rgb: MC.get_img_and_grads(rgb.cuda()), slab_fn=slab_fn)
+    assert rep["img0"] < 1e-13 and rep["img_sum"] < 1e-9 and rep["rec_sum"] < 1e-9, rep
+    assert rep["rows"] < 1e-9 and rep["colsum"] < 1e-9, rep
+    cfg = BO.cfg_from_golden(g)
+    s = cuda_state(sd)
+    dbg = MC.iterate(s, cfg, return_debug=True)
+    np.testing.assert_array_equal(dbg["coords_n"].cpu().numpy().astype(np.int64), g["coords_n"])
+    assert dbg["pairs"][0] == list(g["kf_ref_ids"]) and dbg["pairs"][1] == list(g["kf_target_ids"])
+    assert dbg["pairs"][2] == list(g["one_way_kf_ids"]) and dbg["pairs"][3] == list(g["one_way_target_ids"])
+    assert rel(dbg["H_photo"], g["H0_photo"]) < 1e-9
+    assert rel(dbg["g_photo"], g["g0_photo"]) < 1e-9
+    assert rel(dbg["H"], g["H0"]) < 1e-9
+    assert rel(dbg["g"], g["g0"]) < 1e-9
+    assert rel(dbg["delta"][:, 0], g["delta0"][:, 0]) < 1e-6
+    e = dbg["err"].cpu().numpy()
+    assert abs(e[0] - float(g["it0_photo_err"])) <= 1e-9 * float(g["it0_photo_err"])
+    assert abs(e.sum() - float(g["it0_total_err"])) <= 1e-9 * float(g["it0_total_err"])
+    assert rel(s.kf_poses, g["it0_kf_poses"]) < 1e-7
+    assert rel(s.kf_aff_params, g["it0_kf_aff_params"]) < 1e-6
+    assert rel(s.recent_poses, g["it0_recent_poses"]) < 1e-7
+    assert rel(s.P_m, g["it0_P_m"]) < 1e-7
+    assert rel(s.median_depths, g["it0_median_depths"]) < 1e-9
+    assert rel(s.depth_imgs[:, :, ::8, ::8], g["it0_depth_imgs_sub8"]) < 1e-9

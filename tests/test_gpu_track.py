@@ -61,27 +61,72 @@ def test_tracking_iter_same_inputs_vs_golden(golden_dir, name):
         np.testing.assert_allclose(aff.cpu().numpy().ravel(), g["trace_aff_out"][i].ravel(), atol=1e-5)
 
 
-def test_full_size_640x480_vs_oracle():
-    """BASELINE config 2 shape: 640x480, 4-level pyramid.  CUDA vs oracle on identical inputs,
-    per-iteration (oracle replayed from the CUDA path's own iterates) and end to end."""
+def replay_check(levels, stats, T_final, aff_final, strict=True):
+    """Every iteration the CUDA path ran, replayed by the oracle from the CUDA path's OWN iterate (stats[i, 8:26]):
+    both sides evaluate the same (T, aff) on the same operands, so the north-star bounds apply per iteration
+    and do not depend on how either side's fp32 summation order steers the trajectory."""
+    st = stats.cpu().numpy()
+    masked = {}
+    for i in range(st.shape[0]):
+        l = int(st[i, 0])
+        if l not in masked:
+            m = levels["mask"][l].reshape(-1).cpu()
+            masked[l] = (levels["vals"][l].reshape(-1).cpu()[m], levels["P"][l].reshape(-1, 3).cpu()[m],
+                         levels["dI_dT"][l].reshape(-1, 8).cpu()[m], levels["K"][l].cpu(), levels["img"][l][0, 0].cpu())
+        vals, P, J, K, img = masked[l]
+        T_in = torch.from_numpy(st[i, 8:24].reshape(4, 4).copy())
+        aff_in = torch.from_numpy(st[i, 24:26].copy())
+        Tn, affn, delta, mse, gn, H, g, sigma, nvalid = TO.tracking_iter(T_in, aff_in, vals, P, J, K, img)
+        # a projection within 1 ulp of the [1, w-1) border may land on either side
+        assert abs(st[i, 5] - nvalid) <= 2, (i, st[i, 5], nvalid)
+        q = 2.0 / max(nvalid, 1) if not strict else 0.0   # median rank quantisation, only matters at toy sizes
+        # sigma is an EXACT order statistic on both sides, of residuals r = e^-a I_j + b - I_i that carry a couple of
+        # ulp(1) = 1.2e-7 of fp32 rounding (intensities are O(1); the GPU contracts e^-a I_j + b into one FMA)
+        assert abs(st[i, 4] - sigma) <= 3e-7 + (1e-5 + q) * sigma, (i, st[i, 4], sigma)
+        # north star: residual NORM (sqrt of the robust mean-square error) within 1e-4 relative
+        assert abs(np.sqrt(st[i, 1]) - np.sqrt(mse)) <= (1e-4 + q) * np.sqrt(mse), (i, st[i, 1], mse)
+        assert abs(st[i, 2] - gn) <= 1e-3 * max(gn, 1.0), (i, st[i, 2], gn)
+        T_next = st[i + 1, 8:24].reshape(4, 4) if i + 1 < st.shape[0] else T_final
+        a_next = st[i + 1, 24:26] if i + 1 < st.shape[0] else aff_final
+        assert se3_log_err(T_next, Tn.numpy()) < 1e-4, (i, se3_log_err(T_next, Tn.numpy()))  # SE(3) log: 1e-3 asked
+        np.testing.assert_allclose(a_next, affn.numpy(), atol=1e-4)
+    return st
+
+
+@pytest.fixture(scope="module")
+def full_case():
     from como_b200 import synth
 
     case = synth.make_tracking_case(480, 640, 4, seed=0)
     T, aff, stats = cuda_track(case, case["T_init"], case["aff_init"], TERM)
+    return case, T, aff, stats
+
+
+def test_full_size_640x480_every_iteration_replayed(full_case):
+    """BASELINE config 2 shape (640x480, 4-level pyramid): each CUDA iteration vs the oracle on identical inputs."""
+    case, T, aff, stats = full_case
+    assert stats.shape[0] >= 4
+    replay_check(case, stats, T[0].cpu().numpy(), aff.cpu().numpy().ravel())
+
+
+def test_full_size_640x480_end_to_end_vs_oracle_trajectory(full_case):
+    """Independent trajectories (the oracle's own fp32 summation order depends on the host thread count, so the
+    iterates are not comparable one by one): the final pose must agree within the north-star SE(3)-log bound."""
+    case, T, aff, stats = full_case
     To, affo, trace = TO.track_pyr(case["T_init"], case["aff_init"], case["vals"], case["P"], case["dI_dT"],
                                    case["mask"], case["K"], case["img"], TERM)
-    assert stats.shape[0] == len(trace)
-    st = stats.cpu().numpy()
-    for i, s in enumerate(trace):
-        # iterates differ in the last bits after the first update, so a few border pixels may flip
-        assert abs(st[i, 5] - s["nvalid"]) <= max(3, 1e-4 * s["nvalid"])
-    # first iteration of every level starts from identical inputs only at level 0; compare it strictly
-    assert abs(st[0, 1] - trace[0]["mse"]) <= (1e-4 + 2.0 / trace[0]["nvalid"]) * trace[0]["mse"]
-    assert se3_log_err(T[0].cpu().numpy(), To.numpy()) < 1e-4
-    np.testing.assert_allclose(aff.cpu().numpy().ravel(), affo.numpy().ravel(), atol=1e-4)
+    assert abs(stats.shape[0] - len(trace)) <= 2
+    assert se3_log_err(T[0].cpu().numpy(), To.numpy()) < 1e-3
+    np.testing.assert_allclose(aff.cpu().numpy().ravel(), affo.numpy().ravel(), atol=1e-3)
     # property: converges back to identity from the 8d perturbation
     assert se3_log_err(T[0].cpu().numpy(), np.eye(4)) < 2e-3
-    # finest level single iteration on identical inputs (N = 307200): the 1e-4 residual-norm bound
+
+
+def test_full_size_finest_level_single_iteration_strict():
+    """N = 307200, one iteration from identical inputs: residual norm 1e-4, exact order statistic, update 1e-5."""
+    from como_b200 import synth
+
+    case = synth.make_tracking_case(480, 640, 4, seed=0)
     one = {k: [v[-1]] for k, v in case.items() if isinstance(v, list)}
     T1, aff1, st1 = cuda_track(one, case["T_init"], case["aff_init"], dict(TERM, max_iter=1))
     m = case["mask"][-1].reshape(-1)
@@ -89,10 +134,77 @@ def test_full_size_640x480_vs_oracle():
                          case["P"][-1].reshape(-1, 3)[m], case["dI_dT"][-1].reshape(-1, 8)[m], case["K"][-1],
                          case["img"][-1][0, 0])
     s = st1[0].cpu().numpy()
+    assert abs(s[5] - r[8]) <= 2
     assert abs(s[1] - r[3]) <= 1e-4 * r[3]
     assert abs(s[2] - r[4]) <= 1e-4 * r[4]
-    assert abs(s[4] - r[7]) <= 1e-5 * r[7]  # sigma: exact order statistic
+    assert abs(s[4] - r[7]) <= 3e-7 + 1e-5 * r[7]  # sigma: exact order statistic of residuals with ~ulp(1) rounding
     assert se3_log_err(T1[0].cpu().numpy(), r[0].numpy()) < 1e-5
+    np.testing.assert_array_equal(s[8:24].reshape(4, 4), case["T_init"][0].numpy())
+
+
+def test_run_to_run_bitwise_deterministic(full_case):
+    case, T, aff, stats = full_case
+    T2, aff2, stats2 = cuda_track(case, case["T_init"], case["aff_init"], TERM)
+    assert torch.equal(T, T2) and torch.equal(aff, aff2) and torch.equal(stats, stats2)
+
+
+def test_median_paths_agree_bitwise(full_case):
+    """The candidate-list finish and the pure histogram-narrowing path return the same exact order statistic."""
+    from como_b200 import _lib
+
+    case, T, aff, stats = full_case
+    _lib.track_debug_candidate_cap(0)
+    try:
+        T2, aff2, stats2 = cuda_track(case, case["T_init"], case["aff_init"], TERM)
+    finally:
+        _lib.track_debug_candidate_cap(2048)
+    assert torch.equal(stats[:, 4], stats2[:, 4])
+    assert torch.equal(T, T2) and torch.equal(stats, stats2)
+
+
+@pytest.mark.parametrize("G", [1, 3, 8, 40])
+def test_group_sizes_replay(G, monkeypatch):
+    """Different CTA-group sizes (slice boundaries, shared-memory vs L2 residual residency, single-CTA path):
+    every iteration still matches the oracle from identical inputs."""
+    from como_b200 import synth
+
+    monkeypatch.setenv("COMO_B200_TRACK_G", str(G))
+    case = synth.make_tracking_case(240, 320, 3, seed=3, cell=8)
+    T, aff, stats = cuda_track(case, case["T_init"], case["aff_init"], TERM)
+    replay_check(case, stats, T[0].cpu().numpy(), aff.cpu().numpy().ravel())
+
+
+def test_two_ctas_per_sm_mode_replay(monkeypatch):
+    from como_b200 import synth
+
+    monkeypatch.setenv("COMO_B200_TRACK_OCC", "2")
+    case = synth.make_tracking_case(480, 640, 4, seed=5)
+    T, aff, stats = cuda_track(case, case["T_init"], case["aff_init"], TERM)
+    replay_check(case, stats, T[0].cpu().numpy(), aff.cpu().numpy().ravel())
+
+
+def test_all_zero_residuals_single_bin():
+    """Every |r| is exactly 0 (black frames): one histogram bin holds every pixel -> the narrowing passes run down to
+    a single key; sigma = 0 and the weights are NaN exactly as in the reference (r / 0).  Must terminate, not hang."""
+    from como_b200 import synth
+
+    case = synth.make_tracking_case(120, 160, 2, seed=4, cell=8)
+    case["img"] = [torch.zeros_like(i) for i in case["img"]]
+    case["vals"] = [torch.zeros_like(v) for v in case["vals"]]
+    T, aff, stats = cuda_track(case, case["T_init"], case["aff_init"], dict(TERM, max_iter=2))
+    st = stats.cpu().numpy()
+    # level 0 runs to max_iter (NaN never satisfies a termination test); its NaN pose leaves level 1 without a valid pixel
+    assert st.shape[0] >= 3 and np.all(st[:2, 4] == 0.0) and np.all(st[:2, 5] > 0) and st[-1, 5] == 0
+
+
+@pytest.mark.parametrize("name", ["track_80x60_l3", "track_160x120_l4"])
+def test_golden_inputs_replay(golden_dir, name):
+    """Reference-generated operands (ragged level sizes: 300, 1200, 4800 points -> bulk-copy tails)."""
+    g = load(golden_dir, name)
+    lv = golden_levels(g)
+    T, aff, stats = cuda_track(lv, torch.from_numpy(g["T_init"]), torch.from_numpy(g["aff_init"]),
+                               dict(TERM, max_iter=int(g["max_iter"])))
+    replay_check(lv, stats, T[0].cpu().numpy(), aff.cpu().numpy().ravel(), strict=False)
 
 
 def test_precalc_jacobians_vs_golden(golden_dir):
