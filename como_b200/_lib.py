@@ -98,6 +98,8 @@ reproject_dense = _sig("como_b200_reproject_dense", C.c_int,
 sample_depth_gradmag = _sig("como_b200_sample_depth_gradmag", C.c_int, [VP, I32, I32, VP, VP, I32, VP, VP, VP])
 
 gray_pyramid = _sig("como_b200_gray_pyramid", C.c_int, [VP, I32, I32, I32, C.POINTER(C.c_void_p), VP])
+image_pyramid_fused = _sig("como_b200_image_pyramid_fused", C.c_int,
+                           [VP, I32, I32, I32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), VP])
 image_gradients = _sig("como_b200_image_gradients", C.c_int, [VP, I32, I32, VP, VP, VP])
 img_and_grads_f64 = _sig("como_b200_img_and_grads_f64", C.c_int, [VP, I32, I32, VP, VP])
 kf_reference_level = _sig("como_b200_kf_reference_level", C.c_int,
@@ -118,7 +120,7 @@ DECLARED_SYMBOLS = [
     "como_b200_chol_solve_workspace_bytes", "como_b200_chol_solve",
     "como_b200_kmat_rows", "como_b200_weighted_gram", "como_b200_rows_residual",
     "como_b200_reproject_dense", "como_b200_sample_depth_gradmag", "como_b200_sfm_linearize", "como_b200_sfm_accumulate",
-    "como_b200_gray_pyramid", "como_b200_image_gradients", "como_b200_img_and_grads_f64", "como_b200_kf_reference_level", "como_b200_reproj_depth",
+    "como_b200_gray_pyramid", "como_b200_image_pyramid_fused", "como_b200_image_gradients", "como_b200_img_and_grads_f64", "como_b200_kf_reference_level", "como_b200_reproj_depth",
 ]
 
 

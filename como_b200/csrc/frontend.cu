@@ -52,6 +52,97 @@ __global__ void scharr_kernel(const float* __restrict__ in, int h, int w, float*
   gy[(size_t)y * w + x] = k3 * (v[2][0] - v[0][0]) + k10 * (v[2][1] - v[0][1]) + k3 * (v[2][2] - v[0][2]);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Fused front-end: RGB -> gray -> the whole [1 2 1]^2/16 stride-2 pyramid (-> optional Scharr/32
+// gradients of every level) in ONE launch.  A CTA owns a 64 x 64 tile of the finest level and the matching
+// 32 / 16 / 8 tiles below it; every level is built in shared memory from the level above, with a halo that doubles
+// per level (1 at the coarsest, 3, 7, 15 at the finest for 4 levels), so no level is ever re-read from HBM.  Region
+// entries one pixel outside an image hold torch's 'reflect' value (they are evaluated at the reflected coordinate,
+// which is always inside the same region); entries further out are never read.
+// Same arithmetic as gray_kernel / blur_down_kernel / scharr_kernel above (and the same parity tests).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PYR_TILE = 64;
+constexpr int PYR_MAX_LEVELS = 4;
+
+struct PyrArgs {
+  float* img[PYR_MAX_LEVELS];   // finest first: img[0] is H x W
+  float* gx[PYR_MAX_LEVELS];    // optional (nullptr: no gradients)
+  float* gy[PYR_MAX_LEVELS];
+  int h[PYR_MAX_LEVELS], w[PYR_MAX_LEVELS];
+  int halo[PYR_MAX_LEVELS];
+  int off[PYR_MAX_LEVELS];      // float offset of the level's region in shared memory
+  int num_levels;
+};
+
+__global__ void __launch_bounds__(256) pyramid_fused_kernel(const float* __restrict__ rgb, PyrArgs a) {
+  extern __shared__ float pyr_smem[];
+  const int tid = threadIdx.x;
+  const long long hw0 = (long long)a.h[0] * a.w[0];
+  // ---- level 0: gray of the tile + halo (reflected coordinates outside the image)
+  {
+    const int ts = PYR_TILE, hl = a.halo[0], rs = ts + 2 * hl;
+    const int y0 = blockIdx.y * ts - hl, x0 = blockIdx.x * ts - hl;
+    float* R = pyr_smem + a.off[0];
+    for (int e = tid; e < rs * rs; e += 256) {
+      const int ry = e / rs, rx = e - ry * rs;
+      const int y = y0 + ry, x = x0 + rx;
+      float v = 0.0f;
+      if (y >= -1 && y <= a.h[0] && x >= -1 && x <= a.w[0]) {
+        const long long o = (long long)reflect_idx(y, a.h[0]) * a.w[0] + reflect_idx(x, a.w[0]);
+        const float c0 = __fmul_rn(0.2989f, rgb[o]);
+        const float c1 = __fmul_rn(0.587f, rgb[hw0 + o]);
+        const float c2 = __fmul_rn(0.114f, rgb[2 * hw0 + o]);
+        v = __fadd_rn(__fadd_rn(c0, c1), c2);
+      }
+      R[e] = v;
+    }
+  }
+  __syncthreads();
+  const float wgt[3] = {1.0f / 16.0f, 2.0f / 16.0f, 1.0f / 16.0f};
+  for (int l = 0; l < a.num_levels; ++l) {
+    const int ts = PYR_TILE >> l, hl = a.halo[l], rs = ts + 2 * hl;
+    const int ty0 = blockIdx.y * ts, tx0 = blockIdx.x * ts;
+    const float* R = pyr_smem + a.off[l];
+    // ---- write this level's tile (+ gradients)
+    for (int e = tid; e < ts * ts; e += 256) {
+      const int ry = e / ts, rx = e - ry * ts;
+      const int y = ty0 + ry, x = tx0 + rx;
+      if (y < a.h[l] && x < a.w[l]) {
+        const float* c = R + (ry + hl) * rs + (rx + hl);
+        const size_t o = (size_t)y * a.w[l] + x;
+        a.img[l][o] = c[0];
+        if (a.gx[l]) {
+          const float k3 = 3.0f / 32.0f, k10 = 10.0f / 32.0f;
+          a.gx[l][o] = k3 * (c[-rs + 1] - c[-rs - 1]) + k10 * (c[1] - c[-1]) + k3 * (c[rs + 1] - c[rs - 1]);
+          a.gy[l][o] = k3 * (c[rs - 1] - c[-rs - 1]) + k10 * (c[rs] - c[-rs]) + k3 * (c[rs + 1] - c[-rs + 1]);
+        }
+      }
+    }
+    if (l + 1 == a.num_levels) break;
+    // ---- next level's region from this one: blur 3x3 at the even positions
+    {
+      const int ts1 = ts >> 1, hl1 = a.halo[l + 1], rs1 = ts1 + 2 * hl1;
+      const int y1_0 = blockIdx.y * ts1 - hl1, x1_0 = blockIdx.x * ts1 - hl1;
+      const int y0_0 = ty0 - hl, x0_0 = tx0 - hl;   // coordinates of R[0][0]
+      float* R1 = pyr_smem + a.off[l + 1];
+      for (int e = tid; e < rs1 * rs1; e += 256) {
+        const int ry = e / rs1, rx = e - ry * rs1;
+        const int y1 = y1_0 + ry, x1 = x1_0 + rx;
+        float acc = 0.0f;
+        if (y1 >= -1 && y1 <= a.h[l + 1] && x1 >= -1 && x1 <= a.w[l + 1]) {
+          const int cy = 2 * reflect_idx(y1, a.h[l + 1]) - y0_0, cx = 2 * reflect_idx(x1, a.w[l + 1]) - x0_0;
+          for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx)
+              acc += (wgt[dy + 1] * wgt[dx + 1] * 16.0f) * R[(cy + dy) * rs + (cx + dx)];
+        }
+        R1[e] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // Mapping.get_img_and_grads (como/odom/Mapping.py:368-376) in ONE pass: rgb (3,H,W) f64 -> [I, gx, gy] (3,H,W) f64,
 // the layout the BA gather kernels read.  I = 0.2989 R + 0.587 G + 0.114 B (torchvision rgb_to_grayscale), Scharr
 // with reflect padding (utils/image_processing.py:8-45); the 3x3 gray neighbourhood is rebuilt from RGB on the fly.
@@ -164,6 +255,45 @@ extern "C" int como_b200_gray_pyramid(const float* rgb, int32_t H, int32_t W, in
     w = wo;
   }
   return check_launch("gray_pyramid");
+}
+
+extern "C" int como_b200_image_pyramid_fused(const float* rgb, int32_t H, int32_t W, int32_t num_levels, float* const* levels,
+                                             float* const* gx, float* const* gy, void* stream) {
+  // levels / gx / gy: HOST arrays of num_levels DEVICE pointers, COARSEST FIRST (as the reference stores pyramids);
+  // gx, gy may be NULL (tracking frames need the images only).  num_levels <= 4; larger pyramids use gray_pyramid.
+  COMO_REQUIRE(rgb && levels && num_levels >= 1 && num_levels <= PYR_MAX_LEVELS, "image_pyramid_fused: bad arguments");
+  COMO_REQUIRE((gx == nullptr) == (gy == nullptr), "image_pyramid_fused: gx and gy go together");
+  COMO_REQUIRE(H >= 2 && W >= 2, "image_pyramid_fused: image too small");
+  PyrArgs a;
+  a.num_levels = num_levels;
+  int h = H, w = W, off = 0;
+  for (int l = 0; l < num_levels; ++l) {   // kernel order: finest first
+    a.img[l] = levels[num_levels - 1 - l];
+    a.gx[l] = gx ? gx[num_levels - 1 - l] : nullptr;
+    a.gy[l] = gy ? gy[num_levels - 1 - l] : nullptr;
+    COMO_REQUIRE(a.img[l] != nullptr, "image_pyramid_fused: null level pointer");
+    COMO_REQUIRE(h >= 2 && w >= 2, "image_pyramid_fused: level %d degenerates (%d x %d)", l, h, w);
+    a.h[l] = h;
+    a.w[l] = w;
+    h = (h + 1) / 2;
+    w = (w + 1) / 2;
+  }
+  a.halo[num_levels - 1] = 1;
+  for (int l = num_levels - 2; l >= 0; --l) a.halo[l] = 2 * a.halo[l + 1] + 1;
+  for (int l = 0; l < num_levels; ++l) {
+    const int rs = (PYR_TILE >> l) + 2 * a.halo[l];
+    a.off[l] = off;
+    off += rs * rs;
+  }
+  for (int l = num_levels; l < PYR_MAX_LEVELS; ++l) {
+    a.img[l] = a.gx[l] = a.gy[l] = nullptr;
+    a.h[l] = a.w[l] = a.halo[l] = a.off[l] = 0;
+  }
+  const size_t smem = (size_t)off * sizeof(float);
+  cudaFuncSetAttribute(pyramid_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid((W + PYR_TILE - 1) / PYR_TILE, (H + PYR_TILE - 1) / PYR_TILE);
+  pyramid_fused_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(rgb, a);
+  return check_launch("image_pyramid_fused");
 }
 
 extern "C" int como_b200_image_gradients(const float* img, int32_t h, int32_t w, float* gx, float* gy, void* stream) {

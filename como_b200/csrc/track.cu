@@ -32,25 +32,28 @@
 
 namespace como {
 
-constexpr int CONS_WARPS = 8;
+constexpr int CONS_WARPS = 4;
 constexpr int CONS_THREADS = CONS_WARPS * 32;
 constexpr int TRK_THREADS = CONS_THREADS + 32;  // + producer warp
-constexpr int T1 = 1024;                        // pixels per pass-1 stage
-constexpr int T2 = 512;                         // pixels per pass-2 stage
-constexpr int STAGE_BYTES = 18432;              // max(T1*(12+4+1), T2*(32+4))
+constexpr int MAX_OCC = 3;                      // CTAs per SM the launch bounds allow
+constexpr int T1 = 512;                         // pixels per pass-1 stage (4 per consumer thread)
+constexpr int T2 = 512;                         // pixels per pass-2 stage (4 per consumer thread)
+constexpr int STAGE_BYTES = 20480;              // max(T1*(12+4+1), T2*(32+4+4))
 constexpr int T1_VALS_OFF = T1 * 12, T1_MASK_OFF = T1 * 16;
-constexpr int T2_VALS_OFF = T2 * 32;
+constexpr int T2_VALS_OFF = T2 * 32, T2_R_OFF = T2 * 36;
 constexpr int STAGES = 3;
-constexpr int CHUNK_ALIGN = 256;  // slice starts: 16-byte aligned in every operand array
+constexpr int CHUNK_ALIGN = 512;  // slice = whole tiles (only the last slice of a level is ragged); 16-byte aligned starts
 constexpr int NACC = 45;          // 36 (upper triangle of 8x8) + 8 (gradient) + 1 (robust error)
 constexpr int NACC_PAD = 48;
-constexpr int HIST_BINS = 2048;
+constexpr int HIST_BITS = 10;
+constexpr int HIST_BINS = 1 << HIST_BITS;
 constexpr int MAX_PASSES = 4;     // first histogram + at most 3 narrowing passes cover the 31-bit key
 constexpr int CAND_CAP = 2048;
 constexpr float HUBER_K = 1.345f;
-// first-pass bins: 0 = [0, KEY_LO), 1..2046 = 2^17 key codes each (1/64 octave), 2047 = [KEY_HI, 2^31)
-constexpr unsigned KEY_HI = 0x47800000u;                 // 2^16
-constexpr unsigned KEY_LO = KEY_HI - 2046u * 0x20000u;   // ~2^-16
+// first-pass bins: 0 = [0, KEY_LO), 1..1022 = 2^17 key codes each (1/64 octave), 1023 = [KEY_HI, 2^31)
+constexpr int KEY_SHIFT = 17;
+constexpr unsigned KEY_HI = 0x41000000u;                                          // 2^3
+constexpr unsigned KEY_LO = KEY_HI - (unsigned)(HIST_BINS - 2) * (1u << KEY_SHIFT);  // ~2^-13
 constexpr int MAX_GROUP = 1024;
 
 struct TrackCtl {
@@ -64,40 +67,97 @@ struct TrackCtl {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// workspace: [level descriptors][TrackCtl x B][partial rows x B][residual scratch x B]
 struct TrackLayout {
-  size_t levels_bytes, ctl_off, partials_off, resid_off, per_problem;
+  size_t ctl_off, ctl_stride, partials_off, partials_stride, resid_off, resid_stride, total;
 };
 
 static TrackLayout track_layout(int max_n, int num_problems) {
   TrackLayout L;
-  L.levels_bytes = align_up((size_t)num_problems * COMO_B200_MAX_LEVELS * sizeof(como_b200_track_level_t), 256);
-  L.ctl_off = 0;
-  L.partials_off = align_up(sizeof(TrackCtl), 256);
-  L.resid_off = L.partials_off + align_up((size_t)MAX_GROUP * NACC_PAD * sizeof(double), 256);
-  L.per_problem = L.resid_off + align_up((size_t)max_n * sizeof(float), 256);
+  L.ctl_off = align_up((size_t)num_problems * COMO_B200_MAX_LEVELS * sizeof(como_b200_track_level_t), 256);
+  L.ctl_stride = align_up(sizeof(TrackCtl), 256);
+  L.partials_off = L.ctl_off + (size_t)num_problems * L.ctl_stride;
+  L.partials_stride = align_up((size_t)MAX_GROUP * NACC_PAD * sizeof(double), 256);
+  L.resid_off = L.partials_off + (size_t)num_problems * L.partials_stride;
+  L.resid_stride = align_up(((size_t)max_n + 2 * T1) * sizeof(float), 256);  // padded: tiles store past n
+  L.total = L.resid_off + (size_t)num_problems * L.resid_stride;
   return L;
 }
 
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CONS_THREADS) : "memory"); }
 
-// group barrier among the consumer threads of the G CTAs of one problem
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Group barrier among the consumer threads of the G CTAs of one problem.  Only thread 0 fences (the CTA barrier
+// orders the other threads' writes before its release, and its acquire before their reads); the poll is a relaxed
+// load so that waiting does not keep invalidating the SM's L1 (shared with the co-resident CTA's image taps).
+// Cross-CTA data is always read with ld.cg.
 __device__ __forceinline__ void consumer_group_barrier(unsigned* counter, unsigned& epoch, unsigned group_size) {
-  __threadfence();
   consumer_sync();
   epoch += 1;
-  if (group_size > 1 && threadIdx.x == 0) {
-    red_release_add_u32(counter, 1u);
-    const unsigned target = epoch * group_size;
-    while (ld_acquire_u32(counter) < target) {
+  if (group_size > 1) {
+    if (threadIdx.x == 0) {
+      __threadfence();
+      red_release_add_u32(counter, 1u);
+      const unsigned target = epoch * group_size;
+      while (ld_relaxed_u32(counter) < target) {
+      }
+      __threadfence();
+    }
+    consumer_sync();
+  }
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// Visit every residual of this CTA's slice (shared-memory part [0, r_cap), L2 scratch beyond): f(key) for each
+// valid one.  Four-wide loads, four of them in flight per thread (the scratch is padded, see track_layout).
+template <class F>
+__device__ __forceinline__ void for_each_key(const float* s_r, const float* g_r, int r_cap, int len, F f) {
+  const int tid = threadIdx.x;
+  const int n_s = min(len, r_cap) & ~3, n_all = len & ~3;
+  for (int j = tid * 4; j < n_s; j += CONS_THREADS * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(s_r + j);
+    if (v.x == v.x) f(__float_as_uint(fabsf(v.x)));
+    if (v.y == v.y) f(__float_as_uint(fabsf(v.y)));
+    if (v.z == v.z) f(__float_as_uint(fabsf(v.z)));
+    if (v.w == v.w) f(__float_as_uint(fabsf(v.w)));
+  }
+  const int g0 = (r_cap < len) ? r_cap : n_all;  // r_cap is a multiple of 4
+  for (int j0 = g0 + tid * 4; j0 < n_all; j0 += CONS_THREADS * 16) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * CONS_THREADS * 4;
+      v[u] = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
+                         __int_as_float(0x7fc00000));
+      if (j < n_all) v[u] = __ldcg(reinterpret_cast<const float4*>(g_r + j));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (v[u].x == v[u].x) f(__float_as_uint(fabsf(v[u].x)));
+      if (v[u].y == v[u].y) f(__float_as_uint(fabsf(v[u].y)));
+      if (v[u].z == v[u].z) f(__float_as_uint(fabsf(v[u].z)));
+      if (v[u].w == v[u].w) f(__float_as_uint(fabsf(v[u].w)));
     }
   }
-  consumer_sync();
+  for (int j = n_all + tid; j < len; j += CONS_THREADS) {  // ragged end of the last slice
+    const float r = (j < r_cap) ? s_r[j] : __ldcg(g_r + j);
+    if (r == r) f(__float_as_uint(fabsf(r)));
+  }
 }
 
 __device__ __forceinline__ unsigned first_bin(unsigned key) {
-  if (key < KEY_LO) return 0u;
-  const unsigned b = ((key - KEY_LO) >> 17) + 1u;
-  return b > 2047u ? 2047u : b;
+  const int d = ((int)key - (int)KEY_LO) >> KEY_SHIFT;  // arithmetic shift: negative below KEY_LO
+  return (unsigned)(min(max(d, -1), HIST_BINS - 2) + 1);
 }
 
 __device__ __forceinline__ int clog2(unsigned w) { return w <= 1u ? 0 : 32 - __clz(w - 1u); }
@@ -106,21 +166,19 @@ __device__ __forceinline__ int clog2(unsigned w) { return w <= 1u ? 0 : 32 - __c
 // through L2).  k_is_median: k = (total-1)/2 (torch.median's lower median).  s_out: [bin, rank in bin, count in bin, total].
 __device__ __forceinline__ void select_bin(const unsigned* hist, bool global, unsigned k, bool k_is_median,
                                            unsigned* s_warp, unsigned* s_out) {
+  constexpr int NB = HIST_BINS / CONS_THREADS;  // bins per thread (multiple of 4)
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
-  unsigned c[8];
-  if (global) {
-    const uint4 a = __ldcg(reinterpret_cast<const uint4*>(hist) + 2 * tid);
-    const uint4 b = __ldcg(reinterpret_cast<const uint4*>(hist) + 2 * tid + 1);
-    c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
-  } else {
-    const uint4 a = reinterpret_cast<const uint4*>(hist)[2 * tid];
-    const uint4 b = reinterpret_cast<const uint4*>(hist)[2 * tid + 1];
-    c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+  unsigned c[NB];
+#pragma unroll
+  for (int q = 0; q < NB / 4; ++q) {
+    const uint4* src = reinterpret_cast<const uint4*>(hist) + (NB / 4) * tid + q;
+    const uint4 a = global ? __ldcg(src) : *src;
+    c[4 * q] = a.x; c[4 * q + 1] = a.y; c[4 * q + 2] = a.z; c[4 * q + 3] = a.w;
   }
   unsigned local = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) local += c[j];
+  for (int j = 0; j < NB; ++j) local += c[j];
   unsigned incl = local;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -147,9 +205,9 @@ __device__ __forceinline__ void select_bin(const unsigned* hist, bool global, un
   if (k >= excl && k < incl) {
     unsigned run = excl;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NB; ++j) {
       if (k >= run && k < run + c[j]) {
-        s_out[0] = tid * 8 + j;
+        s_out[0] = tid * NB + j;
         s_out[1] = k - run;
         s_out[2] = c[j];
       }
@@ -218,8 +276,11 @@ __device__ __forceinline__ void produce_tile1(uint8_t* stage, unsigned long long
   }
 }
 
+// r_src: this tile's residuals in the L2 scratch (written by this CTA's consumers in pass 1 through the generic
+// proxy, fenced + signalled on p1_done before the producer gets here), or nullptr when they live in shared memory.
 __device__ __forceinline__ void produce_tile2(uint8_t* stage, unsigned long long* full, unsigned long long* empty,
-                                              unsigned n, const como_b200_track_level_t& lv, int i0, int cnt) {
+                                              unsigned n, const como_b200_track_level_t& lv, int i0, int cnt,
+                                              const float* r_src) {
   const int lane = threadIdx.x & 31;
   mbar_wait(empty, ((n / STAGES) & 1u) ^ 1u);
   const int bulk = cnt & ~3;
@@ -227,21 +288,25 @@ __device__ __forceinline__ void produce_tile2(uint8_t* stage, unsigned long long
   const float* V = lv.vals + i0;
   for (int j = bulk + (lane >> 3); j < cnt; j += 4) {
     reinterpret_cast<float*>(stage)[8 * j + (lane & 7)] = J[8 * j + (lane & 7)];
-    if ((lane & 7) == 0) reinterpret_cast<float*>(stage + T2_VALS_OFF)[j] = V[j];
+    if ((lane & 7) == 0) {
+      reinterpret_cast<float*>(stage + T2_VALS_OFF)[j] = V[j];
+      if (r_src) reinterpret_cast<float*>(stage + T2_R_OFF)[j] = __ldcg(r_src + j);
+    }
   }
   __syncwarp();
   if (lane == 0) {
     if (bulk) {
-      mbar_expect_tx(full, (unsigned)bulk * 36u);
+      mbar_expect_tx(full, (unsigned)bulk * (r_src ? 40u : 36u));
       bulk_g2s(stage, J, (unsigned)bulk * 32u, full);
       bulk_g2s(stage + T2_VALS_OFF, V, (unsigned)bulk * 4u, full);
+      if (r_src) bulk_g2s(stage + T2_R_OFF, r_src, (unsigned)bulk * 4u, full);
     } else {
       mbar_arrive(full);
     }
   }
 }
 
-__global__ void __launch_bounds__(TRK_THREADS, 2)
+__global__ void __launch_bounds__(TRK_THREADS, MAX_OCC)
 track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num_levels,
                  como_b200_track_term_t term, float* __restrict__ T_io, float* __restrict__ aff_io,
                  float* __restrict__ stats, int* __restrict__ num_iters, uint8_t* __restrict__ ws,
@@ -252,10 +317,9 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
 
-  uint8_t* base = ws + lay.levels_bytes + (size_t)prob * lay.per_problem;
-  TrackCtl* ctl = reinterpret_cast<TrackCtl*>(base + lay.ctl_off);
-  double* partials = reinterpret_cast<double*>(base + lay.partials_off);
-  float* g_resid = reinterpret_cast<float*>(base + lay.resid_off);
+  TrackCtl* ctl = reinterpret_cast<TrackCtl*>(ws + lay.ctl_off + (size_t)prob * lay.ctl_stride);
+  double* partials = reinterpret_cast<double*>(ws + lay.partials_off + (size_t)prob * lay.partials_stride);
+  float* g_resid = reinterpret_cast<float*>(ws + lay.resid_off + (size_t)prob * lay.resid_stride);
   const como_b200_track_level_t* levels = levels_all + (size_t)prob * COMO_B200_MAX_LEVELS;
 
   extern __shared__ __align__(128) uint8_t dsm[];
@@ -268,7 +332,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
   __shared__ double s_acc[NACC_PAD];
   __shared__ double s_chol[64];
   __shared__ double s_delta[8];
-  __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES];
+  __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES], p1_done_bar;
   __shared__ float s_T[16];
   __shared__ float s_aff[2];
   __shared__ float s_Pm[12];
@@ -286,6 +350,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], CONS_WARPS);
     }
+    mbar_init(&p1_done_bar, CONS_WARPS);
     s_cnt = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -307,9 +372,13 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
           const unsigned s = n % STAGES;
           produce_tile1(ring + s * STAGE_BYTES, &full_bar[s], &empty_bar[s], n, lv, sl.begin + t0, min(T1, sl.len - t0));
         }
+        // pass-2 tiles carry the residuals pass 1 left in the L2 scratch: wait until this CTA has written them all
+        mbar_wait(&p1_done_bar, (unsigned)pit & 1u);
+        const float* g_r = g_resid + sl.begin;
         for (int t0 = 0; t0 < sl.len; t0 += T2, ++n) {
           const unsigned s = n % STAGES;
-          produce_tile2(ring + s * STAGE_BYTES, &full_bar[s], &empty_bar[s], n, lv, sl.begin + t0, min(T2, sl.len - t0));
+          produce_tile2(ring + s * STAGE_BYTES, &full_bar[s], &empty_bar[s], n, lv, sl.begin + t0, min(T2, sl.len - t0),
+                        t0 < r_cap ? nullptr : g_r + t0);
         }
         __syncthreads();  // the consumers' verdict for this iteration (flag double-buffered by iteration parity)
         if (s_done[pit & 1]) {
@@ -336,8 +405,6 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
     if (N <= 0) continue;
     const int w = lv.w, h = lv.h;
     const SliceInfo sl = slice_of(N, G, c);
-    const float Ax = 1.0f / (float)w, Ay = 1.0f / (float)h;
-    const float wf = (float)w, hf = (float)h;
     const float xmax = (float)(w - 1), ymax = (float)(h - 1);
     float* g_r = g_resid + sl.begin;  // residual of slice pixel j: s_r[j] if j < r_cap else g_r[j]
 
@@ -361,97 +428,118 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
       const float p20 = s_Pm[8], p21 = s_Pm[9], p22 = s_Pm[10], p23 = s_Pm[11];
       const float ea = s_ea, bb = s_aff[1];
 
-      // ---- pass 1: warp, gather, residual, first histogram.  Four pixels per thread and tile so that the
-      // 16 bilinear taps are all in flight together.
+      // ---- pass 1: warp, gather, residual, first histogram.  Four pixels per thread and tile, software pipelined
+      // over two tiles: the 16 bilinear taps of tile t+1 are issued before the residuals of tile t are formed, so a
+      // warp always has a tile's worth of gathers in flight.
       constexpr int PB = T1 / CONS_THREADS;
-      for (int t0 = 0; t0 < sl.len; t0 += T1, ++n) {
+      const float2 A2x = make_float2(2.0f / (float)w, 2.0f / (float)h), A1 = make_float2(1.0f / (float)w, 1.0f / (float)h);
+      const float2 wh2 = make_float2((float)w, (float)h);
+      const float* __restrict__ img = lv.img;
+      const bool has_mask = lv.mask != nullptr;
+      struct P1 {
+        float fxs[PB], fys[PB], vref[PB], v00[PB], v01[PB], v10[PB], v11[PB];
+        bool valid[PB];
+      };
+      // stage A: operands -> warped coordinates -> taps in flight
+      auto gather = [&](int t0, P1& st) {
         const unsigned s = n % STAGES;
         const uint8_t* stage = ring + s * STAGE_BYTES;
         const int cnt = min(T1, sl.len - t0);
         mbar_wait(&full_bar[s], (n / STAGES) & 1u);
-        const float* sP = reinterpret_cast<const float*>(stage);
-        const float* sV = reinterpret_cast<const float*>(stage + T1_VALS_OFF);
-        const uint8_t* sM = stage + T1_MASK_OFF;
-        float X[PB], Y[PB], Z[PB], vref[PB];
+        ++n;
+        const float* sP = reinterpret_cast<const float*>(stage) + 3 * tid;
+        const float* sV = reinterpret_cast<const float*>(stage + T1_VALS_OFF) + tid;
+        const uint8_t* sM = stage + T1_MASK_OFF + tid;
+        float X[PB], Y[PB], Z[PB];
         bool use[PB];
 #pragma unroll
         for (int k = 0; k < PB; ++k) {
-          const int j = tid + k * CONS_THREADS;
-          use[k] = (j < cnt) && (lv.mask ? (sM[j] != 0) : true);
-          X[k] = Y[k] = 0.0f;
-          Z[k] = 1.0f;
-          vref[k] = 0.0f;
-          if (use[k]) {
-            X[k] = sP[3 * j + 0];
-            Y[k] = sP[3 * j + 1];
-            Z[k] = sP[3 * j + 2];
-            vref[k] = sV[j];
-          }
+          // beyond cnt the stage holds stale data: computed, never used
+          use[k] = (tid + k * CONS_THREADS < cnt);
+          if (has_mask) use[k] = use[k] && (sM[k * CONS_THREADS] != 0);
+          X[k] = sP[3 * k * CONS_THREADS + 0];
+          Y[k] = sP[3 * k * CONS_THREADS + 1];
+          Z[k] = sP[3 * k * CONS_THREADS + 2];
+          st.vref[k] = sV[k * CONS_THREADS];
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);  // operands are in registers: release the stage early
-        float w00[PB], w01[PB], w10[PB], w11[PB];
-        const float* t00[PB];
-        int dxs[PB], dys[PB];
-        bool valid[PB];
 #pragma unroll
         for (int k = 0; k < PB; ++k) {
           const float hx = p00 * X[k] + p01 * Y[k] + p02 * Z[k] + p03;
           const float hy = p10 * X[k] + p11 * Y[k] + p12 * Z[k] + p13;
           const float hz = p20 * X[k] + p21 * Y[k] + p22 * Z[k] + p23;
-          const float x = hx / hz, y = hy / hz;
-          valid[k] = use[k] && (x >= 1.0f) && (x < xmax) && (y >= 1.0f) && (y < ymax) && (hz > 0.0f);
-          // the reference maps pixel coords to [-1,1] and grid_sample maps them back; reproduce
-          // that fp32 round trip (coords.py:18-20, grid_sample unnormalize, align_corners=False)
-          const float xn = __fsub_rn(__fadd_rn(__fmul_rn(2.0f * Ax, x), Ax), 1.0f);
-          const float yn = __fsub_rn(__fadd_rn(__fmul_rn(2.0f * Ay, y), Ay), 1.0f);
-          const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(xn, 1.0f), wf), 1.0f), 0.5f);
-          const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(yn, 1.0f), hf), 1.0f), 0.5f);
-          const float x0f = floorf(ix), y0f = floorf(iy);
-          const float fx0 = ix - x0f, fy0 = iy - y0f;
-          const float fx1 = (x0f + 1.0f) - ix, fy1 = (y0f + 1.0f) - iy;
-          w00[k] = fx1 * fy1;
-          w01[k] = fx0 * fy1;
-          w10[k] = fx1 * fy0;
-          w11[k] = fx0 * fy0;
-          int x0 = valid[k] ? (int)x0f : 0, y0 = valid[k] ? (int)y0f : 0;
-          const int xa = min(max(x0, 0), w - 1), xb = min(max(x0 + 1, 0), w - 1);
-          const int ya = min(max(y0, 0), h - 1), yb = min(max(y0 + 1, 0), h - 1);
-          t00[k] = lv.img + (size_t)ya * w + xa;
-          dxs[k] = xb - xa;
-          dys[k] = (yb - ya) * w;
+          // (x, y) = (hx, hy) / hz as the reference divides: reciprocal refined to full precision, then one
+          // residual correction per quotient (the IEEE quotient for operands in the normal range), on packed pairs
+          float r0 = rcp_approx(hz);
+          r0 = fmaf(r0, fmaf(-hz, r0, 1.0f), r0);
+          const float2 r2 = make_float2(r0, r0), h2 = make_float2(hx, hy);
+          float2 q2 = __fmul2_rn(h2, r2);
+          q2 = __ffma2_rn(__ffma2_rn(make_float2(-hz, -hz), q2, h2), r2, q2);
+          st.valid[k] = use[k] && (q2.x >= 1.0f) && (q2.x < xmax) && (q2.y >= 1.0f) && (q2.y < ymax) && (hz > 0.0f);
+          // the reference maps pixel coords to [-1,1] and grid_sample maps them back; reproduce that fp32 round
+          // trip step by step (coords.py:18-20, grid_sample unnormalize, align_corners=False): its rounding moves
+          // a coordinate by up to w * 6e-8 px, which is what one pixel's residual -- the median -- is sensitive to
+          float2 t = __fmul2_rn(A2x, q2);
+          t = __fadd2_rn(t, A1);
+          t = __fadd2_rn(t, make_float2(-1.0f, -1.0f));
+          t = __fadd2_rn(t, make_float2(1.0f, 1.0f));
+          t = __fmul2_rn(t, wh2);
+          t = __fadd2_rn(t, make_float2(-1.0f, -1.0f));
+          t = __fmul2_rn(t, make_float2(0.5f, 0.5f));
+          const float x0f = floorf(t.x), y0f = floorf(t.y);
+          st.fxs[k] = t.x - x0f;
+          st.fys[k] = t.y - y0f;
+          // valid => 1 <= x0 <= w-2 and 1 <= y0 <= h-2: the four taps are inside the image (photo_utils.py:9-31);
+          // invalid points read the first pixels (unconditional loads: no branches), their result is discarded
+          const int off = st.valid[k] ? ((int)y0f * w + (int)x0f) : 0;
+          const float* p0 = img + off;
+          const float* p1 = p0 + w;
+          st.v00[k] = __ldg(p0);
+          st.v01[k] = __ldg(p0 + 1);
+          st.v10[k] = __ldg(p1);
+          st.v11[k] = __ldg(p1 + 1);
         }
-        float v00[PB], v01[PB], v10[PB], v11[PB];
+      };
+      // stage B: interpolate, residual, histogram, store r
+      auto finish = [&](int t0, const P1& st) {
+        const bool tile_in_smem = (t0 < r_cap);  // r_cap is a multiple of T1
+        float* r_tile = (tile_in_smem ? (s_r + t0) : (g_r + t0)) + tid;
+        float rout[PB];
 #pragma unroll
         for (int k = 0; k < PB; ++k) {
-          v00[k] = v01[k] = v10[k] = v11[k] = 0.0f;
-          if (valid[k]) {
-            v00[k] = __ldg(t00[k]);
-            v01[k] = __ldg(t00[k] + dxs[k]);
-            v10[k] = __ldg(t00[k] + dys[k]);
-            v11[k] = __ldg(t00[k] + dys[k] + dxs[k]);
-          }
+          const float top = st.v00[k] + st.fxs[k] * (st.v01[k] - st.v00[k]);
+          const float bot = st.v10[k] + st.fxs[k] * (st.v11[k] - st.v10[k]);
+          const float v = top + st.fys[k] * (bot - top);
+          const float r = (ea * v + bb) - st.vref[k];
+          if (st.valid[k]) atomicAdd(&s_hist[first_bin(__float_as_uint(fabsf(r)))], 1u);
+          rout[k] = st.valid[k] ? r : __int_as_float(0x7fc00000);
         }
+        if (tile_in_smem) {  // rows beyond cnt stay inside the padded slice storage
 #pragma unroll
-        for (int k = 0; k < PB; ++k) {
-          const int j = tid + k * CONS_THREADS;
-          if (j < cnt) {
-            float r = __int_as_float(0x7fc00000);
-            if (valid[k]) {
-              float v = v00[k] * w00[k];
-              v += v01[k] * w01[k];
-              v += v10[k] * w10[k];
-              v += v11[k] * w11[k];
-              const float tmp = ea * v;
-              r = (tmp + bb) - vref[k];
-              atomicAdd(&s_hist[first_bin(__float_as_uint(fabsf(r)))], 1u);
-            }
-            const int js = t0 + j;
-            if (js < r_cap) s_r[js] = r;
-            else __stcg(g_r + js, r);
+          for (int k = 0; k < PB; ++k) r_tile[k * CONS_THREADS] = rout[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < PB; ++k) __stcg(r_tile + k * CONS_THREADS, rout[k]);
+        }
+      };
+      {
+        P1 sa, sb;
+        if (sl.len > 0) gather(0, sa);
+        for (int t0 = 0; t0 < sl.len; t0 += 2 * T1) {
+          const bool more1 = t0 + T1 < sl.len;
+          if (more1) gather(t0 + T1, sb);
+          finish(t0, sa);
+          if (more1) {
+            if (t0 + 2 * T1 < sl.len) gather(t0 + 2 * T1, sa);
+            finish(t0 + T1, sb);
           }
         }
       }
+      // residuals in the L2 scratch are read back by the TMA unit in pass 2 (async proxy): fence, then signal the producer
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p1_done_bar);
       flush_hist(s_hist, gh, single);
       consumer_group_barrier(&ctl->barrier, epoch, G);
 
@@ -465,23 +553,22 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         if (bin == 0u) {
           klo = 0u;
           khi = KEY_LO;
-        } else if (bin == 2047u) {
+        } else if (bin == (unsigned)(HIST_BINS - 1)) {
           klo = KEY_HI;
           khi = 0x80000000u;
         } else {
-          klo = KEY_LO + ((bin - 1u) << 17);
-          khi = klo + 0x20000u;
+          klo = KEY_LO + ((bin - 1u) << KEY_SHIFT);
+          khi = klo + (1u << KEY_SHIFT);
         }
         int pass = 0;
         while (khi - klo > 1u) {
           if (cnt_in <= (unsigned)cand_cap) {
             // compact this CTA's candidates, append them to the problem's list, then select locally
-            for (int j = tid; j < sl.len; j += CONS_THREADS) {
-              const float r = (j < r_cap) ? s_r[j] : __ldcg(g_r + j);
-              if (r == r) {
-                const unsigned key = __float_as_uint(fabsf(r));
-                if (key >= klo && key < khi) s_cand[atomicAdd(&s_cnt, 1u)] = key;
-              }
+            {
+              const unsigned wdt = khi - klo;
+              for_each_key(s_r, g_r, r_cap, sl.len, [&](unsigned key) {
+                if (key - klo < wdt) s_cand[atomicAdd(&s_cnt, 1u)] = key;
+              });
             }
             consumer_sync();
             const unsigned mine = s_cnt;
@@ -496,7 +583,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
             if (tid == 0) s_cnt = 0;
             consumer_sync();
             while (khi - klo > 1u) {
-              const int sh = max(0, clog2(khi - klo) - 11);
+              const int sh = max(0, clog2(khi - klo) - HIST_BITS);
               for (unsigned j = tid; j < cnt_in; j += CONS_THREADS) {
                 const unsigned key = s_cand[j];
                 if (key >= klo && key < khi) atomicAdd(&s_hist[(key - klo) >> sh], 1u);
@@ -514,13 +601,12 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
           }
           // crowded bin: narrow it with another histogram pass over the problem
           ++pass;
-          const int sh = max(0, clog2(khi - klo) - 11);
-          for (int j = tid; j < sl.len; j += CONS_THREADS) {
-            const float r = (j < r_cap) ? s_r[j] : __ldcg(g_r + j);
-            if (r == r) {
-              const unsigned key = __float_as_uint(fabsf(r));
-              if (key >= klo && key < khi) atomicAdd(&s_hist[(key - klo) >> sh], 1u);
-            }
+          const int sh = max(0, clog2(khi - klo) - HIST_BITS);
+          {
+            const unsigned wdt = khi - klo;
+            for_each_key(s_r, g_r, r_cap, sl.len, [&](unsigned key) {
+              if (key - klo < wdt) atomicAdd(&s_hist[(key - klo) >> sh], 1u);
+            });
           }
           flush_hist(s_hist, gh + pass * HIST_BINS, single);
           consumer_group_barrier(&ctl->barrier, epoch, G);
@@ -535,64 +621,79 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         sigma = 1.4826f * __uint_as_float(klo);
       }
 
-      // ---- pass 2: robust weights + normal equations
-      float acc[NACC];
+      // ---- pass 2: robust weights + normal equations.  Four pixels per thread and tile; the residuals of the
+      // next tile are fetched (L2 scratch) while this one is accumulated.  The 8x8 rank-one update runs on packed
+      // fp32 pairs (fma.rn.f32x2): accumulator pair (H[2a][m], H[2a+1][m]) += (w j_2a, w j_2a+1) * (j_m, j_m).
+      constexpr int PB2 = T2 / CONS_THREADS;
+      float2 A2[20], G2[4];
+      float errs = 0.0f;
 #pragma unroll
-      for (int k = 0; k < NACC; ++k) acc[k] = 0.0f;
+      for (int k = 0; k < 20; ++k) A2[k] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) G2[k] = make_float2(0.f, 0.f);
       const float inv_sigma = 1.0f / sigma;
-      const int hsel = (tid >> 2) & 1;  // which half of the 32-byte J row this lane reads first (bank spreading)
+      const float qnan = __int_as_float(0x7fc00000);
       for (int t0 = 0; t0 < sl.len; t0 += T2, ++n) {
         const unsigned s = n % STAGES;
         const uint8_t* stage = ring + s * STAGE_BYTES;
-        const int cnt = min(T2, sl.len - t0);
-        float rr[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int j = tid + k * CONS_THREADS;
-          const int js = t0 + j;
-          rr[k] = __int_as_float(0x7fc00000);
-          if (j < cnt) rr[k] = (js < r_cap) ? s_r[js] : __ldcg(g_r + js);
-        }
         mbar_wait(&full_bar[s], (n / STAGES) & 1u);
-        const float4* sJ = reinterpret_cast<const float4*>(stage);
-        const float* sV = reinterpret_cast<const float*>(stage + T2_VALS_OFF);
-        float vv[2];
-        float4 ja[2], jb[2];
+        const float4* sJ = reinterpret_cast<const float4*>(stage) + 2 * tid;
+        const float* sV = reinterpret_cast<const float*>(stage + T2_VALS_OFF) + tid;
+        const float* sR = (t0 < r_cap ? (s_r + t0) : reinterpret_cast<const float*>(stage + T2_R_OFF)) + tid;
+        const int left = sl.len - t0 - tid;
+        float vv[PB2], rr[PB2];
+        float4 ja[PB2], jb[PB2];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int j = tid + k * CONS_THREADS;
-          vv[k] = 0.0f;
-          ja[k] = jb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j < cnt) {
-            vv[k] = sV[j];
-            const float4 q0 = sJ[2 * j + hsel];
-            const float4 q1 = sJ[2 * j + (hsel ^ 1)];
-            ja[k] = hsel ? q1 : q0;
-            jb[k] = hsel ? q0 : q1;
-          }
+        for (int k = 0; k < PB2; ++k) {  // rows beyond the tile's count hold stale data: their r is forced to NaN
+          vv[k] = sV[k * CONS_THREADS];
+          rr[k] = (k * CONS_THREADS < left) ? sR[k * CONS_THREADS] : qnan;
+          ja[k] = sJ[2 * k * CONS_THREADS];
+          jb[k] = sJ[2 * k * CONS_THREADS + 1];
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < PB2; ++k) {
           const float r = rr[k];
           if (r == r) {
-            const float tmp = (r - bb) + vv[k];
-            float j[8] = {ja[k].x, ja[k].y, ja[k].z, ja[k].w, jb[k].x, jb[k].y, -tmp, 1.0f};
+            const float mt = (bb - r) - vv[k];  // column 6 of J: -e^{-a} I_j
             const float wr = r * inv_sigma;
             const float a = fabsf(wr);
-            const float wgt = (a < HUBER_K) ? 1.0f : HUBER_K / a;
-            acc[44] += wgt * wr * wr;
+            const float wgt = (a < HUBER_K) ? 1.0f : HUBER_K * rcp_approx(a);
+            errs += wgt * wr * wr;
+            const float2 w2 = make_float2(wgt, wgt);
+            const float2 W[4] = {__fmul2_rn(w2, make_float2(ja[k].x, ja[k].y)), __fmul2_rn(w2, make_float2(ja[k].z, ja[k].w)),
+                                 __fmul2_rn(w2, make_float2(jb[k].x, jb[k].y)), __fmul2_rn(w2, make_float2(mt, 1.0f))};
+            const float2 D[8] = {make_float2(ja[k].x, ja[k].x), make_float2(ja[k].y, ja[k].y), make_float2(ja[k].z, ja[k].z),
+                                 make_float2(ja[k].w, ja[k].w), make_float2(jb[k].x, jb[k].x), make_float2(jb[k].y, jb[k].y),
+                                 make_float2(mt, mt),           make_float2(1.0f, 1.0f)};
+            const float2 r2 = make_float2(r, r);
             int q = 0;
 #pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const float wj = wgt * j[kk];
-              acc[36 + kk] += wj * r;
+            for (int a2 = 0; a2 < 4; ++a2) {
+              G2[a2] = __ffma2_rn(W[a2], r2, G2[a2]);
 #pragma unroll
-              for (int m = kk; m < 8; ++m) acc[q++] += wj * j[m];
+              for (int m = 2 * a2; m < 8; ++m, ++q) A2[q] = __ffma2_rn(W[a2], D[m], A2[q]);
             }
           }
         }
+      }
+      // unpack the row pairs into the packed upper triangle
+      float acc[NACC];
+      {
+        int q = 0;
+#pragma unroll
+        for (int a2 = 0; a2 < 4; ++a2) {
+#pragma unroll
+          for (int m = 2 * a2; m < 8; ++m, ++q) {
+            const int r0 = 2 * a2, r1 = 2 * a2 + 1;
+            acc[r0 * 8 - (r0 * (r0 - 1)) / 2 + (m - r0)] = A2[q].x;
+            if (m >= r1) acc[r1 * 8 - (r1 * (r1 - 1)) / 2 + (m - r1)] = A2[q].y;
+          }
+          acc[36 + 2 * a2] = G2[a2].x;
+          acc[36 + 2 * a2 + 1] = G2[a2].y;
+        }
+        acc[44] = errs;
       }
 #pragma unroll
       for (int k = 0; k < NACC; ++k) {
@@ -617,13 +718,21 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
 
       // ---- deterministic cross-CTA sum, solve, update, termination (identical in every CTA)
       if (!single) {
-        const int k = tid >> 2, s4 = tid & 3;
+        const int k = tid >> 1, s2 = tid & 1;   // 64 slots for 45 sums, two strided partial sums each
         double s = 0.0;
-        if (k < NACC)
-          for (int cc = s4; cc < G; cc += 4) s += __ldcg(partials + (size_t)cc * NACC_PAD + k);
+        if (k < NACC) {  // eight loads in flight, added in a fixed order
+          int cc = s2;
+          for (; cc + 14 < G; cc += 16) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(partials + (size_t)(cc + 2 * u) * NACC_PAD + k);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
+          }
+          for (; cc < G; cc += 2) s += __ldcg(partials + (size_t)cc * NACC_PAD + k);
+        }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (s4 == 0 && k < NACC) s_acc[k] = s;
+        if (s2 == 0 && k < NACC) s_acc[k] = s;
         consumer_sync();
       }
       if (wid == 0) {
@@ -709,9 +818,9 @@ struct TrackLaunchCfg {
   size_t dyn_smem;
 };
 
-// Launch shape: G CTAs per problem, 1 or 2 CTAs per SM.  One CTA per SM (the residual slice stays in shared
-// memory) while the problems fit that way; two per SM for larger batches so that one CTA streams while the
-// other sits in a reduction.  COMO_B200_TRACK_G / COMO_B200_TRACK_OCC override (tuning only).
+// Launch shape: G CTAs per problem, 1-3 CTAs per SM.  One CTA per SM (the residual slice stays in shared memory)
+// while the problems fit that way; several per SM for larger batches so that one CTA streams while another sits
+// in a reduction or a group barrier.  COMO_B200_TRACK_G / COMO_B200_TRACK_OCC override (tuning only).
 static int track_config(int num_problems, int max_n, TrackLaunchCfg* cfg) {
   int dev = 0;
   cudaGetDevice(&dev);
@@ -724,28 +833,23 @@ static int track_config(int num_problems, int max_n, TrackLaunchCfg* cfg) {
   const int g_want = max_n > 0 ? (max_n + 2047) / 2048 : 1;
   const char* e_occ = getenv("COMO_B200_TRACK_OCC");
   const char* e_g = getenv("COMO_B200_TRACK_G");
-  int occ = ((long long)num_problems * (g_want < 8 ? g_want : 8) > sms) ? 2 : 1;
-  if (e_occ) occ = atoi(e_occ) >= 2 ? 2 : 1;
-  for (;; occ = 1) {
-    const int per_cta = (occ == 1) ? smem_optin : (smem_sm / 2 - 1024);
+  const long long want = (long long)num_problems * (g_want < 8 ? g_want : 8);
+  int occ = want > 2LL * sms ? 3 : (want > sms ? 2 : 1);
+  if (e_occ && atoi(e_occ) >= 1) occ = atoi(e_occ) > MAX_OCC ? MAX_OCC : atoi(e_occ);
+  for (; occ >= 1; --occ) {
+    const int per_cta = (occ == 1) ? smem_optin : (smem_sm / occ - 1024);
     long long dyn = (long long)per_cta - (long long)fa.sharedSizeBytes;
-    if (dyn > smem_optin - (int)fa.sharedSizeBytes) dyn = smem_optin - (int)fa.sharedSizeBytes;
-    long long r_bytes = dyn - (long long)STAGES * STAGE_BYTES;
-    if (r_bytes < 0) {
-      if (occ == 2) continue;
-      return -1;
-    }
-    int r_cap = (int)(r_bytes / 4) / CHUNK_ALIGN * CHUNK_ALIGN;
-    size_t dyn_smem = (size_t)STAGES * STAGE_BYTES + (size_t)r_cap * 4;
+    if (dyn > smem_optin - (long long)fa.sharedSizeBytes) dyn = smem_optin - (long long)fa.sharedSizeBytes;
+    const long long r_bytes = dyn - (long long)STAGES * STAGE_BYTES;
+    if (r_bytes < 0) continue;
+    const int r_cap = (int)(r_bytes / 4) / T1 * T1;
+    const size_t dyn_smem = (size_t)STAGES * STAGE_BYTES + (size_t)r_cap * 4;
     cudaFuncSetAttribute(track_pyr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, track_pyr_kernel, TRK_THREADS, dyn_smem);
     if (per_sm > occ) per_sm = occ;
     const int cap = per_sm * sms / (num_problems > 0 ? num_problems : 1);
-    if (cap < 1) {
-      if (occ == 2) continue;
-      return 0;
-    }
+    if (cap < 1) continue;
     int G = g_want < cap ? g_want : cap;
     if (e_g && atoi(e_g) >= 1) G = atoi(e_g) < cap ? atoi(e_g) : cap;
     if (G > MAX_GROUP) G = MAX_GROUP;
@@ -754,6 +858,8 @@ static int track_config(int num_problems, int max_n, TrackLaunchCfg* cfg) {
     cfg->dyn_smem = dyn_smem;
     return G;
   }
+  // more problems than co-resident CTAs even at the highest occupancy
+  return 0;
 }
 
 static int g_track_cand_cap = CAND_CAP;
@@ -794,7 +900,7 @@ using namespace como;
 extern "C" size_t como_b200_track_workspace_bytes(int32_t max_n, int32_t num_problems) {
   if (max_n < 0 || num_problems <= 0) return 0;
   const TrackLayout L = track_layout(max_n, num_problems);
-  return L.levels_bytes + (size_t)num_problems * L.per_problem;
+  return L.total;
 }
 
 extern "C" void como_b200_track_debug_candidate_cap(int32_t cap) {
@@ -825,7 +931,7 @@ extern "C" int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_
   const int G = track_config(num_problems, max_n, &cfg);
   COMO_REQUIRE(G >= 1, "track_pyr: %d problems exceed the co-resident CTA capacity", num_problems);
   const TrackLayout L = track_layout(max_n, num_problems);
-  const size_t need = L.levels_bytes + (size_t)num_problems * L.per_problem;
+  const size_t need = L.total;
   if (workspace_bytes < need) {
     set_last_error("track_pyr: workspace %zu < required %zu", workspace_bytes, need);
     return COMO_B200_EWORKSPACE;
@@ -877,8 +983,7 @@ extern "C" int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_
       return COMO_B200_ELAUNCH;
     }
   }
-  for (int p = 0; p < num_problems; ++p)
-    cudaMemsetAsync(ws + L.levels_bytes + (size_t)p * L.per_problem, 0, sizeof(TrackCtl), stream);
+  cudaMemsetAsync(ws + L.ctl_off, 0, (size_t)num_problems * L.ctl_stride, stream);
 
   const como_b200_track_level_t* d_levels = (const como_b200_track_level_t*)ws;
   como_b200_track_term_t t = *term;

@@ -47,8 +47,7 @@ class Tracking:
             raise NotImplementedError("como_b200 Tracking supports tracking.color: gray only")
         if self.dtype != torch.float:
             raise NotImplementedError("como_b200 Tracking runs in float32 (tracking.dtype: float)")
-        torch.cuda.set_device(self.device)
-        self.dev = torch.device(self.device)
+        self.dev = torch.device(self.device)   # no process-wide set_device: every launch below runs under a device guard
         self.intrinsics = self.intrinsics.to(device=self.dev, dtype=self.dtype)
         self.start_level = int(self.cfg["pyr"]["start_level"])
         self.end_level = int(self.cfg["pyr"]["end_level"])
@@ -103,27 +102,50 @@ class Tracking:
         return a
 
     # ------------------------------------------------------------------ images
-    def prep_tracking_img(self, rgb):
-        """rgb (1,3,H,W) -> list of (1,1,h,w) gray levels, coarsest first."""
+    def _pyramid(self, rgb, with_grads):
+        """One fused launch per image: gray + all pyramid levels (+ Scharr gradients laid out [I, gx, gy] per level,
+        the layout kf_reference_level gathers from).  Pyramids deeper than 4 levels use the per-level kernels."""
         rgb = rgb.to(device=self.dev, dtype=torch.float32).contiguous()
         b = rgb.shape[0]
-        out = [torch.empty((b, 1, h, w), dtype=torch.float32, device=self.dev) for (h, w) in self.level_sizes]
+        nl = self.num_levels
         H, W = self.level_sizes[-1]
-        for i in range(b):
-            ptrs = (C.c_void_p * self.num_levels)(*[o[i].data_ptr() for o in out])
-            st = _lib.gray_pyramid(_lib.ptr(rgb[i]), H, W, self.num_levels, ptrs, _lib.stream_ptr(self.dev))
-            _lib.check(st, "como_b200_gray_pyramid")
+        ch = 3 if with_grads else 1
+        out = [torch.empty((b, ch, h, w), dtype=torch.float32, device=self.dev) for (h, w) in self.level_sizes]
+        with torch.cuda.device(self.dev):
+            stream = _lib.stream_ptr(self.dev)
+            for i in range(b):
+                ptrs = (C.c_void_p * nl)(*[o[i, 0].data_ptr() for o in out])
+                if nl <= 4:
+                    gx = (C.c_void_p * nl)(*[o[i, 1].data_ptr() for o in out]) if with_grads else None
+                    gy = (C.c_void_p * nl)(*[o[i, 2].data_ptr() for o in out]) if with_grads else None
+                    st = _lib.image_pyramid_fused(_lib.ptr(rgb[i]), H, W, nl, ptrs, gx, gy, stream)
+                    _lib.check(st, "como_b200_image_pyramid_fused")
+                else:
+                    st = _lib.gray_pyramid(_lib.ptr(rgb[i]), H, W, nl, ptrs, stream)
+                    _lib.check(st, "como_b200_gray_pyramid")
+                    if with_grads:
+                        for o in out:
+                            st = _lib.image_gradients(_lib.ptr(o[i, 0]), o.shape[-2], o.shape[-1], _lib.ptr(o[i, 1]),
+                                                      _lib.ptr(o[i, 2]), stream)
+                            _lib.check(st, "como_b200_image_gradients")
         return out
 
+    def prep_tracking_img(self, rgb):
+        """rgb (1,3,H,W) -> list of (1,1,h,w) gray levels, coarsest first."""
+        return self._pyramid(rgb, False)
+
     def get_img_gradients(self, img_pyr):
+        """Gradients of an existing pyramid (reference signature, Tracking.py:96-102) -> list of (b,3,h,w) [I, gx, gy]."""
         res = []
-        for lvl in img_pyr:
-            gx, gy = torch.empty_like(lvl), torch.empty_like(lvl)
-            for i in range(lvl.shape[0]):
-                st = _lib.image_gradients(_lib.ptr(lvl[i]), lvl.shape[-2], lvl.shape[-1], _lib.ptr(gx[i]), _lib.ptr(gy[i]),
-                                          _lib.stream_ptr(self.dev))
-                _lib.check(st, "como_b200_image_gradients")
-            res.append(torch.cat((lvl, gx, gy), dim=1))
+        with torch.cuda.device(self.dev):
+            for lvl in img_pyr:
+                o = torch.empty((lvl.shape[0], 3, lvl.shape[-2], lvl.shape[-1]), dtype=torch.float32, device=self.dev)
+                o[:, 0:1] = lvl
+                for i in range(lvl.shape[0]):
+                    st = _lib.image_gradients(_lib.ptr(o[i, 0]), lvl.shape[-2], lvl.shape[-1], _lib.ptr(o[i, 1]),
+                                              _lib.ptr(o[i, 2]), _lib.stream_ptr(self.dev))
+                    _lib.check(st, "como_b200_image_gradients")
+                res.append(o)
         return res
 
     # ------------------------------------------------------------------ keyframe / one-way decisions
@@ -162,16 +184,18 @@ class Tracking:
         n = P_last.shape[0]
         H, W = self.level_sizes[-1]
         T = T_curr_kf.reshape(4, 4).to(torch.float32).contiguous()
-        st = _lib.reproj_depth(_lib.ptr(P_last), n, _lib.ptr(T), self._K9[-1], H, W, _lib.ptr(self._winner),
-                               _lib.ptr(self._reproj), _lib.stream_ptr(self.dev))
+        with torch.cuda.device(self.dev):
+            st = _lib.reproj_depth(_lib.ptr(P_last), n, _lib.ptr(T), self._K9[-1], H, W, _lib.ptr(self._winner),
+                                   _lib.ptr(self._reproj), _lib.stream_ptr(self.dev))
         _lib.check(st, "como_b200_reproj_depth")
         return self._reproj.view(1, H, W)
 
     def _reproj_stats(self, T_curr_kf):
         self.get_reproj_last_kf(T_curr_kf)
         H, W = self.level_sizes[-1]
-        st = _lib.median_f32(_lib.ptr(self._reproj), _lib.ptr(self._seg), 1, H * W, 1.0, _lib.ptr(self._med), _lib.ptr(self._cnt),
-                             _lib.ptr(self._med_ws), self._med_ws.numel(), _lib.stream_ptr(self.dev))
+        with torch.cuda.device(self.dev):
+            st = _lib.median_f32(_lib.ptr(self._reproj), _lib.ptr(self._seg), 1, H * W, 1.0, _lib.ptr(self._med),
+                                 _lib.ptr(self._cnt), _lib.ptr(self._med_ws), self._med_ws.numel(), _lib.stream_ptr(self.dev))
         _lib.check(st, "como_b200_median_f32")
         return self._med[0], self._cnt[0]
 
@@ -197,11 +221,14 @@ class Tracking:
             self.last_kf_sent_ts = timestamps[-1]
 
         if timestamps[-1] != self.kf_received_ts:
-            self._kf_img_pyr = self.prep_tracking_img(kf_rgb)
-            self._kf_img_grads = self.get_img_gradients(self._kf_img_pyr)
+            self._kf_img_grads = self._pyramid(kf_rgb, True)   # gray + pyramid + Scharr of every level: one launch
+            self._kf_img_pyr = [g[:, 0:1] for g in self._kf_img_grads]
         num_kf = kf_pose.shape[0]
         rel_poses = (_inv_se3(kf_pose[num_kf - 1:num_kf]) @ kf_pose).to(torch.float32).contiguous()  # (B,4,4)
         Hf, Wf = int(depth.shape[-2]), int(depth.shape[-1])
+        if (Hf, Wf) != tuple(self.level_sizes[-1]) or depth.shape[0] != kf_pose.shape[0]:
+            raise RuntimeError(f"update_kf_reference: depth {tuple(depth.shape)} does not match {kf_pose.shape[0]} keyframes "
+                               f"of size {tuple(self.level_sizes[-1])}")
         self.vals_pyr, self.img_grads_pyr, self.coords_pyr = [], [], []
         self.P_pyr, self.dI_dT_pyr, self.mask_pyr = [], [], []
         for l, (h, w) in enumerate(self.level_sizes):
@@ -214,10 +241,11 @@ class Tracking:
             mask = torch.empty((num_kf, n), dtype=torch.uint8, device=self.dev)
             ig = self._kf_img_grads[l]
             for b in range(num_kf):
-                st = _lib.kf_reference_level(
-                    _lib.ptr(ig[b, 0]), _lib.ptr(ig[b, 1]), _lib.ptr(ig[b, 2]), _lib.ptr(depth[b, 0]), Hf, Wf, sub, h, w,
-                    self._K9[l], _lib.ptr(rel_poses[b]), 50.0, 1e-4, _lib.ptr(vals[b]), _lib.ptr(grads[b]), _lib.ptr(P[b]),
-                    _lib.ptr(J[b]), _lib.ptr(mask[b]), _lib.stream_ptr(self.dev))
+                with torch.cuda.device(self.dev):
+                    st = _lib.kf_reference_level(
+                        _lib.ptr(ig[b, 0]), _lib.ptr(ig[b, 1]), _lib.ptr(ig[b, 2]), _lib.ptr(depth[b, 0]), Hf, Wf, sub, h, w,
+                        self._K9[l], _lib.ptr(rel_poses[b]), 50.0, 1e-4, _lib.ptr(vals[b]), _lib.ptr(grads[b]), _lib.ptr(P[b]),
+                        _lib.ptr(J[b]), _lib.ptr(mask[b]), _lib.stream_ptr(self.dev))
                 _lib.check(st, "como_b200_kf_reference_level")
             self.vals_pyr.append(vals)
             self.img_grads_pyr.append(grads)

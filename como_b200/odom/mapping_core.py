@@ -35,8 +35,22 @@ class _Plan:
     pass
 
 
+def _ts_tuple(s, name):
+    """Timestamps as host floats.  The reference's transfer_data leaves them as CUDA scalars, and float(t) on each of
+    them every iteration would be K + R blocking device->host reads: convert once per change of the list."""
+    ts = getattr(s, name)
+    if not any(isinstance(t, torch.Tensor) for t in ts):
+        return tuple(float(t) for t in ts)
+    cache = s.__dict__.setdefault("_b200_cache", {})
+    key = tuple((id(t), getattr(t, "_version", 0)) for t in ts)
+    hit = cache.get("ts_" + name)
+    if hit is None or hit[0] != key:
+        hit = cache["ts_" + name] = (key, tuple(float(t) for t in ts), list(ts))   # keeps the objects alive: ids stay unique
+    return hit[1]
+
+
 def _structure_key(s):
-    return (tuple(float(t) for t in s.kf_timestamps), s.Knm_Kmminv.data_ptr(), tuple(s.correspondence_mask.shape),
+    return (_ts_tuple(s, "kf_timestamps"), s.Knm_Kmminv.data_ptr(), tuple(s.correspondence_mask.shape),
             s.kf_img_and_grads.data_ptr(), s.L_mm.data_ptr(), bool(s.window_full))
 
 
@@ -101,8 +115,8 @@ def _build_pair_plan(s, cfg, kp, dev, rank=0, world=1):
     q = _Plan()
     K = kp.K
     R = int(s.recent_poses.shape[0]) if s.recent_poses.numel() > 0 else 0
-    ref, tgt, ow_kf, ow_t = setup_photometric_pairs(K, R, s.kf_timestamps, s.recent_timestamps, None,
-                                                    cfg["photo_construction"])
+    ref, tgt, ow_kf, ow_t = setup_photometric_pairs(K, R, list(_ts_tuple(s, "kf_timestamps")),
+                                                    list(_ts_tuple(s, "recent_timestamps")), None, cfg["photo_construction"])
     q.pairs_full = (ref, tgt, ow_kf, ow_t)
     pair_ref, pair_tgt, pair_batch, nbatch = partition_pairs(ref, tgt, ow_kf, ow_t, K,
                                                              int(cfg["photo_construction"]["pairwise_batch_size"]),
@@ -178,7 +192,7 @@ def get_plans(s, cfg, dev, rank=0, world=1):
         cache["kf_plan"] = _build_kf_plan(s, cfg, dev)
         cache["kf_key"] = key
         cache.pop("pair_key", None)
-    pkey = (key, tuple(float(t) for t in s.recent_timestamps), rank, world)
+    pkey = (key, _ts_tuple(s, "recent_timestamps"), rank, world)
     if cache.get("pair_key") != pkey:
         cache["pair_plan"] = _build_pair_plan(s, cfg, cache["kf_plan"], dev, rank, world)
         cache["pair_key"] = pkey
@@ -236,11 +250,62 @@ def solve_system(H, g):
     return x
 
 
-def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return_debug=False):
-    """One BA Gauss-Newton iteration; mutates `s` like Mapping.iterate.  When the pair blocks of one window
-    are sharded over `world` ranks (reference keyframe k on rank k % world), `hist_allreduce(t)` sums the
-    median digit histograms and `allreduce(H, g, err)` sums the photometric normal equations across ranks
-    (NCCL over NVLink); priors, solve and update are replicated on every rank."""
+class ShardComm:
+    """The exchange steps of ONE window sharded over the ranks of a torch.distributed group (NCCL over NVLink):
+      * pair blocks by reference keyframe (k % world == rank): residual + accumulation passes run on 1/world of the pairs
+      * store_vars by contiguous keyframe range: each rank streams K/world predictor slabs; the K median depths are
+        exchanged (sum of vectors that are zero off the owner's range -- exact), dense depth images stay with their owner
+      * the robust scale is a GLOBAL median per pair batch: digit histograms are summed between the radix passes
+      * the photometric normal equations (H, g, error) are summed; priors, solve and update are replicated.
+    `warm()` runs every collective once at its real message size so that connection set-up and buffer registration
+    are not charged to the first timed iteration."""
+
+    def __init__(self, world, rank, device, group=None):
+        import torch.distributed as dist
+
+        self.dist, self.world, self.rank, self.device, self.group = dist, int(world), int(rank), device, group
+        self._warmed = None
+
+    def kf_range(self, K):
+        per = (K + self.world - 1) // self.world
+        return min(K, self.rank * per), min(K, (self.rank + 1) * per)
+
+    def allreduce_hist(self, t):
+        self.dist.all_reduce(t, group=self.group)
+
+    def allreduce_system(self, H, g, err):
+        self.dist.all_reduce(H, group=self.group)
+        self.dist.all_reduce(g, group=self.group)
+        self.dist.all_reduce(err, group=self.group)
+
+    def allreduce_small(self, t):
+        self.dist.all_reduce(t, group=self.group)
+
+    def warm(self, dim, nbatch, K):
+        key = (dim, nbatch, K)
+        if self._warmed == key:
+            return
+        for _ in range(2):
+            self.allreduce_system(torch.zeros(dim, dim, dtype=F64, device=self.device),
+                                  torch.zeros(dim, dtype=F64, device=self.device), torch.zeros(8, dtype=F64, device=self.device))
+            self.allreduce_hist(torch.zeros(nbatch, 2048, dtype=torch.int32, device=self.device))
+            self.allreduce_small(torch.zeros(K, dtype=F64, device=self.device))
+        torch.cuda.synchronize(self.device)
+        self._warmed = key
+
+
+# kernels of one iteration on one GPU, counted in profiles/ (scaffold, predictor stream, 2 medians, residual, accumulation
+# + scatter, priors, solve (3), update + small element-wise ones)
+LAUNCHES_PER_ITERATION = 36
+
+
+def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return_debug=False, comm=None):
+    """One BA Gauss-Newton iteration; mutates `s` like Mapping.iterate.  `comm` (a ShardComm) shards the window over
+    the ranks of a process group; the legacy hooks `hist_allreduce(t)` / `allreduce(H, g, err)` with rank/world do the
+    same for the pair blocks only (store_vars replicated)."""
+    if comm is not None:
+        rank, world = comm.rank, comm.world
+        allreduce, hist_allreduce = comm.allreduce_system, comm.allreduce_hist
     dev = _lib.require_cuda(s.kf_poses, s.Knm_Kmminv, s.P_m, s.kf_img_and_grads)
     for name in ("kf_poses", "kf_aff_params", "P_m", "Knm_Kmminv", "kf_img_and_grads", "L_mm", "pm_first_obs",
                  "median_depths"):
@@ -294,13 +359,21 @@ def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return
             ev = torch.cuda.Event()
             ev.record(main)
             side.wait_event(ev)
+        k0, k1 = (0, K) if comm is None else comm.kf_range(K)
+        if comm is not None:
+            comm.warm(8 * (K + R) + 3 * L, pp.nbatch, K)
+            med_new.zero_()
+            depth[:k0].zero_()
+            depth[k1:].zero_()
         with torch.cuda.stream(side):
             sstream = _lib.stream_ptr(dev)
-            st = _lib.predictor_apply(_lib.ptr(s.Knm_Kmminv), _lib.ptr(scaf), K, H * W, M, _lib.ptr(depth), sstream)
-            _lib.check(st, "como_b200_predictor_apply")
-            st = _lib.median_f64(_lib.ptr(depth), _lib.ptr(seg), K, H * W, 1.0, _lib.ptr(med_new), None, _lib.ptr(mws),
-                                 mws.numel(), sstream)
-            _lib.check(st, "como_b200_median_f64")
+            if k1 > k0:
+                st = _lib.predictor_apply(_lib.ptr(s.Knm_Kmminv[k0:]), _lib.ptr(scaf[k0:]), k1 - k0, H * W, M,
+                                          _lib.ptr(depth[k0:]), sstream)
+                _lib.check(st, "como_b200_predictor_apply")
+                st = _lib.median_f64(_lib.ptr(depth[k0:]), _lib.ptr(seg), k1 - k0, H * W, 1.0, _lib.ptr(med_new[k0:]), None,
+                                     _lib.ptr(mws), mws.numel(), sstream)
+                _lib.check(st, "como_b200_median_f64")
         if side is not main:
             depth.record_stream(side)
             med_new.record_stream(side)
@@ -363,6 +436,8 @@ def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return
                        pairs=pp.pairs_full, vals_n=kp.vals_n.clone())
         if side is not main:
             main.wait_event(store_done)
+        if comm is not None:
+            comm.allreduce_small(med_new)   # every rank's vector is zero off its own keyframe range: the sum is exact
         sg = cfg["sigmas"]
         sig4 = (C.c_double * 4)(1e-2, float(sg["pose_prior"]), float(sg["scale_prior"]), float(sg["mean_depth_prior"]))
         full = bool(s.window_full)
@@ -392,6 +467,37 @@ def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return
         dbg.update(H=Hm.clone(), g=g.clone(), delta=delta.clone(), err=err.clone())
         return dbg
     return getattr(s, "converged", False)
+
+
+def kernel_launchers(s, cfg, dev):
+    """Closures that launch ONE kernel of the iteration each on the buffers of the last single-GPU iterate() call
+    (bench.py times them in isolation for its roofline blocks; ncu captures use them too)."""
+    kp, pp = get_plans(s, cfg, dev, 0, 1)
+    cache = s.__dict__["_b200_cache"]
+    K, M, N, H, W, R = kp.K, kp.M, kp.N, kp.H, kp.W, pp.R
+    scaf = cache["scaf"]
+    intr4 = _host_scalars(cache, "intr4", s.intrinsics, lambda Kh: (Kh[0, 0, 0], Kh[0, 1, 1], Kh[0, 0, 2], Kh[0, 1, 2]), 4)
+    depth = torch.empty(K, 1, H, W, dtype=F64, device=dev)
+    rec_poses = s.recent_poses if R > 0 else None
+    rec_aff = s.recent_aff_params if R > 0 else None
+    rec_img = s.recent_img_and_grads if R > 0 else None
+
+    def predictor_stream():
+        _lib.check(_lib.predictor_apply(_lib.ptr(s.Knm_Kmminv), _lib.ptr(scaf), K, H * W, M, _lib.ptr(depth),
+                                        _lib.stream_ptr(dev)), "como_b200_predictor_apply")
+
+    def ba_residual():
+        _lib.check(_lib.ba_photo_residual(
+            _lib.ptr(s.kf_poses), _lib.ptr(s.kf_aff_params), _lib.ptr(rec_poses), _lib.ptr(rec_aff),
+            _lib.ptr(s.kf_img_and_grads), _lib.ptr(rec_img), _lib.ptr(s.Knm_Kmminv), _lib.ptr(kp.coords),
+            _lib.ptr(kp.vals_n), _lib.ptr(scaf), _lib.ptr(pp.pair_tgt), _lib.ptr(pp.ref_ptr), _lib.ptr(pp.ref_pairs),
+            K, R, M, N, H, W, pp.P, intr4, _lib.ptr(pp.frames), _lib.ptr(pp.refbuf), _lib.ptr(pp.rbuf),
+            _lib.ptr(pp.pairbuf), _lib.stream_ptr(dev)), "como_b200_ba_photo_residual")
+
+    def solve():
+        return solve_system(cache["H"], cache["g"])
+
+    return {"predictor_stream": predictor_stream, "ba_residual": ba_residual, "solve": solve}
 
 
 def get_img_and_grads(rgb):

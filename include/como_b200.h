@@ -270,6 +270,12 @@ int como_b200_sample_depth_gradmag(const double* z_img, int32_t H, int32_t W, co
  * gray pyramid.  levels: HOST array of num_levels DEVICE pointers, coarsest first (reference order). */
 int como_b200_gray_pyramid(const float* rgb, int32_t H, int32_t W, int32_t num_levels, float* const* levels,
                            void* stream);
+/* Fused front-end: Tracking.prep_tracking_img + get_img_gradients (como/odom/Tracking.py:88-102;
+ * utils/image_processing.py:8-87) in ONE launch: rgb (3,H,W) -> gray -> every pyramid level (-> Scharr/32 gradients
+ * of every level when gx/gy are given).  levels / gx / gy: HOST arrays of num_levels DEVICE pointers, coarsest
+ * first; gx = gy = NULL skips the gradients.  num_levels <= 4 (deeper pyramids: gray_pyramid + image_gradients). */
+int como_b200_image_pyramid_fused(const float* rgb, int32_t H, int32_t W, int32_t num_levels, float* const* levels,
+                                  float* const* gx, float* const* gy, void* stream);
 /* ImageGradientModule (utils/image_processing.py:8-44): Scharr/32, reflect padding. */
 int como_b200_image_gradients(const float* img, int32_t h, int32_t w, float* gx, float* gy, void* stream);
 

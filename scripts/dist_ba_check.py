@@ -28,21 +28,17 @@ def main():
             setattr(s_single, k, v.clone())
     s_single.__dict__.pop("_b200_cache", None)
 
-    def allreduce(Hm, g, err):
-        dist.all_reduce(Hm)
-        dist.all_reduce(g)
-        dist.all_reduce(err)
-
+    comm = MC.ShardComm(world, rank, dev)
     ok = True
     for it in range(3):
         d1 = MC.iterate(s_single, cfg, return_debug=True)
-        d2 = MC.iterate(s, cfg, allreduce=allreduce, hist_allreduce=lambda t: dist.all_reduce(t), rank=rank, world=world,
-                        return_debug=True)
+        d2 = MC.iterate(s, cfg, comm=comm, return_debug=True)
         rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
         res = dict(sigma=rel(d2["sigma"], d1["sigma"]), H=rel(d2["H"], d1["H"]), g=rel(d2["g"], d1["g"]),
                    delta=rel(d2["delta"], d1["delta"]), poses=rel(s.kf_poses, s_single.kf_poses),
-                   P_m=rel(s.P_m, s_single.P_m), err=abs(float(d2["err"].sum() - d1["err"].sum())) / float(d1["err"].sum()))
-        bad = res["sigma"] > 1e-9 or res["H"] > 1e-9 or res["g"] > 1e-8 or res["poses"] > 1e-6 or res["P_m"] > 1e-6
+                   P_m=rel(s.P_m, s_single.P_m), med=rel(s.median_depths, s_single.median_depths), err=abs(float(d2["err"].sum() - d1["err"].sum())) / float(d1["err"].sum()))
+        bad = (res["sigma"] > 1e-9 or res["H"] > 1e-9 or res["g"] > 1e-8 or res["poses"] > 1e-6 or res["P_m"] > 1e-6
+               or res["med"] > 0.0)
         ok = ok and not bad
         if rank == 0:
             print(f"iter {it}: " + " ".join(f"{k}={v:.2e}" for k, v in res.items()), "BAD" if bad else "ok", flush=True)
