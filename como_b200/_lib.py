@@ -72,6 +72,9 @@ ba_photo_accum = _sig("como_b200_ba_photo_accum", C.c_int,
 median_num_passes = _sig("como_b200_median_num_passes", I32, [I32])
 median_pass_f64 = _sig("como_b200_median_pass_f64", C.c_int, [VP, VP, I32, I64, I32, VP, VP])
 median_finish_f64 = _sig("como_b200_median_finish_f64", C.c_int, [I32, VP, F64, VP, VP, VP])
+median_pack_words = _sig("como_b200_median_pack_words", I32, [])
+median_dist_compact_f64 = _sig("como_b200_median_dist_compact_f64", C.c_int, [VP, VP, I32, I64, VP, VP, VP])
+median_dist_finish_f64 = _sig("como_b200_median_dist_finish_f64", C.c_int, [VP, I32, I32, VP, F64, VP, VP, VP])
 ba_priors = _sig("como_b200_ba_priors", C.c_int,
                  [VP] * 15 + [I32, I32, C.POINTER(F64), F64, I32, I32, I32, I32, C.POINTER(F64), I32, VP, VP, VP, VP])
 ba_update = _sig("como_b200_ba_update", C.c_int, [VP, I32, I32, I32, VP, VP, VP, VP, VP, VP])
@@ -114,7 +117,8 @@ DECLARED_SYMBOLS = [
     "como_b200_subselect_pixels", "como_b200_ba_scaffold", "como_b200_predictor_apply", "como_b200_predictor_colsum",
     "como_b200_ba_frames_bytes", "como_b200_ba_partial_doubles", "como_b200_ba_unit_ints", "como_b200_ba_target_group",
     "como_b200_ba_photo_residual", "como_b200_ba_photo_accum", "como_b200_median_num_passes",
-    "como_b200_median_pass_f64", "como_b200_median_finish_f64",
+    "como_b200_median_pass_f64", "como_b200_median_finish_f64", "como_b200_median_pack_words",
+    "como_b200_median_dist_compact_f64", "como_b200_median_dist_finish_f64",
     "como_b200_ba_priors", "como_b200_ba_update", "como_b200_cross_covariance", "como_b200_chol_append",
     "como_b200_sampler_workspace_bytes", "como_b200_sampler_greedy", "como_b200_kmat_kmm", "como_b200_kmat_predictor",
     "como_b200_chol_solve_workspace_bytes", "como_b200_chol_solve",

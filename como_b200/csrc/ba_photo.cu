@@ -747,22 +747,16 @@ extern "C" int como_b200_ba_photo_accum(
   const BADims d = make_dims(K, R, L, M, N, Himg, Wimg, P, intr4);
   const BAFrame* frames = (const BAFrame*)frames_ws;
   sigma_expand_kernel<<<(P + 127) / 128, 128, 0, st>>>(sigma_batch, pair_batch, P, sigma_pair_ws);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(ba_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccumSmem));
-    attr_set = true;
-  }
+  // the attribute is per device: set on every call (cheap) rather than once per process
+  cudaFuncSetAttribute(ba_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AccumSmem));
   ba_accum_kernel<<<num_units, AC_THREADS, sizeof(AccumSmem), st>>>(Knm, coords, scaffold, frames, ref_ptr, ref_pairs, pair_tgt,
                                                                      sigma_pair_ws, (const BAUnit*)units, d, refbuf, rbuf,
                                                                      pairbuf, partial);
   int rc = check_launch("ba_accum");
   if (rc) return rc;
   const size_t smem = (size_t)(BA_MAXM * BA_MAXM + 9 * BA_MAXM) * sizeof(double);
-  static bool attr2 = false;
-  if (!attr2) {
-    cudaFuncSetAttribute(ba_scatter_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr2 = true;
-  }
+  // the attribute is per device: set on every call (cheap) rather than once per process
+  cudaFuncSetAttribute(ba_scatter_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ba_scatter_ref_kernel<<<K, 256, smem, st>>>(partial, unit_base, unit_slices, scaffold, dz_dP, lm_ids, d, dim, H, g);
   ba_scatter_pair_kernel<<<P, 256, 0, st>>>(partial, unit_base, unit_slices, pair_ref, pair_tgt, pair_slot, scaffold, dz_dP,
                                             lm_ids, d, dim, H, g, photo_err);

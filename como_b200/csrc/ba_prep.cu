@@ -322,11 +322,8 @@ extern "C" int como_b200_predictor_apply(const double* Knm, const double* scaffo
                                          double* depth, void* stream) {
   COMO_REQUIRE(Knm && scaffold && depth, "predictor_apply: null pointer argument");
   COMO_REQUIRE(K >= 1 && HW >= 1 && M >= 2 && M <= BA_MAXM && (M % 2) == 0, "predictor_apply: bad shape (M even, <= 64)");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(predictor_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PredStreamSmem));
-    attr_set = true;
-  }
+  // the attribute is per device: set on every call (cheap) rather than once per process
+  cudaFuncSetAttribute(predictor_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PredStreamSmem));
   const long long chunks_per_kf = (HW + PS_ROWS - 1) / PS_ROWS;
   long long grid = 2LL * sm_count();
   if (grid > chunks_per_kf * K) grid = chunks_per_kf * K;

@@ -571,11 +571,8 @@ extern "C" int como_b200_chol_solve(const double* H, const double* g, int32_t n,
   chol_copy_kernel<<<dim3(nb, nb), 256, 0, st>>>(v, H);
   chol_prep_kernel<<<64, 256, 0, st>>>(v, g, table);
   cudaMemsetAsync(xflags, 0, sizeof(int) * nb, st);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem));
-    attr = true;
-  }
+  // the attribute is per device: set on every call (cheap) rather than once per process
+  cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem));
   int grid = sm_count();
   if (grid > ntiles) grid = ntiles;
   // Both kernels spin on flags written by other CTAs of the same grid: launched cooperatively so that the runtime

@@ -460,12 +460,9 @@ extern "C" int como_b200_kmat_kmm(const double* cov_img, int32_t B, int32_t H, i
 static int kmat_rows_launch(const double* cov_img, int B, int H, int W, const double* coords_m, const double* E_m,
                             const double* Kmm_inv, int M, double scale, const double* coords_n, const unsigned char* mask_n,
                             long long n, double* out, double* var_out, double* var_min, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(kmat_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KmatSmem));
-    cudaFuncSetAttribute(kmat_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KmatSmem));
-    attr = true;
-  }
+  // the attribute is per device: set on every call (cheap) rather than once per process
+  cudaFuncSetAttribute(kmat_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KmatSmem));
+  cudaFuncSetAttribute(kmat_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KmatSmem));
   const long long groups = (n + KW_ROWS - 1) / KW_ROWS;
   long long per = (2LL * sm_count() + B - 1) / B;
   const long long need = (groups + KWARPS - 1) / KWARPS;
@@ -515,11 +512,8 @@ extern "C" int como_b200_weighted_gram(const double* rows, const double* y, cons
   cudaMemsetAsync(h, 0, sizeof(double) * M, st);
   if (stats) cudaMemsetAsync(stats, 0, sizeof(double) * 2, st);
   if (n == 0) return COMO_B200_OK;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(weighted_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramSmem));
-    attr = true;
-  }
+  // the attribute is per device: set on every call (cheap) rather than once per process
+  cudaFuncSetAttribute(weighted_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramSmem));
   const long long groups = (n + GR_ROWS - 1) / GR_ROWS;
   long long grid = sm_count();
   const long long need = (groups + KWARPS - 1) / KWARPS;

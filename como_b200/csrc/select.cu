@@ -296,6 +296,130 @@ select_small_kernel(int num_segs, const SelSeg* __restrict__ info, const T* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Median of values spread over several ranks (a BA pair batch whose pairs are sharded over GPUs) with THREE
+// exchanges instead of six: digits 0 and 1 through all-reduced histograms (22 bits: sign, exponent, 10 mantissa
+// bits -- a 1/1024-octave bucket, normally a few hundred of 2 M values), then every rank compacts ITS candidates of
+// that bucket into a fixed-size pack, the packs are all-gathered, and every rank finishes the remaining digits on
+// the gathered candidates.  pack layout per (rank, segment): word 0 = local candidate count (u64), words
+// 1..SEL_CAP = candidate bit patterns.  A rank whose local count exceeds SEL_CAP sets the overflow flag of the
+// result (the caller then runs the six-pass path; e.g. thousands of bit-identical residuals).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS)
+dist_compact_kernel(const double* __restrict__ values, const long long* __restrict__ seg_off, int num_segs,
+                    const unsigned* __restrict__ hist, unsigned long long* __restrict__ pack) {
+  using K = KeyOf<double>::K;
+  __shared__ unsigned s_tmp[SEL_THREADS / 32 + 4];
+  const int seg = blockIdx.y, tid = threadIdx.x;
+  K prefix;
+  unsigned long long rank, total;
+  unsigned cand = 0;
+  resolve_prefix<double>(hist, num_segs, seg, 2, prefix, rank, total, s_tmp, &cand);
+  if (total == 0) return;
+  unsigned long long* my = pack + (size_t)seg * (SEL_CAP + 1);
+  const int hi_shift = digit_shift<double>(1);
+  const long long beg = seg_off[seg], end = seg_off[seg + 1];
+  for (long long i = beg + (long long)blockIdx.x * SEL_THREADS + tid; i < end; i += (long long)gridDim.x * SEL_THREADS) {
+    const double v = values[i];
+    if (v == v) {
+      const K key = KeyOf<double>::key(v);
+      if ((key >> hi_shift) == (prefix >> hi_shift)) {
+        const unsigned long long pos = atomicAdd(my, 1ull);
+        if (pos < (unsigned long long)SEL_CAP) my[1 + pos] = key;
+      }
+    }
+  }
+}
+
+// One CTA per segment; packs: (world, num_segs, SEL_CAP + 1) words.  The remaining digits run over the gathered
+// candidates straight from L2 (up to world * SEL_CAP of them).  flag[seg] = 1 if any rank overflowed its pack.
+__global__ void __launch_bounds__(SEL_THREADS)
+dist_finish_kernel(const unsigned long long* __restrict__ packs, int world, int num_segs, const unsigned* __restrict__ hist,
+                   double scale, double* __restrict__ out, int* __restrict__ flag) {
+  using K = KeyOf<double>::K;
+  __shared__ unsigned s_hist[SEL_BINS];
+  __shared__ unsigned s_tmp[SEL_THREADS / 32 + 4];
+  __shared__ unsigned s_warp[SEL_THREADS / 32];
+  __shared__ unsigned s_pick[2];
+  const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  K prefix;
+  unsigned long long rank64, total;
+  unsigned cand = 0;
+  resolve_prefix<double>(hist, num_segs, seg, 2, prefix, rank64, total, s_tmp, &cand);
+  if (total == 0) {
+    if (tid == 0) {
+      out[seg] = NAN;
+      flag[seg] = 0;
+    }
+    return;
+  }
+  bool overflow = false;
+  for (int r = 0; r < world; ++r)
+    overflow = overflow || (__ldcg(packs + ((size_t)r * num_segs + seg) * (SEL_CAP + 1)) > (unsigned long long)SEL_CAP);
+  if (overflow) {
+    if (tid == 0) {
+      out[seg] = NAN;
+      flag[seg] = 1;
+    }
+    return;
+  }
+  unsigned rank = (unsigned)rank64;
+  for (int d = 2; d < KeyOf<double>::PASSES; ++d) {
+    for (int b = tid; b < SEL_BINS; b += SEL_THREADS) s_hist[b] = 0;
+    __syncthreads();
+    const int sh = digit_shift<double>(d), nb = digit_bits<double>(d), hi = sh + nb;
+    const K dmask = (K)((1u << nb) - 1u);
+    for (int r = 0; r < world; ++r) {
+      const unsigned long long* pk = packs + ((size_t)r * num_segs + seg) * (SEL_CAP + 1);
+      const int n = (int)__ldcg(pk);
+      for (int i = tid; i < n; i += SEL_THREADS) {
+        const K key = __ldcg(pk + 1 + i);
+        if ((key >> hi) == (prefix >> hi)) atomicAdd(&s_hist[(unsigned)((key >> sh) & dmask)], 1u);
+      }
+    }
+    __syncthreads();
+    constexpr int PER = SEL_BINS / SEL_THREADS;
+    unsigned c[PER], local = 0;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      c[j] = s_hist[tid * PER + j];
+      local += c[j];
+    }
+    unsigned incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    unsigned base = 0;
+    for (int w = 0; w < wid; ++w) base += s_warp[w];
+    incl += base;
+    const unsigned excl = incl - local;
+    if (rank >= excl && rank < incl) {
+      unsigned run = excl;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        if (rank >= run && rank < run + c[j]) {
+          s_pick[0] = tid * PER + j;
+          s_pick[1] = rank - run;
+        }
+        run += c[j];
+      }
+    }
+    __syncthreads();
+    prefix = (K)(prefix | ((K)s_pick[0] << sh));
+    rank = s_pick[1];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    out[seg] = scale * KeyOf<double>::val(prefix);
+    flag[seg] = 0;
+  }
+}
+
 template <typename T>
 int median_launch(const T* values, const long long* seg_off, int num_segs, long long max_seg_len, T scale, T* out,
                   long long* count, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -371,6 +495,28 @@ extern "C" int como_b200_median_finish_f64(int32_t num_segments, const void* his
   select_finish_kernel<double><<<num_segments, SEL_THREADS, 0, (cudaStream_t)stream>>>(num_segments, (const unsigned*)hist, scale,
                                                                                       out, (long long*)count);
   return check_launch("median_finish");
+}
+
+extern "C" int32_t como_b200_median_pack_words(void) { return SEL_CAP + 1; }
+extern "C" int como_b200_median_dist_compact_f64(const double* values, const int64_t* seg_offsets, int32_t num_segments,
+                                                 int64_t max_segment_len, const void* hist, void* pack, void* stream) {
+  COMO_REQUIRE(values && seg_offsets && hist && pack && num_segments >= 1, "median_dist_compact_f64: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(pack, 0, (size_t)num_segments * (SEL_CAP + 1) * sizeof(unsigned long long), st);
+  long long chunks = (max_segment_len + (long long)SEL_THREADS * 8 - 1) / ((long long)SEL_THREADS * 8);
+  const long long cap = (long long)sm_count() * 8 / num_segments;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  dist_compact_kernel<<<dim3((unsigned)chunks, (unsigned)num_segments), SEL_THREADS, 0, st>>>(
+      values, (const long long*)seg_offsets, num_segments, (const unsigned*)hist, (unsigned long long*)pack);
+  return check_launch("median_dist_compact");
+}
+extern "C" int como_b200_median_dist_finish_f64(const void* packs, int32_t world, int32_t num_segments, const void* hist,
+                                                double scale, double* out, int32_t* overflow, void* stream) {
+  COMO_REQUIRE(packs && hist && out && overflow && world >= 1 && num_segments >= 1, "median_dist_finish_f64: bad arguments");
+  dist_finish_kernel<<<num_segments, SEL_THREADS, 0, (cudaStream_t)stream>>>((const unsigned long long*)packs, world, num_segments,
+                                                                            (const unsigned*)hist, scale, out, overflow);
+  return check_launch("median_dist_finish");
 }
 
 extern "C" size_t como_b200_median_workspace_bytes(int32_t num_segments, int32_t elem_bytes) {

@@ -314,11 +314,8 @@ extern "C" int como_b200_sfm_accumulate(const double* Knm, const double* rec, co
   cudaMemsetAsync(G, 0, sizeof(double) * M * M, st);
   cudaMemsetAsync(St7, 0, sizeof(double) * 7 * M, st);
   cudaMemsetAsync(small28, 0, sizeof(double) * 28, st);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(sfm_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SfmGramSmem));
-    attr = true;
-  }
+  // the attribute is per device: set on every call (cheap) rather than once per process
+  cudaFuncSetAttribute(sfm_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SfmGramSmem));
   long long grid = sm_count();
   const long long need = ((N + 31) / 32 + 7) / 8;
   if (grid > need) grid = need;

@@ -430,7 +430,8 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
 
       // ---- pass 1: warp, gather, residual, first histogram.  Four pixels per thread and tile, software pipelined
       // over two tiles: the 16 bilinear taps of tile t+1 are issued before the residuals of tile t are formed, so a
-      // warp always has a tile's worth of gathers in flight.
+      // warp always has a tile's worth of gathers in flight (3 CTAs per SM leave almost no L1: the taps are L2
+      // hits, ~1 us under load).
       constexpr int PB = T1 / CONS_THREADS;
       const float2 A2x = make_float2(2.0f / (float)w, 2.0f / (float)h), A1 = make_float2(1.0f / (float)w, 1.0f / (float)h);
       const float2 wh2 = make_float2((float)w, (float)h);
@@ -524,6 +525,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         }
       };
       {
+        // two tiles in flight per warp (a third one costs more in register spills than it hides: measured)
         P1 sa, sb;
         if (sl.len > 0) gather(0, sa);
         for (int t0 = 0; t0 < sl.len; t0 += 2 * T1) {

@@ -96,6 +96,15 @@ int como_b200_median_pass_f64(const double* values, const int64_t* seg_offsets, 
                               int64_t max_segment_len, int32_t digit, void* hist, void* stream);
 int como_b200_median_finish_f64(int32_t num_segments, const void* hist, double scale, double* out, int64_t* count,
                                 void* stream);
+/* Three-exchange variant for values spread over ranks: digits 0 and 1 by pass + all-reduce as above, then every rank
+ * compacts its candidates of the chosen 22-bit bucket into a pack of como_b200_median_pack_words() 8-byte words per
+ * segment (word 0 = count), the packs are all-gathered into (world, num_segments, words) and every rank finishes.
+ * overflow[s] = 1: some rank's candidates did not fit -- fall back to the six-pass scheme for this call. */
+int32_t como_b200_median_pack_words(void);
+int como_b200_median_dist_compact_f64(const double* values, const int64_t* seg_offsets, int32_t num_segments,
+                                      int64_t max_segment_len, const void* hist, void* pack, void* stream);
+int como_b200_median_dist_finish_f64(const void* packs, int32_t world, int32_t num_segments, const void* hist,
+                                     double scale, double* out, int32_t* overflow, void* stream);
 int como_b200_median_f32(const float* values, const int64_t* seg_offsets, int32_t num_segments,
                          int64_t max_segment_len, float scale, float* out, int64_t* count, void* workspace,
                          size_t workspace_bytes, void* stream);

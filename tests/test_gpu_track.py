@@ -63,10 +63,26 @@ def test_tracking_iter_same_inputs_vs_golden(golden_dir, name):
 
 def replay_check(levels, stats, T_final, aff_final, strict=True):
     """Every iteration the CUDA path ran, replayed by the oracle from the CUDA path's OWN iterate (stats[i, 8:26]):
-    both sides evaluate the same (T, aff) on the same operands, so the north-star bounds apply per iteration
-    and do not depend on how either side's fp32 summation order steers the trajectory."""
+    both sides evaluate the same (T, aff) on the same operands, so the bounds apply per iteration and do not depend
+    on how either side's fp32 summation order steers the trajectory.
+
+    Validity (1 <= x < w-1, 1 <= y < h-1) is a hard threshold on an fp32 projection.  When the pose is close to the
+    identity -- the first iteration of every level in these cases -- a whole border row/column of reference pixels
+    projects within an ulp of the threshold, and which side each lands on depends on the last bit (FMA contraction).
+    The oracle's per-pixel data gives an exact bound for that: B = the pixels within 4 ulp of a threshold
+    (|margin| <= 4 * 2^-23 * max(w, h)); their count bounds the difference in nvalid and in the median's rank, and the
+    sum of their individual contributions bounds the difference in every accumulated quantity.  On top of that:
+      sigma    2e-6 + 1e-5 sigma: sigma is an EXACT order statistic on both sides (test_exact_order_statistic_bitwise),
+               i.e. ONE pixel's |r|, and that residual carries the fp32 noise of its warped coordinate (~1 ulp of x
+               times the image gradient): up to ~2e-6 in intensity, it does not average out
+      norm     north star, residual norms 1e-4 relative: the un-normalised robust norm sqrt(sum w r^2 / n)
+               = sigma sqrt(mean_sq_err), + 3e-7 (2.5 ulp(1): the norm is only ~2e-3 at a converged coarse level)
+      mse      the sigma^2-normalised value the reference reports: the same plus twice sigma's relative bound
+      |g|      what is left of sum w J r after cancellation (3 of ~1e3 near convergence): 5e-3 of itself
+      update   north star, SE(3) log 1e-3: asserted 1e-4 on (next iterate vs oracle update); affine 1e-4."""
     st = stats.cpu().numpy()
     masked = {}
+    rows, bad = [], []
     for i in range(st.shape[0]):
         l = int(st[i, 0])
         if l not in masked:
@@ -76,28 +92,34 @@ def replay_check(levels, stats, T_final, aff_final, strict=True):
         vals, P, J, K, img = masked[l]
         T_in = torch.from_numpy(st[i, 8:24].reshape(4, 4).copy())
         aff_in = torch.from_numpy(st[i, 24:26].copy())
-        Tn, affn, delta, mse, gn, H, g, sigma, nvalid = TO.tracking_iter(T_in, aff_in, vals, P, J, K, img)
-        # a projection within 1 ulp of the [1, w-1) border may land on either side
-        assert abs(st[i, 5] - nvalid) <= 2, (i, st[i, 5], nvalid)
+        d = {}
+        Tn, affn, delta, mse, gn, H, g, sigma, nvalid = TO.tracking_iter(T_in, aff_in, vals, P, J, K, img, detail=d)
+        # ---- pixels whose validity hangs on the last bits of the projection
+        wd, hd = d["w"], d["h"]
+        margin = torch.minimum(torch.minimum((d["x"] - 1).abs(), (d["x"] - (wd - 1)).abs()),
+                               torch.minimum((d["y"] - 1).abs(), (d["y"] - (hd - 1)).abs()))
+        near = (margin <= 4 * 2.0 ** -23 * max(wd, hd)) & (d["z"] > 0)
+        nb = int(near.sum())
+        rb = d["r"][near].abs().double()
+        contrib = torch.minimum(rb * rb, 1.345 * sigma * rb)                      # w r^2 of each such pixel
+        flip_sum = float(contrib.sum()) / max(nvalid, 1)                           # effect on mean(w r^2)
+        flip_g = float((torch.minimum(rb, torch.full_like(rb, 1.345 * sigma)) * d["Jf"][near].double().norm(dim=1)).sum())
         q = 2.0 / max(nvalid, 1) if not strict else 0.0   # median rank quantisation, only matters at toy sizes
-        # sigma is an EXACT order statistic on both sides (test_exact_order_statistic_bitwise), i.e. ONE pixel's |r|,
-        # and that pixel's residual carries the fp32 noise of its warped coordinate: ~2 ulp of x (1e-5 .. 1e-4 px)
-        # times the image gradient, up to ~2e-6 in intensity at the coarse levels -- it does not average out.
-        tol_s = 2e-6 + (1e-5 + q) * sigma
-        assert abs(st[i, 4] - sigma) <= tol_s, (i, st[i, 4], sigma)
-        # north star: residual NORM within 1e-4 relative.  mean_sq_err is normalised by sigma^2, so compare the
-        # un-normalised robust norm sigma * sqrt(mean_sq_err) = sqrt(sum w r^2 / n) (+ 2.5 ulp(1) of intensity rounding:
-        # at a converged coarse level the norm itself is only ~2e-3) ...
-        norm_g, norm_o = st[i, 4] * np.sqrt(st[i, 1]), sigma * np.sqrt(mse)
-        assert abs(norm_g - norm_o) <= (1e-4 + q) * norm_o + 3e-7, (i, norm_g, norm_o)
-        # ... and the normalised value within what sigma's single-pixel noise allows
-        assert abs(st[i, 1] - mse) <= (1e-4 + 2 * q + 2.5 * tol_s / sigma) * mse, (i, st[i, 1], mse)
-        # |g| is what is left of sum w J r after cancellation (3 of ~1e3 near convergence): 5e-3 of itself
-        assert abs(st[i, 2] - gn) <= 5e-3 * max(gn, 1.0), (i, st[i, 2], gn)
+        dn = abs(st[i, 5] - nvalid)
+        tol_s = 2e-6 + (1e-5 + q + 2.0 * nb / max(nvalid, 1)) * sigma
+        norm_g, norm_o = float(st[i, 4]) * np.sqrt(float(st[i, 1])), sigma * np.sqrt(mse)
+        tol_n = (1e-4 + q) * norm_o + 3e-7 + flip_sum / (2 * norm_o)
         T_next = st[i + 1, 8:24].reshape(4, 4) if i + 1 < st.shape[0] else T_final
         a_next = st[i + 1, 24:26] if i + 1 < st.shape[0] else aff_final
-        assert se3_log_err(T_next, Tn.numpy()) < 1e-4, (i, se3_log_err(T_next, Tn.numpy()))  # SE(3) log: 1e-3 asked
-        np.testing.assert_allclose(a_next, affn.numpy(), atol=1e-4)
+        chk = dict(nvalid=(dn, max(nb, 2 if not strict else 0)), sigma=(abs(st[i, 4] - sigma), tol_s),
+                   norm=(abs(norm_g - norm_o), tol_n),
+                   mse=(abs(st[i, 1] - mse), (2 * tol_n / norm_o + 2 * tol_s / sigma) * mse),
+                   gnorm=(abs(st[i, 2] - gn), 5e-3 * max(gn, 1.0) + flip_g), se3=(se3_log_err(T_next, Tn.numpy()), 1e-4),
+                   aff=(float(np.abs(a_next - affn.numpy()).max()), 1e-4))
+        rows.append(f"it {i} L{l} n={nvalid} border={nb} sigma={sigma:.6g} " +
+                    " ".join(f"{k}={v[0]:.3g}/{v[1]:.3g}" for k, v in chk.items()))
+        bad += [(i, k) for k, v in chk.items() if not v[0] <= v[1]]
+    assert not bad, f"out of bounds {bad}:\n" + "\n".join(rows)
     return st
 
 
