@@ -438,6 +438,92 @@ def cpu_ba_baseline(s_and_snap, cfg, budget_s=25.0, min_iters=5):
             "sample": f"{n} iterations of the same window after 1 warm-up ({dt:.1f} s)"}
 
 
+def torch_cuda_reference_ops(K, R, M, N, H, W, P, dim, device, reps=3):
+    """LOWER BOUND on one Mapping.iterate of the reference's PyTorch-CUDA path: the reference cannot run here (lietorch
+    is not vendored, como_backends builds for sm_86 only), but its dominant tensor operations can -- stock torch CUDA
+    ops (cuBLAS, cuSOLVER, ATen) at the reference's own shapes and dtypes (float64), on random data:
+      store_vars            exp(Knm_Kmminv (K,H,W,M) @ logz_m) + per-keyframe median            Mapping.py:749-758
+      setup_test_points     gather (K,N,M) predictor rows, materialise dPwn_dzm (K,N,3,M,1)       sparse_map.py:184-230
+      create_photo_system   per-pair gathers: dPwn_dzm[ref] (P,N,3,M,1), images[target] (P,3,H,W) photo.py:262-347
+      batch_photo_cost      grid_sample, global median, dIt_dzm = dIt_dPwn @ dPwn_dzm, the Gram
+                            einsum (P,N,M)->(P,M,M), M->3M expansion, scatter_add into H         photo.py:83-233
+      solve_system          cholesky_ex + cholesky_solve at dim                                   linear_system.py:101-112
+    Everything else the reference does (projection Jacobians, priors, pose blocks, robust weights ...) is left out, so
+    the real reference is slower than this sum."""
+    f64 = torch.float64
+    g = torch.Generator(device=device).manual_seed(0)
+    rnd = lambda *sh: torch.rand(*sh, dtype=f64, device=device, generator=g)
+    Knm = rnd(K, H, W, M)
+    logzm = rnd(K, 1, M, 1)
+    rows = torch.randint(0, H, (K, N), device=device, generator=g)
+    cols = torch.randint(0, W, (K, N), device=device, generator=g)
+    kidx = torch.arange(K, device=device)[:, None].expand(K, N)
+    ref_ids = torch.randint(0, K, (P,), device=device, generator=g)
+    tgt_ids = torch.randint(0, K, (P,), device=device, generator=g)
+    imgs = rnd(K, 3, H, W)
+    ray = rnd(K, N, 3, 1, 1)
+    dIt_dPwn = rnd(P, N, 1, 3)
+    grid = rnd(P, N, 1, 2) * 2 - 1
+    Hm = torch.zeros(dim * dim, dtype=f64, device=device)
+    idx = torch.randint(0, dim * dim, (P, 3 * M * 3 * M), device=device, generator=g)
+    A = rnd(dim, dim)
+    Hspd = A @ A.T + dim * torch.eye(dim, dtype=f64, device=device)
+    gvec = rnd(dim, 1)
+    dz = rnd(P, 3)
+    out = {}
+
+    def timed(name, fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / reps
+        return r
+
+    def store_vars():
+        depth = torch.exp(Knm @ logzm)
+        return torch.median(depth.view(K, -1), dim=1).values
+
+    def test_points():
+        Kt = Knm[kidx, rows, cols, :]                                   # (K,N,M)
+        return (ray * Kt[:, :, None, :, None]).contiguous()            # dPwn_dzm (K,N,3,M,1)
+
+    timed("store_vars", store_vars)
+    dPwn_dzm = timed("setup_test_points", test_points)
+
+    def gathers():
+        return dPwn_dzm[ref_ids], imgs[tgt_ids]
+
+    dP_b, img_b = timed("create_photo_system_gathers", gathers)
+
+    def photo():
+        v = torch.nn.functional.grid_sample(img_b, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+        med = torch.median(v[:, 0].abs().reshape(-1))
+        Jz = dIt_dPwn @ dP_b.view(P, N, 3, M)                          # (P,N,1,M)
+        Hz = torch.einsum("bnck,bncl->bkl", Jz, Jz)                    # (P,M,M)
+        HP = (dz[:, None, :, None, None] * Hz[:, :, None, :, None] * dz[:, None, None, None, :]).reshape(P, -1)
+        Hm.scatter_add_(0, idx.reshape(-1), HP.reshape(-1))
+        return med
+
+    timed("batch_photo_cost", photo)
+    del dP_b, img_b, dPwn_dzm
+
+    def solve():
+        Lc, _ = torch.linalg.cholesky_ex(Hspd, upper=False, check_errors=False)
+        return torch.cholesky_solve(gvec, Lc, upper=False)
+
+    timed("solve_system", solve)
+    total = sum(out.values())
+    return {"value": 1e3 / total, "unit": "GN-it/s", "ms_per_step": total, "kind": "torch-cuda-lower-bound",
+            "ops_ms": {k: round(v, 3) for k, v in out.items()},
+            "sample": "dominant tensor ops of the reference's Mapping.iterate at its own shapes (float64), stock torch "
+                      "CUDA; a lower bound on the reference's PyTorch-CUDA time per iteration"}
+
+
 def torch_cuda_ba_baseline(s, cfg, device, iters=5):
     """The oracle port with its tensors on the GPU: stock ATen / cuBLAS / cuSOLVER ops, no como_b200 kernel.  Stated
     proxy for the reference's PyTorch-CUDA path (the reference cannot run here: lietorch is not vendored and its
@@ -755,11 +841,16 @@ def main():
         if args.workload == "all" and not args.no_e2e:
             sec = {}
             if world == 1:
-                sec["torch_cuda_port"] = guarded("torch_cuda_port", lambda: torch_cuda_ba_baseline(s[0], cfg, device))
+                sec["torch_cuda_port"] = guarded("torch_cuda_port", lambda: torch_cuda_ba_baseline(s[0], cfg, device, iters=2))
             if rank == 0:
                 res["cpu_baseline"] = guarded("cpu_baseline", lambda: cpu_ba_baseline(s, cfg)) if world == 1 else None
+            win = res["window"]
             del s
             torch.cuda.empty_cache()
+            if world == 1:
+                sec["torch_cuda_reference_ops"] = guarded("torch_cuda_reference_ops", lambda: torch_cuda_reference_ops(
+                    args.kf, args.oneway, 64, 19200, 480, 640, win["pairs_on_this_rank"], win["system_dim"], device))
+                torch.cuda.empty_cache()
             barrier(world)
             if world > 1 and not args.shard:
                 sec["ba_shard"] = guarded("ba_shard", lambda: run_ba_ours(args, rank, world, device, shard=True, extras=False)[0])

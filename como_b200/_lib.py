@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcomo_b200.so")
+LIB_PATH = os.environ.get("COMO_B200_LIB") or os.path.join(_HERE, "libcomo_b200.so")   # override: tuning builds only
 MAX_LEVELS = 8
 TRACK_STAT_STRIDE = 32
 
@@ -31,6 +31,15 @@ class TrackLevel(C.Structure):
 
 class TrackTerm(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("delta_norm", C.c_float), ("rel_tol", C.c_float), ("grad_norm", C.c_float)]
+
+
+class PackItem(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst_offset_bytes", C.c_int64), ("count", C.c_int64), ("src_dtype", C.c_int32),
+                ("dst_dtype", C.c_int32)]
+
+
+PACK_MAX_ITEMS = 8
+PACK_DTYPES = {torch.float32: 0, torch.float64: 1, torch.uint8: 2, torch.bool: 2, torch.int32: 3, torch.int64: 4}
 
 
 def _sig(name, restype, argtypes):
@@ -100,6 +109,7 @@ reproject_dense = _sig("como_b200_reproject_dense", C.c_int,
                        [VP, I32, I32, C.POINTER(F64), C.POINTER(F64), F64, VP, VP, VP, VP, VP])
 sample_depth_gradmag = _sig("como_b200_sample_depth_gradmag", C.c_int, [VP, I32, I32, VP, VP, I32, VP, VP, VP])
 
+handoff_pack = _sig("como_b200_handoff_pack", C.c_int, [C.POINTER(PackItem), C.c_int32, C.c_void_p, C.c_void_p])
 gray_pyramid = _sig("como_b200_gray_pyramid", C.c_int, [VP, I32, I32, I32, C.POINTER(C.c_void_p), VP])
 image_pyramid_fused = _sig("como_b200_image_pyramid_fused", C.c_int,
                            [VP, I32, I32, I32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), VP])
@@ -124,7 +134,7 @@ DECLARED_SYMBOLS = [
     "como_b200_chol_solve_workspace_bytes", "como_b200_chol_solve",
     "como_b200_kmat_rows", "como_b200_weighted_gram", "como_b200_rows_residual",
     "como_b200_reproject_dense", "como_b200_sample_depth_gradmag", "como_b200_sfm_linearize", "como_b200_sfm_accumulate",
-    "como_b200_gray_pyramid", "como_b200_image_pyramid_fused", "como_b200_image_gradients", "como_b200_img_and_grads_f64", "como_b200_kf_reference_level", "como_b200_reproj_depth",
+    "como_b200_handoff_pack", "como_b200_gray_pyramid", "como_b200_image_pyramid_fused", "como_b200_image_gradients", "como_b200_img_and_grads_f64", "como_b200_kf_reference_level", "como_b200_reproj_depth",
 ]
 
 

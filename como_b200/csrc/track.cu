@@ -32,16 +32,25 @@
 
 namespace como {
 
-constexpr int CONS_WARPS = 4;
+#ifndef TRK_CONS_WARPS
+#define TRK_CONS_WARPS 4
+#endif
+#ifndef TRK_MAX_OCC
+#define TRK_MAX_OCC 3
+#endif
+#ifndef TRK_STAGES
+#define TRK_STAGES 3
+#endif
+constexpr int CONS_WARPS = TRK_CONS_WARPS;
 constexpr int CONS_THREADS = CONS_WARPS * 32;
 constexpr int TRK_THREADS = CONS_THREADS + 32;  // + producer warp
-constexpr int MAX_OCC = 3;                      // CTAs per SM the launch bounds allow
+constexpr int MAX_OCC = TRK_MAX_OCC;             // CTAs per SM the launch bounds allow
 constexpr int T1 = 512;                         // pixels per pass-1 stage (4 per consumer thread)
 constexpr int T2 = 512;                         // pixels per pass-2 stage (4 per consumer thread)
 constexpr int STAGE_BYTES = 20480;              // max(T1*(12+4+1), T2*(32+4+4))
 constexpr int T1_VALS_OFF = T1 * 12, T1_MASK_OFF = T1 * 16;
 constexpr int T2_VALS_OFF = T2 * 32, T2_R_OFF = T2 * 36;
-constexpr int STAGES = 3;
+constexpr int STAGES = TRK_STAGES;
 constexpr int CHUNK_ALIGN = 512;  // slice = whole tiles (only the last slice of a level is ragged); 16-byte aligned starts
 constexpr int NACC = 45;          // 36 (upper triangle of 8x8) + 8 (gradient) + 1 (robust error)
 constexpr int NACC_PAD = 48;

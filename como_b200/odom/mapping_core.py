@@ -265,6 +265,11 @@ class ShardComm:
 
         self.dist, self.world, self.rank, self.device, self.group = dist, int(world), int(rank), device, group
         self._warmed = None
+        # "six": six summed digit histograms, no host read (default).  "three": two histograms + one all-gather of
+        # candidate packs, but one flag read at the end of every iteration -- measured slower at N = 2 (2.53 vs 2.41 ms
+        # per iteration: the host loses its run-ahead), kept for interconnects where small all-reduces cost more.
+        self.fast_median = os.environ.get("COMO_B200_SHARD_MEDIAN", "six") == "three"
+        self.overflow = None
 
     def kf_range(self, K):
         per = (K + self.world - 1) // self.world
@@ -281,6 +286,9 @@ class ShardComm:
     def allreduce_small(self, t):
         self.dist.all_reduce(t, group=self.group)
 
+    def allgather(self, out, mine):
+        self.dist.all_gather_into_tensor(out, mine, group=self.group)
+
     def warm(self, dim, nbatch, K):
         key = (dim, nbatch, K)
         if self._warmed == key:
@@ -290,6 +298,9 @@ class ShardComm:
                                   torch.zeros(dim, dtype=F64, device=self.device), torch.zeros(8, dtype=F64, device=self.device))
             self.allreduce_hist(torch.zeros(nbatch, 2048, dtype=torch.int32, device=self.device))
             self.allreduce_small(torch.zeros(K, dtype=F64, device=self.device))
+            words = int(_lib.median_pack_words())
+            self.allgather(torch.zeros(self.world, nbatch, words, dtype=torch.int64, device=self.device),
+                           torch.zeros(nbatch, words, dtype=torch.int64, device=self.device))
         torch.cuda.synchronize(self.device)
         self._warmed = key
 
@@ -299,10 +310,35 @@ class ShardComm:
 LAUNCHES_PER_ITERATION = 36
 
 
+_IN_PLACE_STATE = ("kf_poses", "kf_aff_params", "recent_poses", "recent_aff_params", "P_m")
+_REBOUND_STATE = ("median_depths", "depth_imgs", "pm", "logzm", "total_err_prev", "iter")
+
+
 def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return_debug=False, comm=None):
     """One BA Gauss-Newton iteration; mutates `s` like Mapping.iterate.  `comm` (a ShardComm) shards the window over
     the ranks of a process group; the legacy hooks `hist_allreduce(t)` / `allreduce(H, g, err)` with rank/world do the
-    same for the pair blocks only (store_vars replicated)."""
+    same for the pair blocks only (store_vars replicated).
+
+    With a ShardComm the global robust scale normally takes three exchanges (two digit histograms + one all-gather of
+    candidate packs).  Should a rank's candidates not fit its pack (thousands of bit-identical residuals), the flag is
+    read once at the end of the iteration, the state is restored and the iteration redone with the six-pass scheme."""
+    if comm is None or not comm.fast_median:
+        return _iterate(s, cfg, allreduce, hist_allreduce, rank, world, return_debug, comm)
+    stash = {n: getattr(s, n).clone() for n in _IN_PLACE_STATE if isinstance(getattr(s, n, None), torch.Tensor)}
+    stash.update({n: getattr(s, n) for n in _REBOUND_STATE if hasattr(s, n)})
+    out = _iterate(s, cfg, allreduce, hist_allreduce, rank, world, return_debug, comm)
+    if int(comm.overflow.max()) != 0:
+        for n, v in stash.items():
+            if n in _IN_PLACE_STATE:
+                getattr(s, n).copy_(v)
+            else:
+                setattr(s, n, v)
+        comm.fast_median = False
+        out = _iterate(s, cfg, allreduce, hist_allreduce, rank, world, return_debug, comm)
+    return out
+
+
+def _iterate(s, cfg, allreduce, hist_allreduce, rank, world, return_debug, comm):
     if comm is not None:
         rank, world = comm.rank, comm.world
         allreduce, hist_allreduce = comm.allreduce_system, comm.allreduce_hist
@@ -408,6 +444,26 @@ def iterate(s, cfg, allreduce=None, hist_allreduce=None, rank=0, world=1, return
                 st = _lib.median_f64(_lib.ptr(pp.rbuf), _lib.ptr(pp.seg_off), pp.nbatch, pp.max_seg, 1.4826, _lib.ptr(sig),
                                      None, _lib.ptr(rws), rws.numel(), stream)
                 _lib.check(st, "como_b200_median_f64")
+        elif comm is not None and comm.fast_median:
+            # sharded pairs, three exchanges: digits 0 and 1 through summed histograms, then the candidates of the
+            # chosen bucket are compacted per rank, all-gathered, and every rank finishes the selection
+            pp.hist.zero_()
+            for dgt in range(2):
+                st = _lib.median_pass_f64(_lib.ptr(pp.rbuf), _lib.ptr(pp.seg_off), pp.nbatch, pp.max_seg, dgt,
+                                          _lib.ptr(pp.hist), stream)
+                _lib.check(st, "como_b200_median_pass_f64")
+                comm.allreduce_hist(pp.hist[dgt])
+            words = int(_lib.median_pack_words())
+            pack = _buf(cache, "med_pack", (pp.nbatch, words), torch.int64, dev)
+            packs = _buf(cache, "med_packs", (world, pp.nbatch, words), torch.int64, dev)
+            st = _lib.median_dist_compact_f64(_lib.ptr(pp.rbuf), _lib.ptr(pp.seg_off), pp.nbatch, pp.max_seg, _lib.ptr(pp.hist),
+                                              _lib.ptr(pack), stream)
+            _lib.check(st, "como_b200_median_dist_compact_f64")
+            comm.allgather(packs, pack)
+            comm.overflow = _buf(cache, "med_overflow", (pp.nbatch,), torch.int32, dev)
+            st = _lib.median_dist_finish_f64(_lib.ptr(packs), world, pp.nbatch, _lib.ptr(pp.hist), 1.4826, _lib.ptr(sig),
+                                             _lib.ptr(comm.overflow), stream)
+            _lib.check(st, "como_b200_median_dist_finish_f64")
         else:
             # sharded pairs: the digit histograms are summed across ranks between the radix passes
             pp.hist.zero_()

@@ -304,6 +304,28 @@ int como_b200_kf_reference_level(const float* img, const float* gx, const float*
 int como_b200_reproj_depth(const float* P, int32_t n, const float* T_dev, const float* K9, int32_t h, int32_t w,
                            int32_t* winner_ws, float* depth_img, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Inter-process hand-off: replaces the per-message tensor shipping of TupleTensorQueue.push
+ * (como/utils/multiprocessing.py:16-21,45-51: every tensor .to(device, dtype), then pickled through mp.Queue, i.e. a
+ * fresh CUDA IPC handle per tensor per message).  One launch packs all tensors of a message into a persistent
+ * device slot, converting to the consumer's dtype on the way; the slot ring is shared with the consumer process once.
+ * ------------------------------------------------------------------------------------------ */
+#define COMO_B200_DT_F32 0
+#define COMO_B200_DT_F64 1
+#define COMO_B200_DT_U8 2
+#define COMO_B200_DT_I32 3
+#define COMO_B200_DT_I64 4
+#define COMO_B200_PACK_MAX_ITEMS 8
+typedef struct {
+  const void* src;           /* DEVICE pointer, contiguous, same device as the slot */
+  int64_t dst_offset_bytes;  /* multiple of 16 */
+  int64_t count;             /* elements */
+  int32_t src_dtype;         /* COMO_B200_DT_* */
+  int32_t dst_dtype;         /* COMO_B200_DT_F32 or COMO_B200_DT_F64 */
+} como_b200_pack_item_t;
+/* items: HOST array (passed by value to the kernel). */
+int como_b200_handoff_pack(const como_b200_pack_item_t* items, int32_t num_items, void* slot, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

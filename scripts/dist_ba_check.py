@@ -38,7 +38,7 @@ def main():
                    delta=rel(d2["delta"], d1["delta"]), poses=rel(s.kf_poses, s_single.kf_poses),
                    P_m=rel(s.P_m, s_single.P_m), med=rel(s.median_depths, s_single.median_depths), err=abs(float(d2["err"].sum() - d1["err"].sum())) / float(d1["err"].sum()))
         bad = (res["sigma"] > 1e-9 or res["H"] > 1e-9 or res["g"] > 1e-8 or res["poses"] > 1e-6 or res["P_m"] > 1e-6
-               or res["med"] > 0.0)
+               or res["med"] > 1e-9)
         ok = ok and not bad
         if rank == 0:
             print(f"iter {it}: " + " ".join(f"{k}={v:.2e}" for k, v in res.items()), "BAD" if bad else "ok", flush=True)

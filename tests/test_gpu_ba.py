@@ -194,6 +194,61 @@ def test_distributed_median_passes_match_fused_median():
         assert float(out1[i]) == ref and float(out2[i]) == ref
 
 
+def test_three_exchange_distributed_median_matches_torch():
+    """The sharded robust scale: two digit histograms (summed over ranks), per-rank candidate packs, all-gather, finish.
+    Two 'ranks' are emulated on one GPU (their histograms added, their packs stacked); the result must be the exact
+    order statistic of the union, empty ranks and empty segments included; bit-identical values that overflow a
+    pack raise the overflow flag (the caller then redoes the iteration with the six-pass scheme)."""
+    from como_b200 import _lib
+
+    torch.manual_seed(7)
+    words = int(_lib.median_pack_words())
+    lens = [[40000, 0, 9000], [25001, 0, 0]]                 # rank x segment; segment 1 is empty everywhere
+    vals = [[torch.rand(n, dtype=torch.float64) * 3e-2 for n in row] for row in lens]
+    vals[0][2][::4] = float("nan")
+    ns, world = 3, 2
+    hist = torch.zeros(2, ns, 2048, dtype=torch.int32, device="cuda")
+    flat, offs = [], []
+    for r in range(world):
+        flat.append(torch.cat(vals[r]).cuda() if sum(lens[r]) else torch.zeros(1, dtype=torch.float64, device="cuda"))
+        offs.append(torch.tensor(np.concatenate([[0], np.cumsum(lens[r])]), dtype=torch.int64).cuda())
+    for d in range(2):
+        parts = []
+        for r in range(world):                               # every rank sees the SUMMED histograms of earlier digits
+            h = hist.clone()
+            h[d].zero_()
+            _lib.check(_lib.median_pass_f64(_lib.ptr(flat[r]), _lib.ptr(offs[r]), ns, max(max(lens[r]), 1), d, _lib.ptr(h),
+                                            _lib.stream_ptr()), "pass")
+            parts.append(h[d].clone())
+        hist[d] = parts[0] + parts[1]
+    packs = torch.zeros(world, ns, words, dtype=torch.int64, device="cuda")
+    for r in range(world):
+        _lib.check(_lib.median_dist_compact_f64(_lib.ptr(flat[r]), _lib.ptr(offs[r]), ns, max(max(lens[r]), 1), _lib.ptr(hist),
+                                                _lib.ptr(packs[r]), _lib.stream_ptr()), "compact")
+    out = torch.empty(ns, dtype=torch.float64, device="cuda")
+    ovf = torch.empty(ns, dtype=torch.int32, device="cuda")
+    _lib.check(_lib.median_dist_finish_f64(_lib.ptr(packs), world, ns, _lib.ptr(hist), 1.4826, _lib.ptr(out), _lib.ptr(ovf),
+                                           _lib.stream_ptr()), "finish")
+    for sgm in range(ns):
+        u = torch.cat([vals[r][sgm] for r in range(world)])
+        u = u[~torch.isnan(u)]
+        if u.numel() == 0:
+            assert torch.isnan(out[sgm]) and int(ovf[sgm]) == 0
+        else:
+            assert float(out[sgm]) == 1.4826 * float(torch.median(u)) and int(ovf[sgm]) == 0
+    # overflow: one rank holds > pack-capacity values inside one 22-bit bucket
+    same = (0.5 + 1e-12 * torch.rand(words + 500, dtype=torch.float64)).cuda()
+    off1 = torch.tensor([0, same.numel()], dtype=torch.int64).cuda()
+    h1 = torch.zeros(2, 1, 2048, dtype=torch.int32, device="cuda")
+    for d in range(2):
+        _lib.check(_lib.median_pass_f64(_lib.ptr(same), _lib.ptr(off1), 1, same.numel(), d, _lib.ptr(h1), _lib.stream_ptr()), "pass")
+    pk = torch.zeros(1, 1, words, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.median_dist_compact_f64(_lib.ptr(same), _lib.ptr(off1), 1, same.numel(), _lib.ptr(h1), _lib.ptr(pk),
+                                            _lib.stream_ptr()), "compact")
+    _lib.check(_lib.median_dist_finish_f64(_lib.ptr(pk), 1, 1, _lib.ptr(h1), 1.0, _lib.ptr(out), _lib.ptr(ovf), _lib.stream_ptr()), "finish")
+    assert int(ovf[0]) == 1
+
+
 def test_full_resolution_k8_window_vs_oracle():
     """BASELINE config 3 shape: 640x480, 8 keyframes, 6 one-way frames, 64 anchors -- one iteration of the CUDA path
     against the oracle on identical state, plus two size-independent properties: the solve reproduces H delta = g and
