@@ -154,6 +154,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                : "memory");
 }
 
+// the same with an L2 cache policy (createpolicy): evict_first for operands that are streamed once per pass, so that they
+// do not push L2-resident scratch (e.g. the tracker's residuals) out
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, unsigned bytes, unsigned long long* bar,
+                                              unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
 // Transposed butterfly: every lane holds 32 partial values v[0..31]; afterwards lane l holds the warp-wide
 // total of value index l (31 double shuffles instead of 32 x 5).
 __device__ __forceinline__ double warp_transpose_sum32(double v[32]) {

@@ -10,7 +10,7 @@
 // ring of shared-memory stages with the TMA unit (cp.async.bulk + mbarrier, SASS UBLKCP), always as far
 // ahead as the ring allows, so the HBM stream never waits for the reductions:
 //   pass-1 tiles: P (12 B/px) + I_ref (4 B/px) + mask (1 B/px)      1024 px per stage
-//   pass-2 tiles: J (32 B/px) + I_ref (4 B/px)                       512 px per stage
+//   pass-2 tiles: J (32 B/px; its column 6 is I_ref) + r (4 B/px)    512 px per stage
 // Per GN iteration (3 group barriers on the common path):
 //   pass 1   warp + bilinear gather (4 taps through the read-only path, the target image is L1/L2 resident)
 //            + residual r; r stays in shared memory when the slice fits (else an L2-resident scratch);
@@ -22,8 +22,9 @@
 //   pass 2   Huber weights, J^T W J / J^T W r / error: registers -> warp shuffle -> CTA -> per-CTA row -> barrier
 //   solve    every CTA sums the rows in a fixed order (bitwise identical everywhere, run to run), solves the
 //            8x8 system (Cholesky), applies T <- T Exp(-d), a -= d6, b -= d7 and evaluates termination.
-// HBM traffic per pixel-iteration: P 12 + I_ref 4 (+4 re-read in pass 2) + mask 1 + J 32 + target 4 B
-// (algorithmic: the 52 B of BASELINE.md).
+// HBM traffic per pixel-iteration: P 12 + I_ref 4 + mask 1 + J 32 + target 4 B (algorithmic: the 52 B of
+// BASELINE.md) + the residual scratch (4 B written, 4 B read by the TMA unit, 4 B by the median scan) when the
+// batch's residuals do not fit L2.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,7 +40,7 @@ namespace como {
 #define TRK_MAX_OCC 3
 #endif
 #ifndef TRK_STAGES
-#define TRK_STAGES 3
+#define TRK_STAGES 2
 #endif
 constexpr int CONS_WARPS = TRK_CONS_WARPS;
 constexpr int CONS_THREADS = CONS_WARPS * 32;
@@ -47,9 +48,9 @@ constexpr int TRK_THREADS = CONS_THREADS + 32;  // + producer warp
 constexpr int MAX_OCC = TRK_MAX_OCC;             // CTAs per SM the launch bounds allow
 constexpr int T1 = 512;                         // pixels per pass-1 stage (4 per consumer thread)
 constexpr int T2 = 512;                         // pixels per pass-2 stage (4 per consumer thread)
-constexpr int STAGE_BYTES = 20480;              // max(T1*(12+4+1), T2*(32+4+4))
+constexpr int STAGE_BYTES = 18432;              // max(T1*(12+4+1), T2*(32+4))
 constexpr int T1_VALS_OFF = T1 * 12, T1_MASK_OFF = T1 * 16;
-constexpr int T2_VALS_OFF = T2 * 32, T2_R_OFF = T2 * 36;
+constexpr int T2_R_OFF = T2 * 32;
 constexpr int STAGES = TRK_STAGES;
 constexpr int CHUNK_ALIGN = 512;  // slice = whole tiles (only the last slice of a level is ragged); 16-byte aligned starts
 constexpr int NACC = 45;          // 36 (upper triangle of 8x8) + 8 (gradient) + 1 (robust error)
@@ -66,8 +67,11 @@ constexpr unsigned KEY_LO = KEY_HI - (unsigned)(HIST_BINS - 2) * (1u << KEY_SHIF
 constexpr int MAX_GROUP = 1024;
 
 struct TrackCtl {
-  unsigned barrier;
-  unsigned pad0[31];
+  unsigned barrier[COMO_B200_MAX_LEVELS];  // one arrival counter per level: the CTAs that hold pixels of that level
+  unsigned level_barrier;                  // all G CTAs, once per level whose active set is smaller than G
+  int total_iter;                          // state handed to the CTAs that sat a level out
+  float T[16], aff[2];
+  unsigned pad0[4];
   unsigned cand_count[2];
   unsigned pad1[30];
   unsigned hist[2][MAX_PASSES][HIST_BINS];
@@ -241,6 +245,8 @@ __device__ __forceinline__ void flush_hist(unsigned* s_hist, unsigned* gh, bool 
 
 struct SliceInfo {
   int begin, len;
+  int active;  // CTAs of the group that hold pixels of this level (slices are whole tiles: a coarse level of a
+               // single-sequence launch occupies only a few of the G CTAs; the others sit the level out)
 };
 
 __device__ __forceinline__ SliceInfo slice_of(int N, int G, int c) {
@@ -249,6 +255,7 @@ __device__ __forceinline__ SliceInfo slice_of(int N, int G, int c) {
   SliceInfo s;
   s.begin = min(N, c * chunk);
   s.len = min(N, s.begin + chunk) - s.begin;
+  s.active = (N + chunk - 1) / chunk;
   return s;
 }
 
@@ -276,9 +283,11 @@ __device__ __forceinline__ void produce_tile1(uint8_t* stage, unsigned long long
     const unsigned bytes = (unsigned)bulk * (lv.mask ? 17u : 16u);
     if (bytes) {
       mbar_expect_tx(full, bytes);
-      bulk_g2s(stage, P, (unsigned)bulk * 12u, full);
-      bulk_g2s(stage + T1_VALS_OFF, V, (unsigned)bulk * 4u, full);
-      if (lv.mask) bulk_g2s(stage + T1_MASK_OFF, lv.mask + i0, (unsigned)bulk, full);
+      // streamed once per pass: evict-first in L2, so that the residual scratch (re-read twice) stays resident
+      const unsigned long long pol = l2_policy_evict_first();
+      bulk_g2s_hint(stage, P, (unsigned)bulk * 12u, full, pol);
+      bulk_g2s_hint(stage + T1_VALS_OFF, V, (unsigned)bulk * 4u, full, pol);
+      if (lv.mask) bulk_g2s_hint(stage + T1_MASK_OFF, lv.mask + i0, (unsigned)bulk, full, pol);
     } else {
       mbar_arrive(full);
     }
@@ -294,20 +303,16 @@ __device__ __forceinline__ void produce_tile2(uint8_t* stage, unsigned long long
   mbar_wait(empty, ((n / STAGES) & 1u) ^ 1u);
   const int bulk = cnt & ~3;
   const float* J = lv.J + 8 * (size_t)i0;
-  const float* V = lv.vals + i0;
   for (int j = bulk + (lane >> 3); j < cnt; j += 4) {
     reinterpret_cast<float*>(stage)[8 * j + (lane & 7)] = J[8 * j + (lane & 7)];
-    if ((lane & 7) == 0) {
-      reinterpret_cast<float*>(stage + T2_VALS_OFF)[j] = V[j];
-      if (r_src) reinterpret_cast<float*>(stage + T2_R_OFF)[j] = __ldcg(r_src + j);
-    }
+    if ((lane & 7) == 0 && r_src) reinterpret_cast<float*>(stage + T2_R_OFF)[j] = __ldcg(r_src + j);
   }
   __syncwarp();
   if (lane == 0) {
     if (bulk) {
-      mbar_expect_tx(full, (unsigned)bulk * (r_src ? 40u : 36u));
-      bulk_g2s(stage, J, (unsigned)bulk * 32u, full);
-      bulk_g2s(stage + T2_VALS_OFF, V, (unsigned)bulk * 4u, full);
+      mbar_expect_tx(full, (unsigned)bulk * (r_src ? 36u : 32u));
+      const unsigned long long pol = l2_policy_evict_first();
+      bulk_g2s_hint(stage, J, (unsigned)bulk * 32u, full, pol);
       if (r_src) bulk_g2s(stage + T2_R_OFF, r_src, (unsigned)bulk * 4u, full);
     } else {
       mbar_arrive(full);
@@ -376,6 +381,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
       const como_b200_track_level_t lv = levels[l];
       if (lv.n <= 0) continue;
       const SliceInfo sl = slice_of(lv.n, G, c);
+      if (c >= sl.active) continue;   // this CTA sits the level out (its consumers skip it too)
       for (;; ++pit) {
         for (int t0 = 0; t0 < sl.len; t0 += T1, ++n) {
           const unsigned s = n % STAGES;
@@ -402,11 +408,11 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
   // ============================================================================================
   // consumer warps
   // ============================================================================================
-  unsigned epoch = 0;
+  unsigned lev_epoch = 0;
   unsigned n = 0;  // tile counter, mirrors the producer's
-  int total_iter = 0;
+  int total_iter = 0;   // iterations of the problem so far (stats index, parity of the problem's global buffers)
+  int lit = 0;          // iterations THIS CTA took part in (parity of its own verdict flag / p1_done phase)
   const int stats_cap = num_levels * term.max_iter;
-  const bool single = (G == 1);
 
   for (int l = 0; l < num_levels; ++l) {
     const como_b200_track_level_t lv = levels[l];
@@ -414,6 +420,19 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
     if (N <= 0) continue;
     const int w = lv.w, h = lv.h;
     const SliceInfo sl = slice_of(N, G, c);
+    const int Ga = sl.active;            // group size of this level
+    const bool single = (Ga == 1);
+    unsigned epoch = 0;
+    unsigned* lbar = &ctl->barrier[l];
+    if (c >= Ga) {
+      // no pixels of this level here: wait for the level's result (T, aff, iteration count) and move on
+      consumer_group_barrier(&ctl->level_barrier, lev_epoch, G);
+      if (tid < 16) s_T[tid] = __ldcg(&ctl->T[tid]);
+      if (tid < 2) s_aff[tid] = __ldcg(&ctl->aff[tid]);
+      total_iter = __ldcg(&ctl->total_iter);
+      consumer_sync();
+      continue;
+    }
     const float xmax = (float)(w - 1), ymax = (float)(h - 1);
     float* g_r = g_resid + sl.begin;  // residual of slice pixel j: s_r[j] if j < r_cap else g_r[j]
 
@@ -552,7 +571,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
       __syncwarp();
       if (lane == 0) mbar_arrive(&p1_done_bar);
       flush_hist(s_hist, gh, single);
-      consumer_group_barrier(&ctl->barrier, epoch, G);
+      consumer_group_barrier(lbar, epoch, Ga);
 
       // ---- exact lower median of |r| over the whole problem
       select_bin(gh, true, 0u, true, s_warp, s_sel);
@@ -588,7 +607,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
               consumer_sync();
               const unsigned gb = s_base;
               for (unsigned j = tid; j < mine; j += CONS_THREADS) __stcg(&ctl->cand[par][gb + j], s_cand[j]);
-              consumer_group_barrier(&ctl->barrier, epoch, G);
+              consumer_group_barrier(lbar, epoch, Ga);
               for (unsigned j = tid; j < cnt_in; j += CONS_THREADS) s_cand[j] = __ldcg(&ctl->cand[par][j]);
             }
             if (tid == 0) s_cnt = 0;
@@ -620,7 +639,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
             });
           }
           flush_hist(s_hist, gh + pass * HIST_BINS, single);
-          consumer_group_barrier(&ctl->barrier, epoch, G);
+          consumer_group_barrier(lbar, epoch, Ga);
           select_bin(gh + pass * HIST_BINS, true, krank, false, s_warp, s_sel);
           const unsigned b2 = s_sel[0];
           krank = s_sel[1];
@@ -649,14 +668,12 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         const uint8_t* stage = ring + s * STAGE_BYTES;
         mbar_wait(&full_bar[s], (n / STAGES) & 1u);
         const float4* sJ = reinterpret_cast<const float4*>(stage) + 2 * tid;
-        const float* sV = reinterpret_cast<const float*>(stage + T2_VALS_OFF) + tid;
         const float* sR = (t0 < r_cap ? (s_r + t0) : reinterpret_cast<const float*>(stage + T2_R_OFF)) + tid;
         const int left = sl.len - t0 - tid;
-        float vv[PB2], rr[PB2];
+        float rr[PB2];
         float4 ja[PB2], jb[PB2];
 #pragma unroll
         for (int k = 0; k < PB2; ++k) {  // rows beyond the tile's count hold stale data: their r is forced to NaN
-          vv[k] = sV[k * CONS_THREADS];
           rr[k] = (k * CONS_THREADS < left) ? sR[k * CONS_THREADS] : qnan;
           ja[k] = sJ[2 * k * CONS_THREADS];
           jb[k] = sJ[2 * k * CONS_THREADS + 1];
@@ -667,7 +684,8 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         for (int k = 0; k < PB2; ++k) {
           const float r = rr[k];
           if (r == r) {
-            const float mt = (bb - r) - vv[k];  // column 6 of J: -e^{-a} I_j
+            // column 6 of J as passed in is I_ref (precalc_jacobians); this iteration's column 6 is -e^{-a} I_j
+            const float mt = (bb - r) - jb[k].z;
             const float wr = r * inv_sigma;
             const float a = fabsf(wr);
             const float wgt = (a < HUBER_K) ? 1.0f : HUBER_K * rcp_approx(a);
@@ -722,10 +740,10 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
       // zero the other parity's histograms / candidate counter for the next iteration (nobody reads them any more)
       {
         unsigned* nz = &ctl->hist[par ^ 1][0][0];
-        for (int b = c * CONS_THREADS + tid; b < MAX_PASSES * HIST_BINS; b += G * CONS_THREADS) nz[b] = 0u;
+        for (int b = c * CONS_THREADS + tid; b < MAX_PASSES * HIST_BINS; b += Ga * CONS_THREADS) nz[b] = 0u;
         if (c == 0 && tid == 0) ctl->cand_count[par ^ 1] = 0u;
       }
-      consumer_group_barrier(&ctl->barrier, epoch, G);
+      consumer_group_barrier(lbar, epoch, Ga);
 
       // ---- deterministic cross-CTA sum, solve, update, termination (identical in every CTA)
       if (!single) {
@@ -733,14 +751,14 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         double s = 0.0;
         if (k < NACC) {  // eight loads in flight, added in a fixed order
           int cc = s2;
-          for (; cc + 14 < G; cc += 16) {
+          for (; cc + 14 < Ga; cc += 16) {
             double v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[u] = __ldcg(partials + (size_t)(cc + 2 * u) * NACC_PAD + k);
 #pragma unroll
             for (int u = 0; u < 8; ++u) s += v[u];
           }
-          for (; cc < G; cc += 2) s += __ldcg(partials + (size_t)cc * NACC_PAD + k);
+          for (; cc < Ga; cc += 2) s += __ldcg(partials + (size_t)cc * NACC_PAD + k);
         }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         if (s2 == 0 && k < NACC) s_acc[k] = s;
@@ -806,15 +824,23 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
           for (int k = 0; k < 16; ++k) s_T[k] = Tn[k];
           s_aff[0] = (float)((double)s_aff[0] - s_delta[6]);
           s_aff[1] = (float)((double)s_aff[1] - s_delta[7]);
-          s_done[total_iter & 1] = done ? 1 : 0;
+          s_done[lit & 1] = done ? 1 : 0;
           s_acc[45] = mse;
         }
       }
       __syncthreads();  // with the producer warp: s_done is this iteration's verdict
       mse_prev = s_acc[45];
-      level_done = (s_done[total_iter & 1] != 0);
+      level_done = (s_done[lit & 1] != 0);
       ++it;
       ++total_iter;
+      ++lit;
+    }
+    if (Ga < G) {
+      // hand the level's result to the CTAs that sat it out
+      if (c == 0 && tid < 16) __stcg(&ctl->T[tid], s_T[tid]);
+      if (c == 0 && tid < 2) __stcg(&ctl->aff[tid], s_aff[tid]);
+      if (c == 0 && tid == 0) __stcg(&ctl->total_iter, total_iter);
+      consumer_group_barrier(&ctl->level_barrier, lev_epoch, G);
     }
   }
   if (c == 0) {
@@ -853,7 +879,17 @@ static int track_config(int num_problems, int max_n, TrackLaunchCfg* cfg) {
     if (dyn > smem_optin - (long long)fa.sharedSizeBytes) dyn = smem_optin - (long long)fa.sharedSizeBytes;
     const long long r_bytes = dyn - (long long)STAGES * STAGE_BYTES;
     if (r_bytes < 0) continue;
-    const int r_cap = (int)(r_bytes / 4) / T1 * T1;
+    // Residual slice in shared memory only if ALL of it fits (single-sequence launches: a few thousand pixels per
+    // CTA); otherwise none of it: shared memory not claimed here stays L1, and the bilinear taps live on L1 hits
+    // (measured: +7 % batched throughput with r_cap = 0 and a 2-stage ring against a full-size carve-out).
+    int r_cap = (int)(r_bytes / 4) / T1 * T1;
+    {
+      const int g_guess = (g_want < sms * occ / (num_problems > 0 ? num_problems : 1)) ? g_want : sms * occ / (num_problems > 0 ? num_problems : 1);
+      int chunk = (max_n + (g_guess > 0 ? g_guess : 1) - 1) / (g_guess > 0 ? g_guess : 1);
+      chunk = (chunk + CHUNK_ALIGN - 1) / CHUNK_ALIGN * CHUNK_ALIGN;
+      r_cap = (chunk <= r_cap) ? chunk : 0;
+    }
+    if (const char* e_rc = getenv("COMO_B200_TRACK_RCAP")) r_cap = atoi(e_rc) / T1 * T1;  // tuning only
     const size_t dyn_smem = (size_t)STAGES * STAGE_BYTES + (size_t)r_cap * 4;
     cudaFuncSetAttribute(track_pyr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
     int per_sm = 0;
@@ -976,14 +1012,21 @@ extern "C" int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_
       cudaEventSynchronize(sl.ev);
     }
     if (sl.cap < cnt) {
-      if (sl.buf) cudaFreeHost(sl.buf);
-      if (cudaMallocHost((void**)&sl.buf, cnt * sizeof(como_b200_track_level_t)) != cudaSuccess) {
-        sl.buf = nullptr;
-        sl.cap = 0;
-        set_last_error("track_pyr: pinned staging allocation failed");
-        return COMO_B200_ELAUNCH;
+      // (re)allocate the whole ring of this device at once: pinned allocations cost milliseconds and must not
+      // trickle into the first SLOTS calls of a new batch size
+      for (int q = 0; q < SLOTS; ++q) {
+        Slot& t = ring[dev][q];
+        if (t.cap >= cnt) continue;
+        if (t.ev) cudaEventSynchronize(t.ev);
+        if (t.buf) cudaFreeHost(t.buf);
+        if (cudaMallocHost((void**)&t.buf, cnt * sizeof(como_b200_track_level_t)) != cudaSuccess) {
+          t.buf = nullptr;
+          t.cap = 0;
+          set_last_error("track_pyr: pinned staging allocation failed");
+          return COMO_B200_ELAUNCH;
+        }
+        t.cap = cnt;
       }
-      sl.cap = cnt;
     }
     memset(sl.buf, 0, cnt * sizeof(como_b200_track_level_t));
     for (int p = 0; p < num_problems; ++p)

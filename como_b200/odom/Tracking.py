@@ -9,7 +9,8 @@ import ctypes as C
 import torch
 
 from como_b200 import _lib
-from como_b200.odom.frontend.photo_tracking import photo_tracking_pyr
+import como_b200.odom.frontend.photo_tracking as _pt
+from como_b200.odom.frontend.photo_tracking import TrackBatchPlan, photo_tracking_pyr  # noqa: F401
 
 
 def _dtype(name):
@@ -77,6 +78,11 @@ class Tracking:
         self._med_ws = torch.empty(int(_lib.median_workspace_bytes(1, 4)), dtype=torch.uint8, device=self.dev)
         self._med = torch.empty(1, dtype=torch.float32, device=self.dev)
         self._cnt = torch.empty(1, dtype=torch.int64, device=self.dev)
+        # per-frame fast path: persistent target pyramid (so that the launch descriptors of the tracker stay valid from
+        # one frame to the next), the cached launch plan, and ONE pinned read-back for the keyframe decisions
+        self._img_bufs = [torch.empty((1, 1, h, w), dtype=torch.float32, device=self.dev) for (h, w) in self.level_sizes]
+        self._plan = None
+        self._host = torch.empty(18, dtype=torch.float32).pin_memory()
 
     def reset_one_way_vars(self):
         self.num_one_way_since_kf = 0
@@ -102,7 +108,7 @@ class Tracking:
         return a
 
     # ------------------------------------------------------------------ images
-    def _pyramid(self, rgb, with_grads):
+    def _pyramid(self, rgb, with_grads, out=None):
         """One fused launch per image: gray + all pyramid levels (+ Scharr gradients laid out [I, gx, gy] per level,
         the layout kf_reference_level gathers from).  Pyramids deeper than 4 levels use the per-level kernels."""
         rgb = rgb.to(device=self.dev, dtype=torch.float32).contiguous()
@@ -110,7 +116,8 @@ class Tracking:
         nl = self.num_levels
         H, W = self.level_sizes[-1]
         ch = 3 if with_grads else 1
-        out = [torch.empty((b, ch, h, w), dtype=torch.float32, device=self.dev) for (h, w) in self.level_sizes]
+        if out is None:
+            out = [torch.empty((b, ch, h, w), dtype=torch.float32, device=self.dev) for (h, w) in self.level_sizes]
         with torch.cuda.device(self.dev):
             stream = _lib.stream_ptr(self.dev)
             for i in range(b):
@@ -254,6 +261,7 @@ class Tracking:
             self.mask_pyr.append(mask.view(torch.bool))
             rr, cc = torch.meshgrid(torch.arange(h, device=self.dev), torch.arange(w, device=self.dev), indexing="ij")
             self.coords_pyr.append(torch.stack((rr.reshape(-1), cc.reshape(-1)), 1)[None].repeat(num_kf, 1, 1))
+        self._plan = None   # new reference operands: the launch plan is rebuilt by the next handle_frame
         self.kf_received_ts = timestamps[-1]
         self.T_w_kf = kf_pose[num_kf - 1:num_kf]
         self.aff_w_kf = kf_aff[num_kf - 1:num_kf]
@@ -261,20 +269,37 @@ class Tracking:
     # ------------------------------------------------------------------ per-frame tracking
     def handle_frame(self, data):
         timestamp, rgb = data
-        img_pyr = self.prep_tracking_img(rgb)
-        self.T_curr_kf, self.aff_curr_kf = photo_tracking_pyr(
-            self.T_curr_kf, self.aff_curr_kf, self.vals_pyr, self.P_pyr, self.dI_dT_pyr, self.mask_pyr,
-            self.intrinsics_pyr, img_pyr, self.cfg["sigmas"]["photo"], self.cfg["term_criteria"])
+        if rgb.shape[0] == 1 and self.vals_pyr[0].shape[0] == 1:
+            # one fused front-end launch into the persistent pyramid, one tracker launch from the cached plan
+            self._pyramid(rgb, False, out=self._img_bufs)
+            if self._plan is None:
+                self._plan = TrackBatchPlan([(self.vals_pyr, self.P_pyr, self.dI_dT_pyr, self.mask_pyr, self.intrinsics_pyr,
+                                              self._img_bufs)], self.cfg["term_criteria"])
+            T, aff, nit = self._plan.run(self.T_curr_kf, self.aff_curr_kf)
+            self.T_curr_kf, self.aff_curr_kf = T.clone(), aff.clone()
+            _pt.last_num_iters = nit
+        else:
+            img_pyr = self.prep_tracking_img(rgb)
+            self.T_curr_kf, self.aff_curr_kf = photo_tracking_pyr(
+                self.T_curr_kf, self.aff_curr_kf, self.vals_pyr, self.P_pyr, self.dI_dT_pyr, self.mask_pyr,
+                self.intrinsics_pyr, img_pyr, self.cfg["sigmas"]["photo"], self.cfg["term_criteria"])
         T_w_curr = self.get_curr_world_pose()
         track_data_viz = (timestamp, T_w_curr.clone())
         track_data_map = None
         median_depth, num_valid = self._reproj_stats(self.T_curr_kf)
-        new_kf = self.check_keyframe(median_depth, num_valid, self.T_curr_kf)
+        # the decisions need three numbers on the host: one pinned read-back (one synchronisation) instead of one
+        # implicit device->host read per comparison
+        self._host.copy_(torch.cat((self.T_curr_kf.reshape(16), median_depth.reshape(1), num_valid.reshape(1).float())),
+                         non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        T_host = self._host[:16].reshape(1, 4, 4).clone()
+        med_h, cnt_h = float(self._host[16]), float(self._host[17])
+        new_kf = self.check_keyframe(med_h, cnt_h, T_host)
         if new_kf:
             track_data_map = ("keyframe", rgb.clone(), self.T_curr_kf, self.aff_curr_kf, self.kf_received_ts, timestamp)
             self.last_kf_sent_ts = timestamp
         else:
-            if self.check_one_way_frame(median_depth, num_valid, self.T_curr_kf, T_w_curr):
+            if self.check_one_way_frame(med_h, cnt_h, T_host, T_w_curr):
                 track_data_map = ("one-way", rgb.clone(), self.T_curr_kf, self.aff_curr_kf, self.kf_received_ts, timestamp)
                 self.last_rec_sent_ts = timestamp
                 self.num_one_way_since_kf += 1

@@ -42,7 +42,8 @@ const char* como_b200_last_error(void);
 typedef struct {
   const float* vals;   /* (n)     reference intensities I_i            [photo_tracking.py:24 vals_i]  */
   const float* P;      /* (n,3)   reference points in the KF frame     [Pi]                           */
-  const float* J;      /* (n,8)   precomputed dI/d[xi,a,b]; cols 6,7 are ignored (rebuilt per iter)   */
+  const float* J;      /* (n,8)   dI/d[xi,a,b] as precalc_jacobians lays it out: col 6 = I_ref (read as
+                        *          such by the accumulation pass), col 7 ignored                      [dI_dT] */
   const uint8_t* mask; /* (n) 0/1 or NULL: which points take part      [masks]                        */
   const float* img;    /* (h,w)   target image of this level           [img_j]                        */
   int32_t n, w, h;
