@@ -69,6 +69,7 @@ subselect_pixels = _sig("como_b200_subselect_pixels", C.c_int, [VP, I32, I32, I3
 ba_scaffold = _sig("como_b200_ba_scaffold", C.c_int,
                    [VP, VP, VP, VP, VP, VP, I32, I32, I32, C.POINTER(F64), VP, VP, VP])
 predictor_apply = _sig("como_b200_predictor_apply", C.c_int, [VP, VP, I32, I64, I32, VP, VP])
+predictor_stream_ctas = _sig("como_b200_predictor_stream_ctas", None, [I32])
 predictor_colsum = _sig("como_b200_predictor_colsum", C.c_int, [VP, I64, I32, VP, VP])
 ba_frames_bytes = _sig("como_b200_ba_frames_bytes", C.c_size_t, [I32])
 ba_partial_doubles = _sig("como_b200_ba_partial_doubles", C.c_size_t, [I32])
@@ -124,7 +125,7 @@ DECLARED_SYMBOLS = [
     "como_b200_abi_version", "como_b200_last_error", "como_b200_track_workspace_bytes", "como_b200_track_pyr",
     "como_b200_track_debug_candidate_cap",
     "como_b200_precalc_jacobians", "como_b200_median_workspace_bytes", "como_b200_median_f64", "como_b200_median_f32",
-    "como_b200_subselect_pixels", "como_b200_ba_scaffold", "como_b200_predictor_apply", "como_b200_predictor_colsum",
+    "como_b200_subselect_pixels", "como_b200_ba_scaffold", "como_b200_predictor_apply", "como_b200_predictor_stream_ctas", "como_b200_predictor_colsum",
     "como_b200_ba_frames_bytes", "como_b200_ba_partial_doubles", "como_b200_ba_unit_ints", "como_b200_ba_target_group",
     "como_b200_ba_photo_residual", "como_b200_ba_photo_accum", "como_b200_median_num_passes",
     "como_b200_median_pass_f64", "como_b200_median_finish_f64", "como_b200_median_pack_words",

@@ -318,6 +318,11 @@ extern "C" int como_b200_subselect_pixels(const double* img_and_grads, int32_t K
   return check_launch("subselect_pixels");
 }
 
+// 0 = two CTAs on every SM.  A smaller grid confines the stream to part of the chip (two CTAs per SM it lands on), so
+// that a compute-bound kernel on another stream gets the remaining SMs for itself instead of queueing behind it.
+static int g_predictor_stream_ctas = 0;
+extern "C" void como_b200_predictor_stream_ctas(int32_t ctas) { g_predictor_stream_ctas = ctas > 0 ? ctas : 0; }
+
 extern "C" int como_b200_predictor_apply(const double* Knm, const double* scaffold, int32_t K, int64_t HW, int32_t M,
                                          double* depth, void* stream) {
   COMO_REQUIRE(Knm && scaffold && depth, "predictor_apply: null pointer argument");
@@ -326,6 +331,7 @@ extern "C" int como_b200_predictor_apply(const double* Knm, const double* scaffo
   cudaFuncSetAttribute(predictor_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PredStreamSmem));
   const long long chunks_per_kf = (HW + PS_ROWS - 1) / PS_ROWS;
   long long grid = 2LL * sm_count();
+  if (g_predictor_stream_ctas > 0) grid = g_predictor_stream_ctas;   // see como_b200_predictor_stream_ctas
   if (grid > chunks_per_kf * K) grid = chunks_per_kf * K;
   predictor_stream_kernel<<<(unsigned)grid, PS_THREADS, sizeof(PredStreamSmem), (cudaStream_t)stream>>>(
       Knm, scaffold, K, HW, M, chunks_per_kf, depth);

@@ -14,6 +14,14 @@ What is replaced (reference name -> como_b200 implementation):
   como.depth_cov.core.distill_depth.distill_depth_from_scratch / distill_conditional_depth_from_scratch
   como.odom.frontend.two_frame_sfm.two_frame_sfm_pyr / two_frame_sfm / setup_reference (also as imported by
   como.odom.frontend.TwoFrameSfm)
+  como.utils.multiprocessing.TupleTensorQueue / transfer_data / release_data / init_gpu (also as imported by
+  como.odom.multiprocessing.ComoMp when that module is importable): slot ring shared once over CUDA IPC
+
+Aliasing contract (the reference's update_vars rebinds fresh tensors; mapping_core.iterate updates kf_poses,
+kf_aff_params, recent_*, P_m IN PLACE): holders of slices of those tensors see the update.  The reference's own
+consumers copy on the way out (get_kf_viz_data clones; get_kf_ref_data goes through transfer_data to another dtype /
+the queue, and como_b200's TupleTensorQueue.pop returns tensors that own their memory), so nothing in the reference's
+flow observes the difference; code that keeps raw slices across iterate() calls must clone them.
 Everything else (UNet, orchestration) keeps running the reference's own Python on the
 same device.  Requires tracking.dtype float / mapping.dtype double, color gray.
 """
@@ -82,10 +90,21 @@ def install():
         setattr(ref_sfm, name, getattr(b_sfm, name))
     ref_sfm_cls.two_frame_sfm_pyr = b_sfm.two_frame_sfm_pyr
     ref_sfm_cls.setup_reference = b_sfm.setup_reference
+    import como.utils.multiprocessing as ref_mp
+
+    from como_b200.utils import multiprocessing as b_mp
+
+    for name in ("TupleTensorQueue", "transfer_data", "release_data", "init_gpu"):
+        setattr(ref_mp, name, getattr(b_mp, name))
+    comp = sys.modules.get("como.odom.multiprocessing.ComoMp")   # needs open3d/glfw to import: patched only if loaded
+    if comp is not None:
+        for name in ("TupleTensorQueue", "release_data", "init_gpu"):
+            if hasattr(comp, name):
+                setattr(comp, name, getattr(b_mp, name))
     ref_mapping.Mapping.iterate = iterate
     ref_mapping.Mapping.store_vars = store_vars
     ref_mapping.Mapping.prep_predictor = prep_predictor
     return {"patched": ["como_backends", "sample_sparse_coords", "photo_tracking_pyr", "precalc_jacobians",
                         "Mapping.iterate", "Mapping.store_vars", "Mapping.prep_predictor", "Mapping.get_img_and_grads", "solve_system",
                         "track_and_init", "distill_depth_from_scratch", "distill_conditional_depth_from_scratch",
-                        "two_frame_sfm_pyr", "setup_reference"]}
+                        "two_frame_sfm_pyr", "setup_reference", "TupleTensorQueue"]}

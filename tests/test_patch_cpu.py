@@ -31,6 +31,8 @@ def test_install_rebinds_reference_names():
         assert RSC.two_frame_sfm_pyr.__module__ == "como_b200.odom.frontend.two_frame_sfm"
         import como.odom.frontend.corr as RC
         assert RC.distill_depth_from_scratch.__module__ == "como_b200.depth_cov.core.distill_depth"
+        import como.utils.multiprocessing as RMP
+        assert RMP.TupleTensorQueue.__module__ == "como_b200.utils.multiprocessing"
         # no CPU fallback: the patched operators refuse CPU tensors loudly
         import torch
         with pytest.raises(RuntimeError, match="same device"):
