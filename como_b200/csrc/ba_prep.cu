@@ -114,8 +114,7 @@ predictor_stream_kernel(const double* __restrict__ Knm, const double* __restrict
       const double2 v = act ? *reinterpret_cast<const double2*>(x + (size_t)j * M + m0) : make_double2(0.0, 0.0);
       acc[j] = v.x * l0 + v.y * l1;
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&S.empty[slot]);
+    stage_release(&S.empty[slot]);
     // transposed butterfly: 8 rows over 32 lanes -> lanes with (lane & 3) == 0 hold one row total each
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

@@ -113,6 +113,10 @@ __device__ __forceinline__ constexpr int tri8(int i, int k) { return i * (i + 1)
 
 // In-register Cholesky of an 8 x 8 block (every lane of the warp computes the same thing: no shuffles on the
 // pivot chain).  rs[j] = 1 / L[j][j].  Non-positive pivot -> NaN.
+// Measured (scripts/chol_probe.py): 1.13 k cycles per block, i.e. ~140 per pivot = one fp64 rsqrt (MUFU seed + two
+// Newton steps of dependent DFMAs at ~17 cycles each) + the dependent multiply / update.  Taking pivots in pairs
+// (second pivot = sqrt(det / p), so that rsqrt(p) and rsqrt(det) overlap) was tried in round 2: the chain keeps the same
+// number of dependent fp64 operations and the block took the same 1.13 k cycles.
 __device__ __forceinline__ void chol8_regs(double (&a)[36], double (&rs)[8]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {

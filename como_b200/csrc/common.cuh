@@ -137,6 +137,17 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Consumer release of a TMA-filled stage: the stage may be overwritten by the async proxy as soon as the arrival is
+// seen, so every lane's reads of the stage must have been PERFORMED first.  __syncwarp() + arrive is not enough: shared
+// loads still in flight in the LSU when lane 0 arrives can lose the race against the refill when the SM is shared
+// with another kernel (seen as a handful of wrong rows per launch -- always the last rows a warp reads -- in
+// predictor_stream_kernel beside cuBLAS / the median kernels; scripts/stream_stress.py).  The CTA-scope fence makes each
+// lane wait for its outstanding loads.
+__device__ __forceinline__ void stage_release(unsigned long long* empty_bar) {
+  __threadfence_block();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(empty_bar);
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"

@@ -491,8 +491,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
           Z[k] = sP[3 * k * CONS_THREADS + 2];
           st.vref[k] = sV[k * CONS_THREADS];
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);  // operands are in registers: release the stage early
+        stage_release(&empty_bar[s]);  // operands are in registers (loads performed): release the stage early
 #pragma unroll
         for (int k = 0; k < PB; ++k) {
           const float hx = p00 * X[k] + p01 * Y[k] + p02 * Z[k] + p03;
@@ -678,8 +677,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
           ja[k] = sJ[2 * k * CONS_THREADS];
           jb[k] = sJ[2 * k * CONS_THREADS + 1];
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        stage_release(&empty_bar[s]);
 #pragma unroll
         for (int k = 0; k < PB2; ++k) {
           const float r = rr[k];

@@ -194,6 +194,53 @@ def test_distributed_median_passes_match_fused_median():
         assert float(out1[i]) == ref and float(out2[i]) == ref
 
 
+def test_predictor_stream_bitwise_when_sharing_the_chip():
+    """store_vars runs on a side stream beside other kernels.  Its result must not depend on what shares the SMs:
+    a confined grid (one CTA per SM / 96 CTAs) co-running with cuBLAS and with the median kernels gives bit-identical
+    depth images.  (Regression test: stage releases used to race with shared loads still in flight in the LSU.)"""
+    from como_b200 import _lib
+
+    torch.manual_seed(0)
+    dev = torch.device("cuda", 0)
+    K, HW, M = 4, 307200, 64
+    Knm = torch.randn(K, HW, M, dtype=torch.float64, device=dev) * 0.05
+    scaf = torch.zeros(K, M, 16, dtype=torch.float64, device=dev)
+    scaf[:, :, 0] = torch.randn(K, M, dtype=torch.float64, device=dev)
+    ref = torch.empty(K, HW, dtype=torch.float64, device=dev)
+    _lib.predictor_stream_ctas(0)
+    _lib.check(_lib.predictor_apply(_lib.ptr(Knm), _lib.ptr(scaf), K, HW, M, _lib.ptr(ref), _lib.stream_ptr()), "pa")
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(dev)
+    A = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    v = torch.rand(4, 300000, dtype=torch.float64, device=dev)
+    off = (torch.arange(5, dtype=torch.int64) * 300000).to(dev)
+    mo = torch.empty(4, dtype=torch.float64, device=dev)
+    ws = torch.empty(int(_lib.median_workspace_bytes(4, 8)), dtype=torch.uint8, device=dev)
+    try:
+        for ctas in (148, 96):
+            for kind in ("matmul", "median"):
+                for rep in range(4):
+                    out = torch.full((K, HW), float("nan"), dtype=torch.float64, device=dev)
+                    torch.cuda.synchronize()
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    side.wait_event(ev)
+                    with torch.cuda.stream(side):
+                        _lib.predictor_stream_ctas(ctas)
+                        _lib.check(_lib.predictor_apply(_lib.ptr(Knm), _lib.ptr(scaf), K, HW, M, _lib.ptr(out),
+                                                        _lib.stream_ptr(dev)), "pa")
+                    for _ in range(3):
+                        if kind == "matmul":
+                            keep = A @ A
+                        else:
+                            _lib.check(_lib.median_f64(_lib.ptr(v), _lib.ptr(off), 4, 300000, 1.0, _lib.ptr(mo), None, _lib.ptr(ws),
+                                                       ws.numel(), _lib.stream_ptr()), "median")
+                    torch.cuda.synchronize()
+                    assert torch.equal(out, ref), (ctas, kind, rep, int((out != ref).sum()))
+    finally:
+        _lib.predictor_stream_ctas(0)
+
+
 def test_three_exchange_distributed_median_matches_torch():
     """The sharded robust scale: two digit histograms (summed over ranks), per-rank candidate packs, all-gather, finish.
     Two 'ranks' are emulated on one GPU (their histograms added, their packs stacked); the result must be the exact
