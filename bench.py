@@ -704,13 +704,15 @@ def cpu_window(K, R, seed=0):
         have = curr[0].double().numpy() if curr is not None and curr.numel() else np.zeros((0, 2))
         pts = [p for p in have]
         chosen = []
+        used = np.zeros(cand.shape[0], dtype=bool)
         for _ in range(max(n - have.shape[0], 0)):
             ref = np.array(pts) if pts else np.array([[-1e9, -1e9]])
             d = ((cand[:, None, :] - ref[None]) ** 2).sum(-1).min(1)
+            d[used] = -1.0
             i = int(d.argmax())
+            used[i] = True
             chosen.append(cand[i].copy())
             pts.append(cand[i].copy())
-            cand[i] = 1e9
         return torch.tensor(np.array(chosen).reshape(-1, 2), dtype=torch.float64)[None]
 
     def predictor(cov, coords):

@@ -317,8 +317,8 @@ extern "C" int como_b200_subselect_pixels(const double* img_and_grads, int32_t K
   return check_launch("subselect_pixels");
 }
 
-// 0 = two CTAs on every SM.  A smaller grid confines the stream to part of the chip (two CTAs per SM it lands on), so
-// that a compute-bound kernel on another stream gets the remaining SMs for itself instead of queueing behind it.
+// 0 = one CTA per SM (default).  Other grids are for experiments (a smaller grid leaves SMs to a kernel on another stream,
+// but one CTA pulls only ~45 GB/s, so the stream slows down in proportion: profiles/r02_corun_probe.txt).
 static int g_predictor_stream_ctas = 0;
 extern "C" void como_b200_predictor_stream_ctas(int32_t ctas) { g_predictor_stream_ctas = ctas > 0 ? ctas : 0; }
 
@@ -329,7 +329,9 @@ extern "C" int como_b200_predictor_apply(const double* Knm, const double* scaffo
   // the attribute is per device: set on every call (cheap) rather than once per process
   cudaFuncSetAttribute(predictor_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PredStreamSmem));
   const long long chunks_per_kf = (HW + PS_ROWS - 1) / PS_ROWS;
-  long long grid = 2LL * sm_count();
+  // one CTA (96 KB in flight) per SM: measured 0.743 ms for the 5.03 GB of a K = 32 window against 0.783 ms with two per
+  // SM (profiles/r02_corun_probe.txt)
+  long long grid = sm_count();
   if (g_predictor_stream_ctas > 0) grid = g_predictor_stream_ctas;   // see como_b200_predictor_stream_ctas
   if (grid > chunks_per_kf * K) grid = chunks_per_kf * K;
   predictor_stream_kernel<<<(unsigned)grid, PS_THREADS, sizeof(PredStreamSmem), (cudaStream_t)stream>>>(

@@ -537,6 +537,11 @@ extern "C" int como_b200_chol_debug_probe(double* tile, long long* clk) {
   return cudaDeviceSynchronize() == cudaSuccess ? 0 : -2;
 }
 
+// 0 = one persistent CTA per SM.  The factorisation is bound by its critical path, not by SM count: a smaller grid
+// leaves SMs to a bandwidth-bound kernel on another stream.
+static int g_chol_ctas = 0;
+extern "C" void como_b200_chol_ctas(int32_t ctas) { g_chol_ctas = ctas > 0 ? ctas : 0; }
+
 extern "C" size_t como_b200_chol_solve_workspace_bytes(int32_t n) {
   const size_t nb = (n + CT - 1) / CT;
   return align256(sizeof(int) * ((nb + 1) * nb + nb)) + align256(sizeof(int2) * (nb * (nb + 3) / 2 + 8)) +
@@ -578,6 +583,7 @@ extern "C" int como_b200_chol_solve(const double* H, const double* g, int32_t n,
   // the attribute is per device: set on every call (cheap) rather than once per process
   cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem));
   int grid = sm_count();
+  if (g_chol_ctas > 0 && g_chol_ctas < grid) grid = g_chol_ctas;   // see como_b200_chol_ctas
   if (grid > ntiles) grid = ntiles;
   // Both kernels spin on flags written by other CTAs of the same grid: launched cooperatively so that the runtime
   // refuses the launch (instead of letting it hang) if the CTAs cannot all be resident.

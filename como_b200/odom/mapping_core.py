@@ -20,11 +20,7 @@ SCAF = 16
 F64 = torch.float64
 
 
-class WindowState:
-    """Plain attribute bag with the reference Mapping's state names."""
-
-    def __init__(self, **kw):
-        self.__dict__.update(kw)
+from como_b200.state import WindowState  # noqa: E402,F401  (re-exported: bench.py and the tests use MC.WindowState)
 
 
 def _i32(x, dev):
@@ -208,9 +204,9 @@ def _buf(cache, name, shape, dtype, dev):
 
 
 _OVERLAP = os.environ.get("COMO_B200_BA_OVERLAP", "1") != "0"
-# CTAs of the store_vars stream when it runs beside the normal-equation build: -1 = one per SM (measured best:
-# 2.66 vs 2.74 ms per iteration with two per SM, profiles/r02_stream_ctas_sweep.txt), 0 = two per SM, n = n CTAs
-_STREAM_CTAS = int(os.environ.get("COMO_B200_STREAM_CTAS", "-1"))
+# CTAs of the store_vars stream (tuning only): 0 = the library default, one per SM (measured best both alone and beside
+# the normal-equation build: profiles/r02_stream_ctas_sweep.txt, r02_corun_probe.txt)
+_STREAM_CTAS = int(os.environ.get("COMO_B200_STREAM_CTAS", "0"))
 
 
 def _host_scalars(cache, name, t, pick, n):
@@ -407,8 +403,7 @@ def _iterate(s, cfg, allreduce, hist_allreduce, rank, world, return_debug, comm)
         with torch.cuda.stream(side):
             sstream = _lib.stream_ptr(dev)
             if k1 > k0:
-                ctas = _STREAM_CTAS if _STREAM_CTAS >= 0 else torch.cuda.get_device_properties(dev).multi_processor_count
-                _lib.predictor_stream_ctas(ctas if side is not main else 0)
+                _lib.predictor_stream_ctas(_STREAM_CTAS)
                 st = _lib.predictor_apply(_lib.ptr(s.Knm_Kmminv[k0:]), _lib.ptr(scaf[k0:]), k1 - k0, H * W, M,
                                           _lib.ptr(depth[k0:]), sstream)
                 _lib.check(st, "como_b200_predictor_apply")
@@ -544,7 +539,7 @@ def kernel_launchers(s, cfg, dev):
     rec_img = s.recent_img_and_grads if R > 0 else None
 
     def predictor_stream():
-        _lib.predictor_stream_ctas(0)   # alone on the chip: two CTAs per SM
+        _lib.predictor_stream_ctas(0)
         _lib.check(_lib.predictor_apply(_lib.ptr(s.Knm_Kmminv), _lib.ptr(scaf), K, H * W, M, _lib.ptr(depth),
                                         _lib.stream_ptr(dev)), "como_b200_predictor_apply")
 

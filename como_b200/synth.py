@@ -175,7 +175,7 @@ def make_ba_window(K, R, H, W, M=64, device="cuda", seed=0, step=6.0, ndrop=20, 
                    sampler=None, predictor=None, img_noise=0.04):
     """`sampler(cov, n, curr_coords_or_None) -> (1,k,2) coords` and `predictor(cov, coords) -> (Kinv, L, slab)` default
     to the CUDA product implementations; tests inject CPU oracles to build the same scene without a GPU."""
-    from como_b200.odom.mapping_core import WindowState
+    from como_b200.state import WindowState
 
     if sampler is None:
         from como_b200.depth_cov.core.samplers import sample_sparse_coords as _ssc

@@ -134,9 +134,8 @@ int como_b200_ba_scaffold(const double* kf_poses, double* P_m, const int32_t* lm
 /* store_vars (Mapping.py:749-758): depth (K,HW) = exp(Knm_Kmminv (K,HW,M) . logz_m); logz_m read from scaffold. */
 int como_b200_predictor_apply(const double* Knm, const double* scaffold, int32_t K, int64_t HW, int32_t M,
                               double* depth, void* stream);
-/* Grid size of the streaming kernel behind predictor_apply: 0 (default) = two CTAs on every SM; a smaller count
- * confines the stream to part of the chip so that kernels on other streams run beside it (store_vars runs next to the
- * normal-equation build in Mapping.iterate). */
+/* Grid size of the streaming kernel behind predictor_apply: 0 (default) = one CTA on every SM; other values are for
+ * experiments with kernels on other streams (store_vars runs next to the normal-equation build in Mapping.iterate). */
 void como_b200_predictor_stream_ctas(int32_t ctas);
 /* column sums of one keyframe's predictor (mean_log_depth_cost, gp_priors.py:99-106); M must divide 256. */
 int como_b200_predictor_colsum(const double* Knm, int64_t HW, int32_t M, double* colsum, void* stream);
@@ -229,6 +228,8 @@ int como_b200_kmat_predictor(const double* cov_img, int32_t B, int32_t H, int32_
  * H (n,n) row-major fp64 (only the lower triangle is read, H is not modified), g (n), x (n).  Tiled dataflow
  * Cholesky + fused forward substitution + backward substitution (csrc/chol.cu).  Non-PD input gives NaN. */
 size_t como_b200_chol_solve_workspace_bytes(int32_t n);
+/* Grid size of the factorisation (0 = one CTA per SM, the default). */
+void como_b200_chol_ctas(int32_t ctas);
 int como_b200_chol_solve(const double* H, const double* g, int32_t n, double* x, void* workspace,
                          size_t workspace_bytes, void* stream);
 
