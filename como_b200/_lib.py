@@ -25,7 +25,7 @@ lib = C.CDLL(LIB_PATH)
 class TrackLevel(C.Structure):
     _fields_ = [
         ("vals", C.c_void_p), ("P", C.c_void_p), ("J", C.c_void_p), ("mask", C.c_void_p), ("img", C.c_void_p),
-        ("n", C.c_int32), ("w", C.c_int32), ("h", C.c_int32), ("K", C.c_float * 9),
+        ("pack", C.c_void_p), ("n", C.c_int32), ("w", C.c_int32), ("h", C.c_int32), ("K", C.c_float * 9),
     ]
 
 
@@ -52,6 +52,8 @@ def _sig(name, restype, argtypes):
 abi_version = _sig("como_b200_abi_version", C.c_int, [])
 last_error = _sig("como_b200_last_error", C.c_char_p, [])
 track_workspace_bytes = _sig("como_b200_track_workspace_bytes", C.c_size_t, [C.c_int32, C.c_int32])
+track_pack_bytes = _sig("como_b200_track_pack_bytes", C.c_size_t, [C.c_int32])
+track_pack = _sig("como_b200_track_pack", C.c_int, [C.POINTER(TrackLevel), C.c_void_p])
 track_pyr = _sig(
     "como_b200_track_pyr", C.c_int,
     [C.POINTER(TrackLevel), C.c_int32, C.c_int32, C.POINTER(TrackTerm), C.c_void_p, C.c_void_p, C.c_void_p,
@@ -123,7 +125,7 @@ reproj_depth = _sig("como_b200_reproj_depth", C.c_int, [VP, I32, VP, C.POINTER(F
 
 # every symbol include/como_b200.h declares (checked by tests/test_abi.py without a GPU)
 DECLARED_SYMBOLS = [
-    "como_b200_abi_version", "como_b200_last_error", "como_b200_track_workspace_bytes", "como_b200_track_pyr",
+    "como_b200_abi_version", "como_b200_last_error", "como_b200_track_workspace_bytes", "como_b200_track_pack_bytes", "como_b200_track_pack", "como_b200_track_pyr",
     "como_b200_track_debug_candidate_cap",
     "como_b200_precalc_jacobians", "como_b200_median_workspace_bytes", "como_b200_median_f64", "como_b200_median_f32",
     "como_b200_subselect_pixels", "como_b200_ba_scaffold", "como_b200_predictor_apply", "como_b200_predictor_stream_ctas", "como_b200_predictor_colsum",

@@ -38,14 +38,19 @@ const char* como_b200_last_error(void);
  * torch ops under them (geometry/camera.py:57-68, frontend/photo_utils.py:9-31, lietorch SE3.exp).
  * One persistent cooperative launch runs the whole coarse-to-fine loop incl. termination tests.
  * ------------------------------------------------------------------------------------------ */
-/* vals, P, J and mask must be 16-byte aligned (they are streamed with bulk async copies). */
+/* A level as the reference passes it (vals, P, J, mask) plus `pack`: the same operands re-laid out ONCE per keyframe
+ * by como_b200_track_pack into 512-pixel tiles [P | I_ref | J cols 0..3 | J cols 4..5 | residual scratch] (masked and
+ * padding pixels carry NaN points), so that each GN pass streams one contiguous run per tile with the TMA unit and the
+ * residual travels inside the Jacobian tile instead of through a second array.  como_b200_track_pyr reads only
+ * pack, img, n, w, h, K; it WRITES the residual slots of `pack` (one launch at a time per pack). */
 typedef struct {
   const float* vals;   /* (n)     reference intensities I_i            [photo_tracking.py:24 vals_i]  */
   const float* P;      /* (n,3)   reference points in the KF frame     [Pi]                           */
-  const float* J;      /* (n,8)   dI/d[xi,a,b] as precalc_jacobians lays it out: col 6 = I_ref (read as
-                        *          such by the accumulation pass), col 7 ignored                      [dI_dT] */
+  const float* J;      /* (n,8)   dI/d[xi,a,b] as precalc_jacobians lays it out; cols 6 (rewritten every iteration by the
+                        *          reference, photo_tracking.py:125) and 7 (ones) are not read         [dI_dT] */
   const uint8_t* mask; /* (n) 0/1 or NULL: which points take part      [masks]                        */
   const float* img;    /* (h,w)   target image of this level           [img_j]                        */
+  void* pack;          /* como_b200_track_pack_bytes(n) bytes, 128-byte aligned, filled by como_b200_track_pack */
   int32_t n, w, h;
   float K[9];          /* row-major 3x3 intrinsics of this level       [intrinsics]                   */
 } como_b200_track_level_t;
@@ -59,11 +64,15 @@ typedef struct {
 
 /* per-iteration record written to `stats` (32 floats per iteration, iteration-major) */
 #define COMO_B200_TRACK_STAT_STRIDE 32
-/* [0]=level [1]=mean_sq_err [2]=grad_norm [3]=delta_norm [4]=sigma_r [5]=num_valid [6]=done [7]=reserved
+/* [0]=level [1]=mean_sq_err [2]=grad_norm [3]=delta_norm [4]=sigma_r [5]=num_valid [6]=done [7]=median path (0 scan, 1 predicted bin window)
  * [8..23]=Tji (row-major 4x4) and [24..25]=[a,b] this iteration was linearised at (tracking_iter's inputs,
  * photo_tracking.py:117) -- lets a checker replay every iteration from identical inputs; [26..31]=reserved */
 
 size_t como_b200_track_workspace_bytes(int32_t max_n, int32_t num_problems);
+/* Keyframe-side re-layout (once per keyframe and level; the reference's update_kf_reference, Tracking.py:243-379,
+ * is where vals / P / J / mask are produced).  Reads level->vals, P, J (cols 0..5), mask, n; writes level->pack. */
+size_t como_b200_track_pack_bytes(int32_t n);
+int como_b200_track_pack(const como_b200_track_level_t* level, void* stream);
 
 /* levels: HOST array [num_problems][num_levels] (coarsest first, as the reference stores pyramids).
  * T: DEVICE (num_problems,4,4) in/out Tji; aff: DEVICE (num_problems,2) in/out [a,b].
