@@ -37,5 +37,5 @@ int sm_count() {
 
 }  // namespace como
 
-extern "C" int como_b200_abi_version(void) { return 2; }
+extern "C" int como_b200_abi_version(void) { return 3; }
 extern "C" const char* como_b200_last_error(void) { return como::g_err; }

@@ -6,25 +6,28 @@
 //   como/odom/frontend/photo_utils.py:9-31, como/odom/backend/robust_loss.py:9-16.
 //
 // Layout of the launch: grid (G, B) -- G co-resident CTAs share one of B independent problems.  A CTA is
-// 8 consumer warps + 1 producer warp.  The producer warp streams the CTA's slice of the operands through a
-// ring of shared-memory stages with the TMA unit (cp.async.bulk + mbarrier, SASS UBLKCP), always as far
-// ahead as the ring allows, so the HBM stream never waits for the reductions:
-//   pass-1 tiles: P (12 B/px) + I_ref (4 B/px) + mask (1 B/px)      1024 px per stage
-//   pass-2 tiles: J (32 B/px; its column 6 is I_ref) + r (4 B/px)    512 px per stage
+// 4 consumer warps + 1 producer warp, up to 3 CTAs per SM.  The keyframe-side operands are re-laid out once per
+// keyframe (como_b200_track_pack) into 512-pixel tiles
+//   [ P 12 B/px | I_ref 4 | J cols 0..3 16 | J cols 4..5 8 | residual 4 ]      (masked / padding pixels: NaN points)
+// so that the producer warp streams ONE contiguous run per tile and pass with the TMA unit (cp.async.bulk + mbarrier,
+// SASS UBLKCP), always as far ahead as the ring allows:
+//   pass-1 stage: [P | I_ref]             8 KB, S1 stages
+//   pass-2 stage: [I_ref | J | residual] 16 KB, 2 stages (the same 32 KB of shared memory)
 // Per GN iteration (3 group barriers on the common path):
 //   pass 1   warp + bilinear gather (4 taps through the read-only path, the target image is L1/L2 resident)
-//            + residual r; r stays in shared memory when the slice fits (else an L2-resident scratch);
-//            2048-bin histogram of |r| with 1/64-octave bins over [2^-16, 2^16)          -> barrier
-//   median   the bin holding the lower-median rank is compacted (a few hundred candidates), barrier,
-//            every CTA selects the exact order statistic locally -> sigma = 1.4826 med.  Bins too
-//            crowded for the candidate list are narrowed by further 11-bit histogram passes (exact for
-//            any input, e.g. identical frames where every |r| is 0).
+//            + residual r -> the tile's residual slot (or shared memory when the whole slice fits);
+//            1024-bin histogram of |r| with 1/64-octave bins                             -> barrier
+//   median   exact lower median: the bin holding the rank is compacted (a scan of the residual slots; a few hundred
+//            candidates), barrier, every CTA selects the order statistic locally; crowded bins are narrowed by
+//            further histogram passes (exact for any input, e.g. identical frames where every |r| is 0)
 //   pass 2   Huber weights, J^T W J / J^T W r / error: registers -> warp shuffle -> CTA -> per-CTA row -> barrier
 //   solve    every CTA sums the rows in a fixed order (bitwise identical everywhere, run to run), solves the
 //            8x8 system (Cholesky), applies T <- T Exp(-d), a -= d6, b -= d7 and evaluates termination.
-// HBM traffic per pixel-iteration: P 12 + I_ref 4 + mask 1 + J 32 + target 4 B (algorithmic: the 52 B of
-// BASELINE.md) + the residual scratch (4 B written, 4 B read by the TMA unit, 4 B by the median scan) when the
-// batch's residuals do not fit L2.
+// HBM traffic per pixel-iteration: P 12 + I_ref 4 + J 24 + I_ref 4 + target 4 B (the 52 algorithmic bytes of
+// BASELINE.md count J as the reference stores it: 32 B) + the residual slot (4 B written, 4 B read by the median
+// scan, 4 B inside the pass-2 tile) when the batch's residuals do not fit L2.  (Capturing the keys around a predicted
+// median bin during pass 1 to skip the scan was built and measured: the median moves by tens of bins between the
+// iterations of a converging sequence, the prediction held for 12 % of them.)
 #include <cooperative_groups.h>
 #include <stdlib.h>
 #include <string.h>
@@ -39,20 +42,30 @@ namespace como {
 #ifndef TRK_MAX_OCC
 #define TRK_MAX_OCC 3
 #endif
-#ifndef TRK_STAGES
-#define TRK_STAGES 2
+#ifndef TRK_P1_DEPTH
+#define TRK_P1_DEPTH 1
+#endif
+#ifndef TRK_STAGES1
+#define TRK_STAGES1 4
 #endif
 constexpr int CONS_WARPS = TRK_CONS_WARPS;
 constexpr int CONS_THREADS = CONS_WARPS * 32;
 constexpr int TRK_THREADS = CONS_THREADS + 32;  // + producer warp
 constexpr int MAX_OCC = TRK_MAX_OCC;             // CTAs per SM the launch bounds allow
-constexpr int T1 = 512;                         // pixels per pass-1 stage (4 per consumer thread)
-constexpr int T2 = 512;                         // pixels per pass-2 stage (4 per consumer thread)
-constexpr int STAGE_BYTES = 18432;              // max(T1*(12+4+1), T2*(32+4))
-constexpr int T1_VALS_OFF = T1 * 12, T1_MASK_OFF = T1 * 16;
-constexpr int T2_R_OFF = T2 * 32;
-constexpr int STAGES = TRK_STAGES;
-constexpr int CHUNK_ALIGN = 512;  // slice = whole tiles (only the last slice of a level is ragged); 16-byte aligned starts
+constexpr int TILE = 512;                       // pixels per tile (4 per consumer thread)
+// packed keyframe tile (como_b200_track_pack): byte offsets inside one tile
+constexpr int PK_P_OFF = 0;                     // TILE x (X, Y, Z); NaN where masked or beyond n
+constexpr int PK_I_OFF = TILE * 12;             // TILE x I_ref
+constexpr int PK_JA_OFF = TILE * 16;            // TILE x float4: J columns 0..3
+constexpr int PK_JB_OFF = TILE * 32;            // TILE x float2: J columns 4..5
+constexpr int PK_R_OFF = TILE * 40;             // TILE x residual (written by pass 1, read inside the pass-2 tile)
+constexpr int PK_TILE_BYTES = TILE * 44;
+constexpr int P1_BYTES = TILE * 16;             // pass-1 stage = [P | I_ref]
+constexpr int P2_BYTES = TILE * 32;             // pass-2 stage = [I_ref | ja | jb | r], copied from PK_I_OFF on
+constexpr int ST2_I = 0, ST2_JA = TILE * 4, ST2_JB = TILE * 20, ST2_R = TILE * 28;
+constexpr int S1 = TRK_STAGES1, S2 = 2;
+constexpr int RING_BYTES = (S1 * P1_BYTES > S2 * P2_BYTES) ? S1 * P1_BYTES : S2 * P2_BYTES;
+constexpr int CHUNK_ALIGN = TILE;  // a CTA's slice = whole tiles
 constexpr int NACC = 45;          // 36 (upper triangle of 8x8) + 8 (gradient) + 1 (robust error)
 constexpr int NACC_PAD = 48;
 constexpr int HIST_BITS = 10;
@@ -80,20 +93,19 @@ struct TrackCtl {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// workspace: [level descriptors][TrackCtl x B][partial rows x B][residual scratch x B]
+// workspace: [level descriptors][TrackCtl x B][partial rows x B]
 struct TrackLayout {
-  size_t ctl_off, ctl_stride, partials_off, partials_stride, resid_off, resid_stride, total;
+  size_t ctl_off, ctl_stride, partials_off, partials_stride, total;
 };
 
 static TrackLayout track_layout(int max_n, int num_problems) {
+  (void)max_n;  // the residuals live in the packed tiles
   TrackLayout L;
   L.ctl_off = align_up((size_t)num_problems * COMO_B200_MAX_LEVELS * sizeof(como_b200_track_level_t), 256);
   L.ctl_stride = align_up(sizeof(TrackCtl), 256);
   L.partials_off = L.ctl_off + (size_t)num_problems * L.ctl_stride;
   L.partials_stride = align_up((size_t)MAX_GROUP * NACC_PAD * sizeof(double), 256);
-  L.resid_off = L.partials_off + (size_t)num_problems * L.partials_stride;
-  L.resid_stride = align_up(((size_t)max_n + 2 * T1) * sizeof(float), 256);  // padded: tiles store past n
-  L.total = L.resid_off + (size_t)num_problems * L.resid_stride;
+  L.total = L.partials_off + (size_t)num_problems * L.partials_stride;
   return L;
 }
 
@@ -131,40 +143,30 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return r;
 }
 
-// Visit every residual of this CTA's slice (shared-memory part [0, r_cap), L2 scratch beyond): f(key) for each
-// valid one.  Four-wide loads, four of them in flight per thread (the scratch is padded, see track_layout).
+// Visit every residual of this CTA's slice (tiles [0, r_cap / TILE) in shared memory, the others in the residual
+// slots of the packed tiles): f(key) for each valid one.  One float4 per thread and tile, four tiles in flight.
 template <class F>
-__device__ __forceinline__ void for_each_key(const float* s_r, const float* g_r, int r_cap, int len, F f) {
+__device__ __forceinline__ void for_each_key(const float* s_r, const uint8_t* pack, int r_cap, int ntiles, F f) {
   const int tid = threadIdx.x;
-  const int n_s = min(len, r_cap) & ~3, n_all = len & ~3;
-  for (int j = tid * 4; j < n_s; j += CONS_THREADS * 4) {
-    const float4 v = *reinterpret_cast<const float4*>(s_r + j);
+  const int ts = min(ntiles, r_cap / TILE);
+  auto visit = [&](const float4& v) {
     if (v.x == v.x) f(__float_as_uint(fabsf(v.x)));
     if (v.y == v.y) f(__float_as_uint(fabsf(v.y)));
     if (v.z == v.z) f(__float_as_uint(fabsf(v.z)));
     if (v.w == v.w) f(__float_as_uint(fabsf(v.w)));
-  }
-  const int g0 = (r_cap < len) ? r_cap : n_all;  // r_cap is a multiple of 4
-  for (int j0 = g0 + tid * 4; j0 < n_all; j0 += CONS_THREADS * 16) {
+  };
+  for (int t = 0; t < ts; ++t) visit(*(reinterpret_cast<const float4*>(s_r + t * TILE) + tid));
+  const float qn = __int_as_float(0x7fc00000);
+  for (int t0 = ts; t0 < ntiles; t0 += 4) {
     float4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u * CONS_THREADS * 4;
-      v[u] = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
-                         __int_as_float(0x7fc00000));
-      if (j < n_all) v[u] = __ldcg(reinterpret_cast<const float4*>(g_r + j));
+      v[u] = make_float4(qn, qn, qn, qn);
+      if (t0 + u < ntiles)
+        v[u] = __ldcg(reinterpret_cast<const float4*>(pack + (size_t)(t0 + u) * PK_TILE_BYTES + PK_R_OFF) + tid);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (v[u].x == v[u].x) f(__float_as_uint(fabsf(v[u].x)));
-      if (v[u].y == v[u].y) f(__float_as_uint(fabsf(v[u].y)));
-      if (v[u].z == v[u].z) f(__float_as_uint(fabsf(v[u].z)));
-      if (v[u].w == v[u].w) f(__float_as_uint(fabsf(v[u].w)));
-    }
-  }
-  for (int j = n_all + tid; j < len; j += CONS_THREADS) {  // ragged end of the last slice
-    const float r = (j < r_cap) ? s_r[j] : __ldcg(g_r + j);
-    if (r == r) f(__float_as_uint(fabsf(r)));
+    for (int u = 0; u < 4; ++u) visit(v[u]);
   }
 }
 
@@ -175,7 +177,7 @@ __device__ __forceinline__ unsigned first_bin(unsigned key) {
 
 __device__ __forceinline__ int clog2(unsigned w) { return w <= 1u ? 0 : 32 - __clz(w - 1u); }
 
-// Consumer-block search of the bin holding 0-based rank k in a 2048-bin histogram (shared, or global read
+// Consumer-block search of the bin holding 0-based rank k in a 1024-bin histogram (shared, or global read
 // through L2).  k_is_median: k = (total-1)/2 (torch.median's lower median).  s_out: [bin, rank in bin, count in bin, total].
 __device__ __forceinline__ void select_bin(const unsigned* hist, bool global, unsigned k, bool k_is_median,
                                            unsigned* s_warp, unsigned* s_out) {
@@ -260,67 +262,21 @@ __device__ __forceinline__ SliceInfo slice_of(int N, int G, int c) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// producer warp: one tile = wait for the stage to be released, tail elements by plain stores, then
-// one arrive.expect_tx + up to three bulk copies
+// producer (one elected lane): wait for the stage to be released, one arrive.expect_tx + one bulk copy.
+// Operands are streamed once per pass: evict-first in L2.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void produce_tile1(uint8_t* stage, unsigned long long* full, unsigned long long* empty,
-                                              unsigned n, const como_b200_track_level_t& lv, int i0, int cnt) {
-  const int lane = threadIdx.x & 31;
-  mbar_wait(empty, ((n / STAGES) & 1u) ^ 1u);
-  const int bulk = cnt & ~15;
-  const float* P = lv.P + 3 * (size_t)i0;
-  const float* V = lv.vals + i0;
-  for (int j = bulk + lane; j < cnt; j += 32) {
-    float* sp = reinterpret_cast<float*>(stage) + 3 * j;
-    sp[0] = P[3 * j];
-    sp[1] = P[3 * j + 1];
-    sp[2] = P[3 * j + 2];
-    reinterpret_cast<float*>(stage + T1_VALS_OFF)[j] = V[j];
-    if (lv.mask) (stage + T1_MASK_OFF)[j] = lv.mask[i0 + j];
-  }
-  __syncwarp();
-  if (lane == 0) {
-    const unsigned bytes = (unsigned)bulk * (lv.mask ? 17u : 16u);
-    if (bytes) {
-      mbar_expect_tx(full, bytes);
-      // streamed once per pass: evict-first in L2, so that the residual scratch (re-read twice) stays resident
-      const unsigned long long pol = l2_policy_evict_first();
-      bulk_g2s_hint(stage, P, (unsigned)bulk * 12u, full, pol);
-      bulk_g2s_hint(stage + T1_VALS_OFF, V, (unsigned)bulk * 4u, full, pol);
-      if (lv.mask) bulk_g2s_hint(stage + T1_MASK_OFF, lv.mask + i0, (unsigned)bulk, full, pol);
-    } else {
-      mbar_arrive(full);
-    }
-  }
+__device__ __forceinline__ void produce(uint8_t* stage, unsigned long long* full, unsigned long long* empty,
+                                        unsigned parity, const uint8_t* src, unsigned bytes, unsigned long long pol) {
+  mbar_wait(empty, parity ^ 1u);
+  mbar_expect_tx(full, bytes);
+  bulk_g2s_hint(stage, src, bytes, full, pol);
 }
 
-// r_src: this tile's residuals in the L2 scratch (written by this CTA's consumers in pass 1 through the generic
-// proxy, fenced + signalled on p1_done before the producer gets here), or nullptr when they live in shared memory.
-__device__ __forceinline__ void produce_tile2(uint8_t* stage, unsigned long long* full, unsigned long long* empty,
-                                              unsigned n, const como_b200_track_level_t& lv, int i0, int cnt,
-                                              const float* r_src) {
-  const int lane = threadIdx.x & 31;
-  mbar_wait(empty, ((n / STAGES) & 1u) ^ 1u);
-  const int bulk = cnt & ~3;
-  const float* J = lv.J + 8 * (size_t)i0;
-  for (int j = bulk + (lane >> 3); j < cnt; j += 4) {
-    reinterpret_cast<float*>(stage)[8 * j + (lane & 7)] = J[8 * j + (lane & 7)];
-    if ((lane & 7) == 0 && r_src) reinterpret_cast<float*>(stage + T2_R_OFF)[j] = __ldcg(r_src + j);
-  }
-  __syncwarp();
-  if (lane == 0) {
-    if (bulk) {
-      mbar_expect_tx(full, (unsigned)bulk * (r_src ? 36u : 32u));
-      const unsigned long long pol = l2_policy_evict_first();
-      bulk_g2s_hint(stage, J, (unsigned)bulk * 32u, full, pol);
-      if (r_src) bulk_g2s(stage + T2_R_OFF, r_src, (unsigned)bulk * 4u, full);
-    } else {
-      mbar_arrive(full);
-    }
-  }
-}
-
+#ifdef TRK_MAXNREG
+__global__ void __maxnreg__(TRK_MAXNREG)
+#else
 __global__ void __launch_bounds__(TRK_THREADS, MAX_OCC)
+#endif
 track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num_levels,
                  como_b200_track_term_t term, float* __restrict__ T_io, float* __restrict__ aff_io,
                  float* __restrict__ stats, int* __restrict__ num_iters, uint8_t* __restrict__ ws,
@@ -333,20 +289,19 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
 
   TrackCtl* ctl = reinterpret_cast<TrackCtl*>(ws + lay.ctl_off + (size_t)prob * lay.ctl_stride);
   double* partials = reinterpret_cast<double*>(ws + lay.partials_off + (size_t)prob * lay.partials_stride);
-  float* g_resid = reinterpret_cast<float*>(ws + lay.resid_off + (size_t)prob * lay.resid_stride);
   const como_b200_track_level_t* levels = levels_all + (size_t)prob * COMO_B200_MAX_LEVELS;
 
   extern __shared__ __align__(128) uint8_t dsm[];
   uint8_t* ring = dsm;
-  float* s_r = reinterpret_cast<float*>(dsm + STAGES * STAGE_BYTES);
+  float* s_r = reinterpret_cast<float*>(dsm + RING_BYTES);
 
-  __shared__ __align__(16) unsigned s_hist[HIST_BINS];
+  __shared__ __align__(16) unsigned s_hist[HIST_BINS + 32];  // [HIST_BINS + lane]: spare bins for invalid pixels
   __shared__ __align__(16) unsigned s_cand[CAND_CAP];
   __shared__ double s_red[CONS_WARPS][NACC_PAD];
   __shared__ double s_acc[NACC_PAD];
   __shared__ double s_chol[64];
   __shared__ double s_delta[8];
-  __shared__ unsigned long long full_bar[STAGES], empty_bar[STAGES], p1_done_bar;
+  __shared__ unsigned long long full1[S1], empty1[S1], full2[S2], empty2[S2], p1_done_bar;
   __shared__ float s_T[16];
   __shared__ float s_aff[2];
   __shared__ float s_Pm[12];
@@ -360,9 +315,13 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
   if (tid < 16) s_T[tid] = T_io[prob * 16 + tid];
   if (tid < 2) s_aff[tid] = aff_io[prob * 2 + tid];
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CONS_WARPS);
+    for (int s = 0; s < S1; ++s) {
+      mbar_init(&full1[s], 1);
+      mbar_init(&empty1[s], CONS_WARPS);
+    }
+    for (int s = 0; s < S2; ++s) {
+      mbar_init(&full2[s], 1);
+      mbar_init(&empty2[s], CONS_WARPS);
     }
     mbar_init(&p1_done_bar, CONS_WARPS);
     s_cnt = 0;
@@ -372,29 +331,37 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
   __syncthreads();
 
   // ============================================================================================
-  // producer warp
+  // producer warp.  The two passes use separate barrier sets over the same ring memory; they never overlap in time:
+  // pass-2 copies start after p1_done (every consumer warp is through pass 1), pass-1 copies of the next iteration
+  // after the iteration's closing __syncthreads.
   // ============================================================================================
   if (wid == CONS_WARPS) {
-    unsigned n = 0;
+    unsigned n1 = 0, n2 = 0;
     int pit = 0;
+    const unsigned long long pol = l2_policy_evict_first();
     for (int l = 0; l < num_levels; ++l) {
       const como_b200_track_level_t lv = levels[l];
       if (lv.n <= 0) continue;
       const SliceInfo sl = slice_of(lv.n, G, c);
       if (c >= sl.active) continue;   // this CTA sits the level out (its consumers skip it too)
+      const uint8_t* pack = reinterpret_cast<const uint8_t*>(lv.pack) + (size_t)(sl.begin / TILE) * PK_TILE_BYTES;
+      const int ntiles = (sl.len + TILE - 1) / TILE;
+      const int ts = min(ntiles, r_cap / TILE);   // tiles whose residuals stay in shared memory
       for (;; ++pit) {
-        for (int t0 = 0; t0 < sl.len; t0 += T1, ++n) {
-          const unsigned s = n % STAGES;
-          produce_tile1(ring + s * STAGE_BYTES, &full_bar[s], &empty_bar[s], n, lv, sl.begin + t0, min(T1, sl.len - t0));
+        if (lane == 0) {
+          for (int t = 0; t < ntiles; ++t, ++n1) {
+            const unsigned s = n1 % S1;
+            produce(ring + s * P1_BYTES, &full1[s], &empty1[s], (n1 / S1) & 1u, pack + (size_t)t * PK_TILE_BYTES, P1_BYTES, pol);
+          }
+          // pass-2 tiles carry the residuals pass 1 wrote into the packed tiles: wait until this CTA has written them all
+          mbar_wait(&p1_done_bar, (unsigned)pit & 1u);
+          for (int t = 0; t < ntiles; ++t, ++n2) {
+            const unsigned s = n2 % S2;
+            produce(ring + s * P2_BYTES, &full2[s], &empty2[s], (n2 / S2) & 1u, pack + (size_t)t * PK_TILE_BYTES + PK_I_OFF,
+                    t < ts ? (unsigned)ST2_R : (unsigned)P2_BYTES, pol);
+          }
         }
-        // pass-2 tiles carry the residuals pass 1 left in the L2 scratch: wait until this CTA has written them all
-        mbar_wait(&p1_done_bar, (unsigned)pit & 1u);
-        const float* g_r = g_resid + sl.begin;
-        for (int t0 = 0; t0 < sl.len; t0 += T2, ++n) {
-          const unsigned s = n % STAGES;
-          produce_tile2(ring + s * STAGE_BYTES, &full_bar[s], &empty_bar[s], n, lv, sl.begin + t0, min(T2, sl.len - t0),
-                        t0 < r_cap ? nullptr : g_r + t0);
-        }
+        __syncwarp();
         __syncthreads();  // the consumers' verdict for this iteration (flag double-buffered by iteration parity)
         if (s_done[pit & 1]) {
           ++pit;
@@ -409,7 +376,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
   // consumer warps
   // ============================================================================================
   unsigned lev_epoch = 0;
-  unsigned n = 0;  // tile counter, mirrors the producer's
+  unsigned n1 = 0, n2 = 0;  // tile counters, mirror the producer's
   int total_iter = 0;   // iterations of the problem so far (stats index, parity of the problem's global buffers)
   int lit = 0;          // iterations THIS CTA took part in (parity of its own verdict flag / p1_done phase)
   const int stats_cap = num_levels * term.max_iter;
@@ -433,8 +400,8 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
       consumer_sync();
       continue;
     }
-    const float xmax = (float)(w - 1), ymax = (float)(h - 1);
-    float* g_r = g_resid + sl.begin;  // residual of slice pixel j: s_r[j] if j < r_cap else g_r[j]
+    uint8_t* pack = reinterpret_cast<uint8_t*>(lv.pack) + (size_t)(sl.begin / TILE) * PK_TILE_BYTES;
+    const int ntiles = (sl.len + TILE - 1) / TILE;
 
     double mse_prev = INFINITY;
     int it = 0;
@@ -451,47 +418,42 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
       }
       if (tid == 12) s_ea = expf(-s_aff[0]);
       consumer_sync();
-      const float p00 = s_Pm[0], p01 = s_Pm[1], p02 = s_Pm[2], p03 = s_Pm[3];
-      const float p10 = s_Pm[4], p11 = s_Pm[5], p12 = s_Pm[6], p13 = s_Pm[7];
-      const float p20 = s_Pm[8], p21 = s_Pm[9], p22 = s_Pm[10], p23 = s_Pm[11];
       const float ea = s_ea, bb = s_aff[1];
 
       // ---- pass 1: warp, gather, residual, first histogram.  Four pixels per thread and tile, software pipelined
       // over two tiles: the 16 bilinear taps of tile t+1 are issued before the residuals of tile t are formed, so a
-      // warp always has a tile's worth of gathers in flight (3 CTAs per SM leave almost no L1: the taps are L2
-      // hits, ~1 us under load).
-      constexpr int PB = T1 / CONS_THREADS;
-      const float2 A2x = make_float2(2.0f / (float)w, 2.0f / (float)h), A1 = make_float2(1.0f / (float)w, 1.0f / (float)h);
+      // warp always has a tile's worth of gathers in flight.
+      constexpr int PB = TILE / CONS_THREADS;
       const float2 wh2 = make_float2((float)w, (float)h);
+      const float2 A1 = make_float2(1.0f / wh2.x, 1.0f / wh2.y);
       const float* __restrict__ img = lv.img;
-      const bool has_mask = lv.mask != nullptr;
       struct P1 {
-        float fxs[PB], fys[PB], vref[PB], v00[PB], v01[PB], v10[PB], v11[PB];
-        bool valid[PB];
+        float fxs[PB], fys[PB], vref[PB], v00[PB], v01[PB], v10[PB], v11[PB];   // vref = NaN marks an invalid pixel
       };
       // stage A: operands -> warped coordinates -> taps in flight
-      auto gather = [&](int t0, P1& st) {
-        const unsigned s = n % STAGES;
-        const uint8_t* stage = ring + s * STAGE_BYTES;
-        const int cnt = min(T1, sl.len - t0);
-        mbar_wait(&full_bar[s], (n / STAGES) & 1u);
-        ++n;
+      auto gather = [&](P1& st) {
+        const unsigned s = n1 % S1;
+        const uint8_t* stage = ring + s * P1_BYTES;
+        mbar_wait(&full1[s], (n1 / S1) & 1u);
+        ++n1;
         const float* sP = reinterpret_cast<const float*>(stage) + 3 * tid;
-        const float* sV = reinterpret_cast<const float*>(stage + T1_VALS_OFF) + tid;
-        const uint8_t* sM = stage + T1_MASK_OFF + tid;
+        const float* sV = reinterpret_cast<const float*>(stage + PK_I_OFF) + tid;
         float X[PB], Y[PB], Z[PB];
-        bool use[PB];
 #pragma unroll
         for (int k = 0; k < PB; ++k) {
-          // beyond cnt the stage holds stale data: computed, never used
-          use[k] = (tid + k * CONS_THREADS < cnt);
-          if (has_mask) use[k] = use[k] && (sM[k * CONS_THREADS] != 0);
           X[k] = sP[3 * k * CONS_THREADS + 0];
           Y[k] = sP[3 * k * CONS_THREADS + 1];
           Z[k] = sP[3 * k * CONS_THREADS + 2];
           st.vref[k] = sV[k * CONS_THREADS];
         }
-        stage_release(&empty_bar[s]);  // operands are in registers (loads performed): release the stage early
+        // projection matrix of this iteration: broadcast loads, short-lived (12 registers less across the pipeline)
+        const volatile float* vPm = s_Pm;   // volatile: keeps the compiler from hoisting the loads back out of the loop
+        const float p00 = vPm[0], p01 = vPm[1], p02 = vPm[2], p03 = vPm[3];
+        const float p10 = vPm[4], p11 = vPm[5], p12 = vPm[6], p13 = vPm[7];
+        const float p20 = vPm[8], p21 = vPm[9], p22 = vPm[10], p23 = vPm[11];
+        const float2 A2x = __fadd2_rn(A1, A1);   // 2/w, 2/h: doubling is exact
+        const float xmax = wh2.x - 1.0f, ymax = wh2.y - 1.0f;
+        stage_release(&empty1[s]);  // operands are in registers (loads performed): release the stage early
 #pragma unroll
         for (int k = 0; k < PB; ++k) {
           const float hx = p00 * X[k] + p01 * Y[k] + p02 * Z[k] + p03;
@@ -504,7 +466,9 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
           const float2 r2 = make_float2(r0, r0), h2 = make_float2(hx, hy);
           float2 q2 = __fmul2_rn(h2, r2);
           q2 = __ffma2_rn(__ffma2_rn(make_float2(-hz, -hz), q2, h2), r2, q2);
-          st.valid[k] = use[k] && (q2.x >= 1.0f) && (q2.x < xmax) && (q2.y >= 1.0f) && (q2.y < ymax) && (hz > 0.0f);
+          // masked and padding pixels carry NaN points: every comparison fails
+          const bool valid = (q2.x >= 1.0f) && (q2.x < xmax) && (q2.y >= 1.0f) && (q2.y < ymax) && (hz > 0.0f);
+          if (!valid) st.vref[k] = __int_as_float(0x7fc00000);
           // the reference maps pixel coords to [-1,1] and grid_sample maps them back; reproduce that fp32 round
           // trip step by step (coords.py:18-20, grid_sample unnormalize, align_corners=False): its rounding moves
           // a coordinate by up to w * 6e-8 px, which is what one pixel's residual -- the median -- is sensitive to
@@ -518,32 +482,41 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
           const float x0f = floorf(t.x), y0f = floorf(t.y);
           st.fxs[k] = t.x - x0f;
           st.fys[k] = t.y - y0f;
-          // valid => 1 <= x0 <= w-2 and 1 <= y0 <= h-2: the four taps are inside the image (photo_utils.py:9-31);
-          // invalid points read the first pixels (unconditional loads: no branches), their result is discarded
-          const int off = st.valid[k] ? ((int)y0f * w + (int)x0f) : 0;
+          // valid => 1 <= x < w-1 and 1 <= y < h-1 (photo_utils.py:9-31); invalid points read the first pixels
+          // (unconditional loads: no branches), their result is discarded
+          // The fp32 round trip can land a coordinate that is a hair below w-1 / h-1 exactly on it: the far taps
+          // then have weight 0 (grid_sample reads them as padding) and must not be fetched from beyond the row /
+          // the image, so their offsets collapse onto the near taps.
+          const int xi = (int)x0f, yi = (int)y0f;
+          const int off = valid ? (yi * w + xi) : 0;
+          const int dx = (xi < w - 1) ? 1 : 0, dy = (yi < h - 1) ? w : 0;
           const float* p0 = img + off;
-          const float* p1 = p0 + w;
+          const float* p1 = p0 + dy;
           st.v00[k] = __ldg(p0);
-          st.v01[k] = __ldg(p0 + 1);
+          st.v01[k] = __ldg(p0 + dx);
           st.v10[k] = __ldg(p1);
-          st.v11[k] = __ldg(p1 + 1);
+          st.v11[k] = __ldg(p1 + dx);
         }
       };
       // stage B: interpolate, residual, histogram, store r
-      auto finish = [&](int t0, const P1& st) {
-        const bool tile_in_smem = (t0 < r_cap);  // r_cap is a multiple of T1
-        float* r_tile = (tile_in_smem ? (s_r + t0) : (g_r + t0)) + tid;
+      auto finish = [&](int t, const P1& st) {
+        const bool tile_in_smem = (t * TILE < r_cap);  // r_cap is a multiple of TILE
+        float* r_tile = (tile_in_smem ? (s_r + t * TILE) : reinterpret_cast<float*>(pack + (size_t)t * PK_TILE_BYTES + PK_R_OFF)) + tid;
         float rout[PB];
 #pragma unroll
         for (int k = 0; k < PB; ++k) {
           const float top = st.v00[k] + st.fxs[k] * (st.v01[k] - st.v00[k]);
           const float bot = st.v10[k] + st.fxs[k] * (st.v11[k] - st.v10[k]);
           const float v = top + st.fys[k] * (bot - top);
-          const float r = (ea * v + bb) - st.vref[k];
-          if (st.valid[k]) atomicAdd(&s_hist[first_bin(__float_as_uint(fabsf(r)))], 1u);
-          rout[k] = st.valid[k] ? r : __int_as_float(0x7fc00000);
+          const float r = (ea * v + bb) - st.vref[k];   // NaN for invalid pixels
+          const unsigned key = __float_as_uint(fabsf(r));
+          const bool valid = (r == r);
+          const unsigned bin = first_bin(key);
+          // branch-free: invalid pixels count into spare bins
+          atomicAdd(&s_hist[valid ? bin : (unsigned)(HIST_BINS + lane)], 1u);
+          rout[k] = r;
         }
-        if (tile_in_smem) {  // rows beyond cnt stay inside the padded slice storage
+        if (tile_in_smem) {
 #pragma unroll
           for (int k = 0; k < PB; ++k) r_tile[k * CONS_THREADS] = rout[k];
         } else {
@@ -552,20 +525,28 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         }
       };
       {
+#if TRK_P1_DEPTH == 2
         // two tiles in flight per warp (a third one costs more in register spills than it hides: measured)
         P1 sa, sb;
-        if (sl.len > 0) gather(0, sa);
-        for (int t0 = 0; t0 < sl.len; t0 += 2 * T1) {
-          const bool more1 = t0 + T1 < sl.len;
-          if (more1) gather(t0 + T1, sb);
-          finish(t0, sa);
+        if (ntiles > 0) gather(sa);
+        for (int t = 0; t < ntiles; t += 2) {
+          const bool more1 = t + 1 < ntiles;
+          if (more1) gather(sb);
+          finish(t, sa);
           if (more1) {
-            if (t0 + 2 * T1 < sl.len) gather(t0 + 2 * T1, sa);
-            finish(t0 + T1, sb);
+            if (t + 2 < ntiles) gather(sa);
+            finish(t + 1, sb);
           }
         }
+#else
+        P1 sa;
+        for (int t = 0; t < ntiles; ++t) {
+          gather(sa);
+          finish(t, sa);
+        }
+#endif
       }
-      // residuals in the L2 scratch are read back by the TMA unit in pass 2 (async proxy): fence, then signal the producer
+      // the residual slots are read back by the TMA unit in pass 2 (async proxy): fence, then signal the producer
       asm volatile("fence.proxy.async;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&p1_done_bar);
@@ -589,13 +570,14 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
           klo = KEY_LO + ((bin - 1u) << KEY_SHIFT);
           khi = klo + (1u << KEY_SHIFT);
         }
+        bool have_cands = false;
         int pass = 0;
         while (khi - klo > 1u) {
-          if (cnt_in <= (unsigned)cand_cap) {
+          if (!have_cands && cnt_in <= (unsigned)cand_cap) {
             // compact this CTA's candidates, append them to the problem's list, then select locally
             {
               const unsigned wdt = khi - klo;
-              for_each_key(s_r, g_r, r_cap, sl.len, [&](unsigned key) {
+              for_each_key(s_r, pack, r_cap, ntiles, [&](unsigned key) {
                 if (key - klo < wdt) s_cand[atomicAdd(&s_cnt, 1u)] = key;
               });
             }
@@ -611,6 +593,9 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
             }
             if (tid == 0) s_cnt = 0;
             consumer_sync();
+            have_cands = true;
+          }
+          if (have_cands) {
             while (khi - klo > 1u) {
               const int sh = max(0, clog2(khi - klo) - HIST_BITS);
               for (unsigned j = tid; j < cnt_in; j += CONS_THREADS) {
@@ -633,7 +618,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
           const int sh = max(0, clog2(khi - klo) - HIST_BITS);
           {
             const unsigned wdt = khi - klo;
-            for_each_key(s_r, g_r, r_cap, sl.len, [&](unsigned key) {
+            for_each_key(s_r, pack, r_cap, ntiles, [&](unsigned key) {
               if (key - klo < wdt) atomicAdd(&s_hist[(key - klo) >> sh], 1u);
             });
           }
@@ -650,10 +635,8 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         sigma = 1.4826f * __uint_as_float(klo);
       }
 
-      // ---- pass 2: robust weights + normal equations.  Four pixels per thread and tile; the residuals of the
-      // next tile are fetched (L2 scratch) while this one is accumulated.  The 8x8 rank-one update runs on packed
-      // fp32 pairs (fma.rn.f32x2): accumulator pair (H[2a][m], H[2a+1][m]) += (w j_2a, w j_2a+1) * (j_m, j_m).
-      constexpr int PB2 = T2 / CONS_THREADS;
+      // ---- pass 2: robust weights + normal equations.  Four pixels per thread and tile.  The 8x8 rank-one update
+      // runs on packed fp32 pairs (fma.rn.f32x2): accumulator pair (H[2a][m], H[2a+1][m]) += (w j_2a, w j_2a+1) * (j_m, j_m).
       float2 A2[20], G2[4];
       float errs = 0.0f;
 #pragma unroll
@@ -661,36 +644,38 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
 #pragma unroll
       for (int k = 0; k < 4; ++k) G2[k] = make_float2(0.f, 0.f);
       const float inv_sigma = 1.0f / sigma;
-      const float qnan = __int_as_float(0x7fc00000);
-      for (int t0 = 0; t0 < sl.len; t0 += T2, ++n) {
-        const unsigned s = n % STAGES;
-        const uint8_t* stage = ring + s * STAGE_BYTES;
-        mbar_wait(&full_bar[s], (n / STAGES) & 1u);
-        const float4* sJ = reinterpret_cast<const float4*>(stage) + 2 * tid;
-        const float* sR = (t0 < r_cap ? (s_r + t0) : reinterpret_cast<const float*>(stage + T2_R_OFF)) + tid;
-        const int left = sl.len - t0 - tid;
-        float rr[PB2];
-        float4 ja[PB2], jb[PB2];
+      for (int t = 0; t < ntiles; ++t, ++n2) {
+        const unsigned s = n2 % S2;
+        const uint8_t* stage = ring + s * P2_BYTES;
+        mbar_wait(&full2[s], (n2 / S2) & 1u);
+        const float* sI = reinterpret_cast<const float*>(stage + ST2_I) + tid;
+        const float4* sJA = reinterpret_cast<const float4*>(stage + ST2_JA) + tid;
+        const float2* sJB = reinterpret_cast<const float2*>(stage + ST2_JB) + tid;
+        const float* sR = (t * TILE < r_cap ? (s_r + t * TILE) : reinterpret_cast<const float*>(stage + ST2_R)) + tid;
+        float rr[PB], iref[PB];
+        float4 ja[PB];
+        float2 jb[PB];
 #pragma unroll
-        for (int k = 0; k < PB2; ++k) {  // rows beyond the tile's count hold stale data: their r is forced to NaN
-          rr[k] = (k * CONS_THREADS < left) ? sR[k * CONS_THREADS] : qnan;
-          ja[k] = sJ[2 * k * CONS_THREADS];
-          jb[k] = sJ[2 * k * CONS_THREADS + 1];
+        for (int k = 0; k < PB; ++k) {  // padding and masked pixels: pass 1 left NaN
+          rr[k] = sR[k * CONS_THREADS];
+          iref[k] = sI[k * CONS_THREADS];
+          ja[k] = sJA[k * CONS_THREADS];
+          jb[k] = sJB[k * CONS_THREADS];
         }
-        stage_release(&empty_bar[s]);
+        stage_release(&empty2[s]);
 #pragma unroll
-        for (int k = 0; k < PB2; ++k) {
+        for (int k = 0; k < PB; ++k) {
           const float r = rr[k];
           if (r == r) {
-            // column 6 of J as passed in is I_ref (precalc_jacobians); this iteration's column 6 is -e^{-a} I_j
-            const float mt = (bb - r) - jb[k].z;
+            // this iteration's column 6 is -e^{-a} I_j = (b - r) - I_ref (photo_tracking.py:124-127)
+            const float mt = (bb - r) - iref[k];
             const float wr = r * inv_sigma;
             const float a = fabsf(wr);
             const float wgt = (a < HUBER_K) ? 1.0f : HUBER_K * rcp_approx(a);
             errs += wgt * wr * wr;
             const float2 w2 = make_float2(wgt, wgt);
             const float2 W[4] = {__fmul2_rn(w2, make_float2(ja[k].x, ja[k].y)), __fmul2_rn(w2, make_float2(ja[k].z, ja[k].w)),
-                                 __fmul2_rn(w2, make_float2(jb[k].x, jb[k].y)), __fmul2_rn(w2, make_float2(mt, 1.0f))};
+                                 __fmul2_rn(w2, jb[k]), __fmul2_rn(w2, make_float2(mt, 1.0f))};
             const float2 D[8] = {make_float2(ja[k].x, ja[k].x), make_float2(ja[k].y, ja[k].y), make_float2(ja[k].z, ja[k].z),
                                  make_float2(ja[k].w, ja[k].w), make_float2(jb[k].x, jb[k].x), make_float2(jb[k].y, jb[k].y),
                                  make_float2(mt, mt),           make_float2(1.0f, 1.0f)};
@@ -869,26 +854,27 @@ static int track_config(int num_problems, int max_n, TrackLaunchCfg* cfg) {
   const char* e_occ = getenv("COMO_B200_TRACK_OCC");
   const char* e_g = getenv("COMO_B200_TRACK_G");
   const long long want = (long long)num_problems * (g_want < 8 ? g_want : 8);
-  int occ = want > 2LL * sms ? 3 : (want > sms ? 2 : 1);
+  int occ = (int)((want + sms - 1) / sms);   // CTAs per SM wanted: 1 .. MAX_OCC
+  occ = occ < 1 ? 1 : (occ > MAX_OCC ? MAX_OCC : occ);
   if (e_occ && atoi(e_occ) >= 1) occ = atoi(e_occ) > MAX_OCC ? MAX_OCC : atoi(e_occ);
   for (; occ >= 1; --occ) {
     const int per_cta = (occ == 1) ? smem_optin : (smem_sm / occ - 1024);
     long long dyn = (long long)per_cta - (long long)fa.sharedSizeBytes;
     if (dyn > smem_optin - (long long)fa.sharedSizeBytes) dyn = smem_optin - (long long)fa.sharedSizeBytes;
-    const long long r_bytes = dyn - (long long)STAGES * STAGE_BYTES;
+    const long long r_bytes = dyn - (long long)RING_BYTES;
     if (r_bytes < 0) continue;
     // Residual slice in shared memory only if ALL of it fits (single-sequence launches: a few thousand pixels per
     // CTA); otherwise none of it: shared memory not claimed here stays L1, and the bilinear taps live on L1 hits
-    // (measured: +7 % batched throughput with r_cap = 0 and a 2-stage ring against a full-size carve-out).
-    int r_cap = (int)(r_bytes / 4) / T1 * T1;
+    // (measured: +7 % batched throughput with r_cap = 0 and a small ring against a full-size carve-out).
+    int r_cap = (int)(r_bytes / 4) / TILE * TILE;
     {
       const int g_guess = (g_want < sms * occ / (num_problems > 0 ? num_problems : 1)) ? g_want : sms * occ / (num_problems > 0 ? num_problems : 1);
       int chunk = (max_n + (g_guess > 0 ? g_guess : 1) - 1) / (g_guess > 0 ? g_guess : 1);
       chunk = (chunk + CHUNK_ALIGN - 1) / CHUNK_ALIGN * CHUNK_ALIGN;
       r_cap = (chunk <= r_cap) ? chunk : 0;
     }
-    if (const char* e_rc = getenv("COMO_B200_TRACK_RCAP")) r_cap = atoi(e_rc) / T1 * T1;  // tuning only
-    const size_t dyn_smem = (size_t)STAGES * STAGE_BYTES + (size_t)r_cap * 4;
+    if (const char* e_rc = getenv("COMO_B200_TRACK_RCAP")) r_cap = atoi(e_rc) / TILE * TILE;  // tuning only
+    const size_t dyn_smem = (size_t)RING_BYTES + (size_t)r_cap * 4;
     cudaFuncSetAttribute(track_pyr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, track_pyr_kernel, TRK_THREADS, dyn_smem);
@@ -908,6 +894,39 @@ static int track_config(int num_problems, int max_n, TrackLaunchCfg* cfg) {
 }
 
 static int g_track_cand_cap = CAND_CAP;
+
+// ---------------------------------------------------------------------------------------------
+// keyframe-side re-layout: (vals, P, J, mask) -> 512-pixel tiles [P | I_ref | J 0..3 | J 4..5 | residual]
+// ---------------------------------------------------------------------------------------------
+__global__ void track_pack_kernel(const float* __restrict__ vals, const float* __restrict__ P, const float* __restrict__ J,
+                                  const uint8_t* __restrict__ mask, int n, uint8_t* __restrict__ pack) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // slot index over whole tiles
+  const int ntiles = (n + TILE - 1) / TILE;
+  if (i >= ntiles * TILE) return;
+  const int t = i / TILE, j = i % TILE;
+  uint8_t* tile = pack + (size_t)t * PK_TILE_BYTES;
+  const float qn = __int_as_float(0x7fc00000);
+  const bool use = (i < n) && (mask == nullptr || mask[i] != 0);
+  float X = qn, Y = qn, Z = qn, I = 0.0f;
+  float4 ja = make_float4(0.f, 0.f, 0.f, 0.f);
+  float2 jb = make_float2(0.f, 0.f);
+  if (use) {
+    X = P[3 * (size_t)i];
+    Y = P[3 * (size_t)i + 1];
+    Z = P[3 * (size_t)i + 2];
+    I = vals[i];
+    ja = *reinterpret_cast<const float4*>(J + 8 * (size_t)i);
+    jb = *reinterpret_cast<const float2*>(J + 8 * (size_t)i + 4);
+  }
+  float* tp = reinterpret_cast<float*>(tile + PK_P_OFF) + 3 * j;
+  tp[0] = X;
+  tp[1] = Y;
+  tp[2] = Z;
+  reinterpret_cast<float*>(tile + PK_I_OFF)[j] = I;
+  reinterpret_cast<float4*>(tile + PK_JA_OFF)[j] = ja;
+  reinterpret_cast<float2*>(tile + PK_JB_OFF)[j] = jb;
+  reinterpret_cast<float*>(tile + PK_R_OFF)[j] = qn;
+}
 
 // ---------------------------------------------------------------------------------------------
 // precalc_jacobians: dI/dxi = gradI * dpi/dP * [-P^ | I]; cols 6,7 = [I_ref, 1].
@@ -948,6 +967,24 @@ extern "C" size_t como_b200_track_workspace_bytes(int32_t max_n, int32_t num_pro
   return L.total;
 }
 
+extern "C" size_t como_b200_track_pack_bytes(int32_t n) {
+  if (n <= 0) return 0;
+  return (size_t)((n + TILE - 1) / TILE) * PK_TILE_BYTES;
+}
+
+extern "C" int como_b200_track_pack(const como_b200_track_level_t* lv, void* stream_) {
+  COMO_REQUIRE(lv, "track_pack: null level");
+  COMO_REQUIRE(lv->n >= 0, "track_pack: negative n");
+  if (lv->n == 0) return COMO_B200_OK;
+  COMO_REQUIRE(lv->vals && lv->P && lv->J && lv->pack, "track_pack: null pointer (vals, P, J and pack are required)");
+  COMO_REQUIRE(((uintptr_t)lv->J & 15) == 0 && ((uintptr_t)lv->pack & 127) == 0,
+               "track_pack: J must be 16-byte and pack 128-byte aligned");
+  const int slots = (lv->n + TILE - 1) / TILE * TILE;
+  track_pack_kernel<<<(slots + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(lv->vals, lv->P, lv->J, lv->mask, lv->n,
+                                                                           (uint8_t*)lv->pack);
+  return check_launch("track_pack");
+}
+
 extern "C" void como_b200_track_debug_candidate_cap(int32_t cap) {
   g_track_cand_cap = cap < 0 ? 0 : (cap > CAND_CAP ? CAND_CAP : cap);
 }
@@ -967,9 +1004,8 @@ extern "C" int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_
     for (int l = 0; l < num_levels; ++l) {
       const como_b200_track_level_t& lv = levels[p * num_levels + l];
       COMO_REQUIRE(lv.n >= 0 && lv.w >= 3 && lv.h >= 3, "track_pyr: bad level shape n=%d w=%d h=%d", lv.n, lv.w, lv.h);
-      COMO_REQUIRE(lv.n == 0 || (lv.vals && lv.P && lv.J && lv.img), "track_pyr: null level pointer");
-      COMO_REQUIRE((((uintptr_t)lv.J | (uintptr_t)lv.P | (uintptr_t)lv.vals | (uintptr_t)lv.mask) & 15) == 0,
-                   "track_pyr: vals, P, J and mask must be 16-byte aligned");
+      COMO_REQUIRE(lv.n == 0 || (lv.pack && lv.img), "track_pyr: null level pointer (pack and img are required)");
+      COMO_REQUIRE(((uintptr_t)lv.pack & 127) == 0, "track_pyr: pack must be 128-byte aligned");
       if (lv.n > max_n) max_n = lv.n;
     }
   TrackLaunchCfg cfg;

@@ -47,34 +47,63 @@ def _aligned(t):
     return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
 
 
-def _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, keep):
+_pack_cache = {}
+
+
+def _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, keep, used=None):
+    """Level descriptors of one problem.  The keyframe-side operands are re-laid out into the tracker's tile format
+    (como_b200_track_pack) once per set of operand tensors: cached on identity + version counters of (vals, P, J, mask),
+    dropped when the Jacobian tensor dies.  `used`: packs already claimed by other problems of the same launch -- the
+    kernel keeps its residuals inside the pack, so a problem listed twice gets a private copy."""
     num_levels = len(vals_i)
     arr = (_lib.TrackLevel * num_levels)()
     max_n = 0
     for l in range(num_levels):
-        v = vals_i[l]
-        if v.shape[-1] != 1:
+        v0, P0, J0, m0 = vals_i[l], Pi[l], dI_dT[l], masks[l]
+        if v0.shape[-1] != 1:
             raise NotImplementedError("como_b200 tracking supports tracking.color: gray (C=1) only")
-        v = _aligned(v.reshape(-1).float())
-        P = _aligned(Pi[l].reshape(-1, 3).float())
-        J = _aligned(dI_dT[l].reshape(-1, 8).float())
-        m = masks[l].reshape(-1).contiguous()
-        if m.dtype != torch.uint8:
-            m = m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
-        m = _aligned(m)
         img = img_j[l]
         if img.shape[0] != 1 or img.shape[1] != 1:
             raise NotImplementedError("como_b200 tracking expects img_j[l] of shape (1,1,h,w)")
         img = img.contiguous().float()
         Kl = _k9_list(intrinsics[l])
-        keep += [v, P, J, m, img]
-        n = v.shape[0]
+        n = v0.numel()
         max_n = max(max_n, n)
         a = arr[l]
-        a.vals, a.P, a.J, a.mask, a.img = v.data_ptr(), P.data_ptr(), J.data_ptr(), m.data_ptr(), img.data_ptr()
+        a.img = img.data_ptr()
         a.n, a.w, a.h = n, img.shape[-1], img.shape[-2]
         for k in range(9):
             a.K[k] = Kl[k]
+        dev = v0.device
+        key = tuple(id(t) for t in (v0, P0, J0, m0))
+        ent = _pack_cache.get(key)
+        if ent is not None and all(r() is t for r, t in zip(ent[0], (v0, P0, J0, m0))) and \
+                ent[1] == tuple(t._version for t in (v0, P0, J0, m0)):
+            pack = ent[2]
+        else:
+            v = v0.reshape(-1).float().contiguous()
+            P = P0.reshape(-1, 3).float().contiguous()
+            J = _aligned(J0.reshape(-1, 8).float())
+            m = m0.reshape(-1).contiguous()
+            if m.dtype != torch.uint8:
+                m = m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
+            a.vals, a.P, a.J, a.mask = v.data_ptr(), P.data_ptr(), J.data_ptr(), m.data_ptr()
+            pack = torch.empty(max(int(_lib.track_pack_bytes(n)), 128), dtype=torch.uint8, device=dev)
+            a.pack = pack.data_ptr()
+            if n > 0:
+                _lib.check(_lib.track_pack(C.byref(a), _lib.stream_ptr(dev)), "como_b200_track_pack")
+            if len(_pack_cache) > 1024:
+                _pack_cache.clear()
+            refs = (weakref.ref(v0), weakref.ref(P0), weakref.ref(J0, lambda _r, key=key: _pack_cache.pop(key, None)),
+                    weakref.ref(m0))
+            _pack_cache[key] = (refs, tuple(t._version for t in (v0, P0, J0, m0)), pack)
+            a.vals = a.P = a.J = a.mask = None   # temporaries: the launch reads only pack and img
+        if used is not None:
+            if pack.data_ptr() in used:
+                pack = pack.clone()
+            used.add(pack.data_ptr())
+        a.pack = pack.data_ptr()
+        keep += [pack, img]
     return arr, max_n
 
 
@@ -126,8 +155,9 @@ def photo_tracking_pyr_batch(Tji_init, aff_init, problems, term_criteria, return
     with torch.cuda.device(dev):
         arr = (_lib.TrackLevel * (B * num_levels))()
         max_n = 0
+        used = set()
         for p, (vals_i, Pi, dI_dT, masks, intrinsics, img_j) in enumerate(problems):
-            a, mn = _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, keep)
+            a, mn = _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, keep, used)
             max_n = max(max_n, mn)
             for l in range(num_levels):
                 arr[p * num_levels + l] = a[l]
@@ -159,8 +189,9 @@ class TrackBatchPlan:
         with torch.cuda.device(self.dev):
             self.arr = (_lib.TrackLevel * (self.B * self.num_levels))()
             max_n = 0
+            used = set()
             for p, (vals_i, Pi, dI_dT, masks, intrinsics, img_j) in enumerate(problems):
-                a, mn = _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, self.keep)
+                a, mn = _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, self.keep, used)
                 max_n = max(max_n, mn)
                 for l in range(self.num_levels):
                     self.arr[p * self.num_levels + l] = a[l]

@@ -64,7 +64,7 @@ typedef struct {
 
 /* per-iteration record written to `stats` (32 floats per iteration, iteration-major) */
 #define COMO_B200_TRACK_STAT_STRIDE 32
-/* [0]=level [1]=mean_sq_err [2]=grad_norm [3]=delta_norm [4]=sigma_r [5]=num_valid [6]=done [7]=median path (0 scan, 1 predicted bin window)
+/* [0]=level [1]=mean_sq_err [2]=grad_norm [3]=delta_norm [4]=sigma_r [5]=num_valid [6]=done [7]=reserved
  * [8..23]=Tji (row-major 4x4) and [24..25]=[a,b] this iteration was linearised at (tracking_iter's inputs,
  * photo_tracking.py:117) -- lets a checker replay every iteration from identical inputs; [26..31]=reserved */
 

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_abi_version_and_error_string():
-    assert _lib.abi_version() == 2   # 2: 32-float tracking stats record, fused pyramid, distributed median
+    assert _lib.abi_version() == 3   # 3: packed keyframe tiles for the tracker (como_b200_track_pack)
     assert isinstance(_lib.last_error(), bytes)
 
 
