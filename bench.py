@@ -801,7 +801,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"], help="--impl reference only: where the port runs")
     ap.add_argument("--workload", default="all", choices=["all", "ba_window", "track640", "kf_init"])
-    ap.add_argument("--batch", type=int, default=444, help="track640: independent sequences per launch (444 = 3 CTAs on each of the 148 SMs, one problem per CTA)")
+    ap.add_argument("--batch", type=int, default=592, help="track640: independent sequences per launch (592 = 4 CTAs on each of the 148 SMs, one problem per CTA)")
     ap.add_argument("--kf", type=int, default=BA_K)
     ap.add_argument("--oneway", type=int, default=BA_R)
     ap.add_argument("--shard", type=int, default=0, help="1: headline = ONE window sharded over the GPUs (strong scaling)")

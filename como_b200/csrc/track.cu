@@ -40,7 +40,7 @@ namespace como {
 #define TRK_CONS_WARPS 4
 #endif
 #ifndef TRK_MAX_OCC
-#define TRK_MAX_OCC 3
+#define TRK_MAX_OCC 4
 #endif
 #ifndef TRK_P1_DEPTH
 #define TRK_P1_DEPTH 1
@@ -272,11 +272,10 @@ __device__ __forceinline__ void produce(uint8_t* stage, unsigned long long* full
   bulk_g2s_hint(stage, src, bytes, full, pol);
 }
 
-#ifdef TRK_MAXNREG
-__global__ void __maxnreg__(TRK_MAXNREG)
-#else
-__global__ void __launch_bounds__(TRK_THREADS, MAX_OCC)
-#endif
+// OCC_BOUND: CTAs per SM the register allocation is sized for -- 3 (128 registers) or 4 (96 registers, a handful of
+// spills in the accumulation pass; pays off only when the batch really puts four CTAs on every SM)
+template <int OCC_BOUND>
+__global__ void __launch_bounds__(TRK_THREADS, OCC_BOUND)
 track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num_levels,
                  como_b200_track_term_t term, float* __restrict__ T_io, float* __restrict__ aff_io,
                  float* __restrict__ stats, int* __restrict__ num_iters, uint8_t* __restrict__ ws,
@@ -836,6 +835,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
 struct TrackLaunchCfg {
   int G, r_cap;
   size_t dyn_smem;
+  const void* kernel;
 };
 
 // Launch shape: G CTAs per problem, 1-3 CTAs per SM.  One CTA per SM (the residual slice stays in shared memory)
@@ -848,7 +848,6 @@ static int track_config(int num_problems, int max_n, TrackLaunchCfg* cfg) {
   cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, track_pyr_kernel) != cudaSuccess) return -1;
   const int sms = sm_count();
   const int g_want = max_n > 0 ? (max_n + 2047) / 2048 : 1;
   const char* e_occ = getenv("COMO_B200_TRACK_OCC");
@@ -856,8 +855,13 @@ static int track_config(int num_problems, int max_n, TrackLaunchCfg* cfg) {
   const long long want = (long long)num_problems * (g_want < 8 ? g_want : 8);
   int occ = (int)((want + sms - 1) / sms);   // CTAs per SM wanted: 1 .. MAX_OCC
   occ = occ < 1 ? 1 : (occ > MAX_OCC ? MAX_OCC : occ);
+  // the 4-per-SM kernel (96 registers) only for batches that need it: measured 0.67 vs 0.70 of the roofline at 444
+  // sequences, 0.73 at 592
+  if (occ > 3 && num_problems <= 3 * sms) occ = 3;
   if (e_occ && atoi(e_occ) >= 1) occ = atoi(e_occ) > MAX_OCC ? MAX_OCC : atoi(e_occ);
   for (; occ >= 1; --occ) {
+    const void* kernel = (occ >= 4) ? (const void*)track_pyr_kernel<4> : (const void*)track_pyr_kernel<3>;
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return -1;
     const int per_cta = (occ == 1) ? smem_optin : (smem_sm / occ - 1024);
     long long dyn = (long long)per_cta - (long long)fa.sharedSizeBytes;
     if (dyn > smem_optin - (long long)fa.sharedSizeBytes) dyn = smem_optin - (long long)fa.sharedSizeBytes;
@@ -875,9 +879,9 @@ static int track_config(int num_problems, int max_n, TrackLaunchCfg* cfg) {
     }
     if (const char* e_rc = getenv("COMO_B200_TRACK_RCAP")) r_cap = atoi(e_rc) / TILE * TILE;  // tuning only
     const size_t dyn_smem = (size_t)RING_BYTES + (size_t)r_cap * 4;
-    cudaFuncSetAttribute(track_pyr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, track_pyr_kernel, TRK_THREADS, dyn_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRK_THREADS, dyn_smem);
     if (per_sm > occ) per_sm = occ;
     const int cap = per_sm * sms / (num_problems > 0 ? num_problems : 1);
     if (cap < 1) continue;
@@ -887,6 +891,7 @@ static int track_config(int num_problems, int max_n, TrackLaunchCfg* cfg) {
     cfg->G = G;
     cfg->r_cap = r_cap;
     cfg->dyn_smem = dyn_smem;
+    cfg->kernel = kernel;
     return G;
   }
   // more problems than co-resident CTAs even at the highest occupancy
@@ -1080,7 +1085,7 @@ extern "C" int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_
   void* args[] = {(void*)&d_levels, (void*)&num_levels, (void*)&t,  (void*)&T,   (void*)&aff,   (void*)&stats,
                   (void*)&num_iters, (void*)&ws,        (void*)&lay, (void*)&r_cap, (void*)&cand_cap};
   dim3 grid(G, num_problems), block(TRK_THREADS);
-  cudaError_t e = cudaLaunchCooperativeKernel((void*)track_pyr_kernel, grid, block, args, cfg.dyn_smem, stream);
+  cudaError_t e = cudaLaunchCooperativeKernel(cfg.kernel, grid, block, args, cfg.dyn_smem, stream);
   if (e != cudaSuccess) {
     set_last_error("track_pyr: cooperative launch failed: %s", cudaGetErrorString(e));
     return COMO_B200_ELAUNCH;

@@ -15,8 +15,6 @@ except Exception as e:
     print(sys.argv[1], 'FAILED', e); print(open('gpurun_out/w_%s.err'%sys.argv[1]).read()[-600:])
 PY
 }
-run base 444 A=1
-run o4_b592 592 COMO_B200_LIB=$PWD/variants/libcomo_b200_o4.so
-run o4_b444 444 COMO_B200_LIB=$PWD/variants/libcomo_b200_o4.so
-run base_b148 148 A=1
-run base_b74 74 A=1
+run b592 592 A=1
+run b444 444 A=1
+run b296 296 A=1

@@ -241,6 +241,68 @@ def test_two_ctas_per_sm_mode_replay(monkeypatch):
     replay_check(case, stats, T[0].cpu().numpy(), aff.cpu().numpy().ravel())
 
 
+@pytest.mark.parametrize("G", [1, 4])
+def test_four_ctas_per_sm_kernel_replay(G, monkeypatch):
+    """The 96-register build of the kernel (batches of more than 3 x 148 sequences use it); G = 1: one CTA streams a whole
+    problem through the packed tiles' residual slots (no shared-memory residency)."""
+    from como_b200 import synth
+
+    monkeypatch.setenv("COMO_B200_TRACK_OCC", "4")
+    monkeypatch.setenv("COMO_B200_TRACK_G", str(G))
+    monkeypatch.setenv("COMO_B200_TRACK_RCAP", "0")
+    case = synth.make_tracking_case(240, 320, 3, seed=7, cell=8)
+    T, aff, stats = cuda_track(case, case["T_init"], case["aff_init"], TERM)
+    replay_check(case, stats, T[0].cpu().numpy(), aff.cpu().numpy().ravel())
+
+
+def test_far_taps_on_the_image_border_stay_in_bounds():
+    """A coordinate a hair below h-1 / w-1 can round onto it in the reference's fp32 normalise / unnormalise round trip:
+    the far row / column then has weight 0 (grid_sample treats it as padding) and must not be fetched -- it lies past
+    the image.  The image sits in the last bytes of its allocation so that such a fetch faults."""
+    from como_b200 import synth
+
+    case = synth.make_tracking_case(120, 160, 1, seed=11, cell=8)
+    h, w = case["img"][0].shape[-2:]
+    K = case["K"][0].double()
+    Ti = torch.linalg.inv(case["T_init"][0].double())
+    n = case["P"][0].reshape(-1, 3).shape[0]
+    # points that project, under the initial pose, to y = h-1-eps (first half) or x = w-1-eps (second half)
+    eps = torch.logspace(-7, -2, n, dtype=torch.float64)
+    xs = torch.linspace(1.5, w - 2.5, n, dtype=torch.float64)
+    ys = torch.linspace(1.5, h - 2.5, n, dtype=torch.float64)
+    half = torch.arange(n) < n // 2
+    px = torch.where(half, xs, (w - 1) - eps)
+    py = torch.where(half, (h - 1) - eps, ys)
+    z = torch.full((n,), 2.0, dtype=torch.float64)
+    Pc = torch.stack(((px - K[0, 2]) / K[0, 0] * z, (py - K[1, 2]) / K[1, 1] * z, z), -1)
+    case["P"][0] = ((Ti[:3, :3] @ Pc.T).T + Ti[:3, 3]).float().reshape(case["P"][0].shape)
+    case["mask"][0] = torch.ones_like(case["mask"][0])
+    buf = torch.empty(1 << 20, dtype=torch.float32, device="cuda")   # a whole allocator block: nothing mapped behind it
+    img = buf[-h * w:].view(1, 1, h, w)
+    img.copy_(case["img"][0])
+    from como_b200.odom.frontend.photo_tracking import photo_tracking_pyr
+
+    c = lambda x: x.cuda()
+    T, aff, stats = photo_tracking_pyr(c(case["T_init"]), c(case["aff_init"]), [c(case["vals"][0])], [c(case["P"][0])],
+                                       [c(case["dI_dT"][0])], [c(case["mask"][0])], [case["K"][0]], [img], 0.1,
+                                       dict(TERM, max_iter=1), return_stats=True)
+    torch.cuda.synchronize()
+    assert stats.shape[0] == 1 and bool(torch.isfinite(stats[0, :6]).all())
+    # most points sit within a few ulp of the validity threshold here, so only the aggregate is compared: the valid
+    # count within the number of such points, the robust scale and error within a percent
+    st = stats.cpu().numpy()
+    m = case["mask"][0].reshape(-1)
+    d = {}
+    out = TO.tracking_iter(torch.from_numpy(st[0, 8:24].reshape(4, 4).copy()), torch.from_numpy(st[0, 24:26].copy()),
+                           case["vals"][0].reshape(-1)[m], case["P"][0].reshape(-1, 3)[m],
+                           case["dI_dT"][0].reshape(-1, 8)[m], case["K"][0], case["img"][0][0, 0], detail=d)
+    mse, sigma, nvalid = out[3], out[7], out[8]
+    margin = torch.minimum((d["x"] - (w - 1)).abs(), (d["y"] - (h - 1)).abs())
+    nb = int(((margin <= 4 * 2.0 ** -23 * max(w, h)) & (d["z"] > 0)).sum())
+    assert nb > 1000 and abs(st[0, 5] - nvalid) <= nb
+    assert abs(st[0, 4] - sigma) <= 1e-2 * sigma and abs(st[0, 1] - mse) <= 2e-2 * mse
+
+
 def test_all_zero_residuals_single_bin():
     """Every |r| is exactly 0 (black frames): one histogram bin holds every pixel -> the narrowing passes run down to
     a single key; sigma = 0 and the weights are NaN exactly as in the reference (r / 0).  Must terminate, not hang."""
