@@ -233,7 +233,10 @@ def run_track_ours(args, rank, world, device, B, e2e=True):
         "scaling": "weak", "dtype": "f32", "config": track_config(B, world, [int(m.sum()) for m in cases[0]["mask"]]),
         "gn_iterations_per_step": its // max(args.steps * world, 1), "gpu_launches": args.steps,
         "roofline": {"kernel": "track_pyr_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": ach / peak,
+                     # dram__bytes_read + write of one launch at this exact shape (ncu --set full,
+                     # profiles/r02_track_pyr_kernel_b592_full.txt): 24.78 GB + 1.86 GB; other batch sizes: not captured
+                     "traffic": 26647081000 if B == 592 else None, "peak_source": peak_src,
                      "alg_bytes_per_launch": alg_bytes, "launch_ms": kernel_ms, "launches_timed": reps,
                      "bytes_per_px_iter": TRACK_BYTES_PER_PX_ITER},
         "clocks": clocks,
