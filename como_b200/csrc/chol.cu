@@ -167,10 +167,9 @@ __device__ __forceinline__ void small_gemm(const double* A, const double* B, dou
 }
 
 // ---- 64 x 64 Cholesky of S.T (lower triangle in place).  256 threads.
-// Blocked by 8: (a) warp 0 factorises the 8 x 8 diagonal block in registers (one rsqrt per pivot) while warp 1
-// inverts the PREVIOUS diagonal block (needed by the panel solves of other tiles, not by this loop), (b) the rows
-// below are solved against the block by substitution (one thread per row), (c) the trailing block is updated on the
-// tensor path.  On return S.L8inv[b] holds the inverse of diagonal block b (8 x 8 row-major, zero above the
+// Blocked by 8: (a, b) warps 0-1 factorise the 8 x 8 diagonal block in registers (one rsqrt per pivot) and solve the
+// rows below it in the same sweep, one row per lane, while warp 2 inverts the PREVIOUS diagonal block (needed by the
+// panel solves of other tiles, not by this loop), (c) the trailing block is updated on the tensor path.  On return S.L8inv[b] holds the inverse of diagonal block b (8 x 8 row-major, zero above the
 // diagonal) and s_invdiag the reciprocal pivots.
 __device__ void potrf64(CholSmem& S, double* s_invdiag, long long* clk = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -194,43 +193,56 @@ __device__ void potrf64(CholSmem& S, double* s_invdiag, long long* clk = nullptr
   for (int jb = 0; jb < 8; ++jb) {
     const int c0 = 8 * jb;
     if (clk && tid == 0) clk[4 * jb] = clock64();
-    if (warp == 0) {
-      double a8[36], rs8[8];
+    // (a)+(b) warps 0 and 1: every lane factorises the 8 x 8 diagonal block redundantly in registers AND carries one
+    // row of the panel below it through the same right-looking sweep (l_rj = a_rj / L_jj, a_rk -= l_rj L_kj): the
+    // panel solve hangs off the pivot chain instead of following it as a second dependent chain of the same length.
+    if (warp < 2) {
+      const int r = c0 + 8 + tid;          // this lane's panel row (tid < 64)
+      const bool has_row = r < CT;
+      double a8[36], rs8[8], pr[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int k = 0; k <= i; ++k) a8[tri8(i, k)] = T[(c0 + i) * CPITCH + c0 + k];
-      chol8_regs(a8, rs8);
-      // every lane holds the same result and stores it (same address, same value): no divergent selection
+      const double* prow = T + (has_row ? r : c0) * CPITCH + c0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int c = 0; c < 8; ++c) pr[c] = prow[c];
+      // both warps have read the block before warp 0 overwrites it with the factor
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+      if (warp == 0 || has_row) {
 #pragma unroll
-        for (int k = 0; k <= i; ++k) T[(c0 + i) * CPITCH + c0 + k] = a8[tri8(i, k)];
+        for (int j = 0; j < 8; ++j) {
+          const double rj = rsqrt(a8[tri8(j, j)]);
+          rs8[j] = rj;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s_invdiag[c0 + j] = rs8[j];
-    } else if (warp == 1 && jb > 0) {
-      invert_block(jb - 1);
+          for (int i = j; i < 8; ++i) a8[tri8(i, j)] *= rj;        // (j,j): d * rsqrt(d) = sqrt(d)
+          pr[j] *= rj;
+#pragma unroll
+          for (int i = j + 1; i < 8; ++i)
+#pragma unroll
+            for (int k = j + 1; k <= i; ++k) a8[tri8(i, k)] -= a8[tri8(i, j)] * a8[tri8(k, j)];
+#pragma unroll
+          for (int k = j + 1; k < 8; ++k) pr[k] -= pr[j] * a8[tri8(k, j)];
+        }
+        if (warp == 0) {
+          // every lane holds the same block and stores it (same address, same value): no divergent selection
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int k = 0; k <= i; ++k) T[(c0 + i) * CPITCH + c0 + k] = a8[tri8(i, k)];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s_invdiag[c0 + j] = rs8[j];
+        }
+        if (has_row) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) T[r * CPITCH + c0 + c] = pr[c];
+        }
+      }
+    } else if (warp == 2 && jb > 0) {
+      invert_block(jb - 1);   // inverse of the PREVIOUS diagonal block: for the panel solves of other tiles
     }
     __syncthreads();
     if (clk && tid == 0) clk[4 * jb + 1] = clock64();
-    // (b) rows below: P L8^T = A  ->  p_c = (a_c - sum_{m<c} p_m L8[c][m]) / L8[c][c]
-    {
-      const int r = c0 + 8 + tid;
-      if (r < CT) {
-        double pv[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          double sacc = T[r * CPITCH + c0 + c];
-#pragma unroll
-          for (int m = 0; m < 8; ++m)
-            if (m < c) sacc -= pv[m] * T[(c0 + c) * CPITCH + c0 + m];
-          pv[c] = sacc * s_invdiag[c0 + c];
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) T[r * CPITCH + c0 + c] = pv[c];
-      }
-    }
-    __syncthreads();
     if (clk && tid == 0) clk[4 * jb + 2] = clock64();
     // (c) trailing update T22 -= P P^T on the tensor path: warp w owns row tile jb + 1 + w (lower tiles only)
     {
@@ -251,7 +263,7 @@ __device__ void potrf64(CholSmem& S, double* s_invdiag, long long* clk = nullptr
     __syncthreads();
     if (clk && tid == 0) clk[4 * jb + 3] = clock64();
   }
-  if (warp == 1) invert_block(7);
+  if (warp == 2) invert_block(7);
   __syncthreads();
   if (clk && tid == 0) clk[32] = clock64();
 }
