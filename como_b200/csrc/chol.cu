@@ -111,26 +111,6 @@ struct CholSmem {
 // Packed lower triangle of an 8 x 8 block: element (i, k), k <= i, at i (i + 1) / 2 + k.
 __device__ __forceinline__ constexpr int tri8(int i, int k) { return i * (i + 1) / 2 + k; }
 
-// In-register Cholesky of an 8 x 8 block (every lane of the warp computes the same thing: no shuffles on the
-// pivot chain).  rs[j] = 1 / L[j][j].  Non-positive pivot -> NaN.
-// Measured (scripts/chol_probe.py): 1.13 k cycles per block, i.e. ~140 per pivot = one fp64 rsqrt (MUFU seed + two
-// Newton steps of dependent DFMAs at ~17 cycles each) + the dependent multiply / update.  Taking pivots in pairs
-// (second pivot = sqrt(det / p), so that rsqrt(p) and rsqrt(det) overlap) was tried in round 2: the chain keeps the same
-// number of dependent fp64 operations and the block took the same 1.13 k cycles.
-__device__ __forceinline__ void chol8_regs(double (&a)[36], double (&rs)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const double r = rsqrt(a[tri8(j, j)]);
-    rs[j] = r;
-#pragma unroll
-    for (int i = j; i < 8; ++i) a[tri8(i, j)] *= r;        // (j,j): d * rsqrt(d) = sqrt(d)
-#pragma unroll
-    for (int i = j + 1; i < 8; ++i)
-#pragma unroll
-      for (int k = j + 1; k <= i; ++k) a[tri8(i, k)] -= a[tri8(i, j)] * a[tri8(k, j)];
-  }
-}
-
 // Inverse of a lower-triangular 8 x 8 block held in registers: x[i][j] = -rs_i sum_{m=j}^{i-1} l[i][m] x[m][j]
 __device__ __forceinline__ void inv8_regs(const double (&l)[36], const double (&rs)[8], double (&x)[36]) {
 #pragma unroll
@@ -167,9 +147,16 @@ __device__ __forceinline__ void small_gemm(const double* A, const double* B, dou
 }
 
 // ---- 64 x 64 Cholesky of S.T (lower triangle in place).  256 threads.
-// Blocked by 8: (a, b) warps 0-1 factorise the 8 x 8 diagonal block in registers (one rsqrt per pivot) and solve the
+// Blocked by 8: (a, b) warps 0-1 factorise the 8 x 8 diagonal block in registers (every lane the same block: no shuffles on the
+// pivot chain; ~140 cycles per pivot = one fp64 rsqrt -- MUFU seed + two Newton steps of dependent DFMAs at ~17 cycles
+// each -- + the dependent multiply / update; taking pivots in pairs kept the same chain length) and solve the
 // rows below it in the same sweep, one row per lane, while warp 2 inverts the PREVIOUS diagonal block (needed by the
-// panel solves of other tiles, not by this loop), (c) the trailing block is updated on the tensor path.  On return S.L8inv[b] holds the inverse of diagonal block b (8 x 8 row-major, zero above the
+// panel solves of other tiles, not by this loop), (c) the trailing block is updated on the tensor path.
+// Measured per 8-column step (scripts/chol_probe.py): (a, b) 1.34 k cycles, (c) 0.28 k; the separate substitution
+// phase this replaced cost about as much as the 0.2 k it adds to the sweep (896 -> 893 us for n = 2848).  Building
+// the block inverse inside the same sweep instead of on warp 2 was tried as well: the extra dependent-free DFMAs are
+// NOT hidden by the pivot latency (1.87 k cycles per step, 983 us) -- the fp64 pipe of one SM sub-partition is the
+// limit, not the chain alone.  On return S.L8inv[b] holds the inverse of diagonal block b (8 x 8 row-major, zero above the
 // diagonal) and s_invdiag the reciprocal pivots.
 __device__ void potrf64(CholSmem& S, double* s_invdiag, long long* clk = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
