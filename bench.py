@@ -11,6 +11,7 @@ every number DESIGN.md quotes is produced by the driver's own run:
                   (the "warp + Jacobian kernel" of the metric; roofline on 52 B per pixel-iteration)
   track640_single the same tracker on ONE live sequence: per-frame latency (kernel, and through Tracking.handle_frame)
   kf_init         one keyframe creation (track_and_init) at 640x480 with 64 anchors
+  sfm             one two-frame SfM bootstrap alignment at 640x480, 3 levels, 64 anchors
   ba_shard        (N > 1 only) ONE 32-keyframe window sharded over the N GPUs (strong scaling, NCCL exchange)
 A "step" is one pass of the hot path over one batch of synthetic input.  Every workload's inputs exceed the
 126 MB L2 (5.0 GB predictor slabs; B x 21 MB tracking operands; 157 MB predictor rows), so no L2 flush is needed.
@@ -666,6 +667,98 @@ def cpu_kfinit_baseline(c):
             "sample": f"1 keyframe creation on the same inputs ({dt:.1f} s)"}
 
 
+
+# --------------------------------------------------------------------------------------------- two-frame SfM workload
+SFM_INIT = {"start_level": 0, "end_level": 3, "max_iter": 50, "delta_norm": 1.0e-4, "rel_tol": 1.0e-4,
+            "kf_depth_motion_ratio": 0.04, "kf_num_pixels_frac": 0.75}    # config/como.yml:65-72
+
+
+def build_sfm_case(device, seed=0, H=480, W=640, M=64, shift_px=2.5):
+    """Synthetic bootstrap pair: frame 1 is frame 0 translated by 2.5 px; 3-level [I, gx, gy] pyramids in
+    the mapper's dtype, anchors chosen by the sampler, the reference's identity / zero-log-depth initialisation."""
+    import torch.nn.functional as F
+
+    from como_b200 import synth
+    from como_b200.depth_cov.core.samplers import sample_sparse_coords
+    from como_b200.odom import mapping_core as MC
+    from como_b200.odom.frontend import two_frame_sfm as SF
+
+    tex = synth.make_rgb(H, W, seed=seed + 1, cell=16, extra_w=16, dtype=torch.float64, device=device)
+    x1, a = int(shift_px), shift_px - int(shift_px)
+    rgb0 = tex[..., 0:W].contiguous()
+    rgb1 = ((1 - a) * tex[..., x1:x1 + W] + a * tex[..., x1 + 1:x1 + 1 + W]).contiguous()
+
+    def pyr(rgb):   # coarsest first; the down-sampling filter is part of the synthetic input, not of the timed path
+        out, cur = [], rgb
+        for l in range(SFM_INIT["end_level"]):
+            out.insert(0, MC.get_img_and_grads(cur))
+            cur = F.avg_pool2d(cur, 2)
+        return out
+
+    iag0, iag1 = pyr(rgb0), pyr(rgb1)
+    cov = synth.make_cov_image_wide(H, W, seed=seed).to(device)
+    scale = 0.086
+    coords_m, _ = sample_sparse_coords(cov, M, "greedy_conditional_entropy", 1e-2, border=3, dist_thresh=0.1,
+                                       signal_var=scale, fixed_var=0.0)
+    dims = torch.tensor([H, W], dtype=torch.float64, device=device)
+    cm_norm = 2.0 * (1.0 / dims) * coords_m.double() + (1.0 / dims) - 1.0
+    K = synth.make_intrinsics(H, W, dtype=torch.float64).to(device)
+    vals, coords, Knm, sizes, Kp, dr, Hp = SF.setup_reference(iag0, cm_norm, scale, cov, K)
+    T0 = torch.eye(4, dtype=torch.float64, device=device)[None]
+    d0 = torch.zeros(1, coords_m.shape[1], 1, dtype=torch.float64, device=device)
+    aff = torch.zeros(1, 2, 1, dtype=torch.float64, device=device)
+    return dict(T0=T0, d0=d0, aff=aff, coords=coords, vals=vals, Knm=Knm, imgs=iag1, dr=dr, Hp=Hp, Kp=Kp, rgb1=rgb1,
+                H=H, W=W, M=int(coords_m.shape[1]), pyr=pyr)
+
+
+def run_sfm_ours(args, rank, world, device):
+    from como_b200.odom.frontend import two_frame_sfm as SF
+
+    c = build_sfm_case(device, seed=rank)
+    its = [0]
+
+    def step(i=0, imgs=None):
+        out = SF.two_frame_sfm_pyr(c["T0"], c["d0"], c["aff"], c["coords"], c["vals"], c["Knm"], c["imgs"] if imgs is None else imgs,
+                                   c["dr"], c["Hp"], c["Kp"], {"photo": 0.1}, None, SFM_INIT)
+        its[0] += sum(SF.two_frame_sfm_pyr.last_iters)
+        return out
+
+    for _ in range(max(min(args.warmup, 3), 2)):
+        step()
+    its[0] = 0
+    steps = max(2, min(args.steps, 5))     # one alignment is ~50 GN iterations over three levels
+    ms, clocks = timed_loop(step, steps, world, device)
+    n_it = its[0]
+    # end to end: the new frame arrives as pinned host RGB; gray + gradients + pyramid on the device, pose and depths back
+    rgb_host = c["rgb1"].cpu().pin_memory()
+    out_host = torch.empty(16 + c["M"], dtype=torch.float64).pin_memory()
+    its[0] = 0
+
+    def e2e_step(i):
+        rgb = rgb_host.to(device, non_blocking=True)
+        out = step(0, c["pyr"](rgb))
+        out_host[:16].copy_(out[0].reshape(-1), non_blocking=True)
+        out_host[16:].copy_(out[1].reshape(-1), non_blocking=True)
+
+    e2e_step(0)
+    its[0] = 0
+    e_ms, _ = timed_loop(e2e_step, steps, world, device, clock=False)
+    e_it = its[0]
+    px = [int(v.numel()) for v in c["vals"]]
+    return {
+        "metric": "GN-iterations/sec (two-frame SfM bootstrap, 640x480, 3 levels, 64 anchors)",
+        "value": world * n_it / (ms * 1e-3), "unit": "GN-it/s", "n_gpus": world, "steps": steps,
+        "ms_per_step": ms / steps, "ms_per_alignment": ms / steps, "gn_iterations_per_alignment": n_it // steps,
+        "scaling": "weak", "dtype": "f64",
+        "config": {"workload": "sfm", "resolution": "640x480", "anchors": c["M"], "px_per_level": px,
+                   "l2": "predictor rows (157 MB at the finest level) exceed the 126 MB L2; no flush",
+                   "parallelism": f"replicas x{world} (independent bootstraps, no collective)"},
+        "e2e": {"value": world * e_it / (e_ms * 1e-3), "unit": "GN-it/s", "ms_per_alignment": e_ms / steps,
+                "h2d_bytes_per_step": int(rgb_host.numel()) * 8, "d2h_bytes_per_step": int(out_host.numel()) * 8},
+        "clocks": clocks,
+    }
+
+
 # --------------------------------------------------------------------------------------------- dist helpers
 def barrier(world):
     if world > 1:
@@ -803,7 +896,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--device", default="cpu", choices=["cpu", "cuda"], help="--impl reference only: where the port runs")
-    ap.add_argument("--workload", default="all", choices=["all", "ba_window", "track640", "kf_init"])
+    ap.add_argument("--workload", default="all", choices=["all", "ba_window", "track640", "kf_init", "sfm"])
     ap.add_argument("--batch", type=int, default=592, help="track640: independent sequences per launch (592 = 4 CTAs on each of the 148 SMs, one problem per CTA)")
     ap.add_argument("--kf", type=int, default=BA_K)
     ap.add_argument("--oneway", type=int, default=BA_R)
@@ -834,6 +927,11 @@ def main():
         res.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "data": "synthetic"})
         if rank == 0:
             res["cpu_baseline"] = cpu_track_baseline(cases) if (world == 1 and not args.no_e2e) else None
+            print(json.dumps(res))
+    elif args.workload == "sfm":
+        res = run_sfm_ours(args, rank, world, device)
+        res.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "data": "synthetic"})
+        if rank == 0:
             print(json.dumps(res))
     elif args.workload == "kf_init":
         res, case = run_kfinit_ours(args, rank, world, device)
@@ -871,6 +969,8 @@ def main():
             torch.cuda.empty_cache()
             sec["track640_single"] = guarded("track640_single", lambda: trk(1, True))
             sec["kf_init"] = guarded("kf_init", lambda: run_kfinit_ours(args, rank, world, device)[0])
+            torch.cuda.empty_cache()
+            sec["sfm"] = guarded("sfm", lambda: run_sfm_ours(args, rank, world, device))
             res["secondary"] = sec
         elif rank == 0 and not args.no_e2e:
             res["cpu_baseline"] = guarded("cpu_baseline", lambda: cpu_ba_baseline(s, cfg)) if world == 1 else None
