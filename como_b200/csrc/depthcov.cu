@@ -74,21 +74,46 @@ __global__ void cross_cov_kernel(const T* __restrict__ x1, const T* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ Cholesky append
-// L (B,n,n) row-major; appends row N:  L[N,:N] = L[:N,:N]^-1 k_ni (forward substitution, ascending order),
-// L[N,N] = sqrt(k_ii - sum L[N,:]^2).  One warp per batch (N <= 64... any N, serial in N like the reference).
-__global__ void chol_append_kernel(float* __restrict__ L, const float* __restrict__ k_ni, float k_ii, int n, int N) {
+// L (B,n,n) row-major; appends row N:  L[N,:N] = L[:N,:N]^-1 k_ni (forward substitution),
+// L[N,N] = sqrt(k_ii - sum L[N,:]^2).  One CTA per batch element, column oriented: thread r owns rows r, r + 128, ...;
+// after column c is resolved every later row subtracts its L[r][c] * v_c -- each row still receives its subtractions
+// in ascending column order, i.e. the same fp32 sequence as the reference's serial loop (no FMA contraction in this
+// file), with N block barriers instead of N^2 / 2 dependent operations in one thread.
+constexpr int CA_THREADS = 128;
+constexpr int CA_ROWS = 8;   // rows per thread: N <= 1024
+__global__ void __launch_bounds__(CA_THREADS)
+chol_append_kernel(float* __restrict__ L, const float* __restrict__ k_ni, float k_ii, int n, int N) {
   const int b = blockIdx.x;
   float* Lb = L + (size_t)b * n * n;
-  if (threadIdx.x != 0) return;
-  float ss = 0.0f;
-  for (int r = 0; r < N; ++r) {
-    float s = k_ni[(size_t)b * N + r];
-    for (int c = 0; c < r; ++c) s -= Lb[r * n + c] * Lb[N * n + c];
-    const float v = s / Lb[r * n + r];
-    Lb[N * n + r] = v;
-    ss += v * v;
+  __shared__ float s_v;
+  float acc[CA_ROWS];
+#pragma unroll
+  for (int q = 0; q < CA_ROWS; ++q) {
+    const int r = threadIdx.x + q * CA_THREADS;
+    acc[q] = (r < N) ? k_ni[(size_t)b * N + r] : 0.0f;
   }
-  Lb[N * n + N] = sqrtf(k_ii - ss);
+  float ss = 0.0f;   // thread 0 only
+  for (int c = 0; c < N; ++c) {
+    if (threadIdx.x == c % CA_THREADS) {
+      float a = 0.0f;
+#pragma unroll
+      for (int q = 0; q < CA_ROWS; ++q)
+        if (q == c / CA_THREADS) a = acc[q];
+      const float v = a / Lb[c * n + c];
+      Lb[N * n + c] = v;
+      s_v = v;
+    }
+    __syncthreads();
+    const float v = s_v;
+    if (threadIdx.x == 0) ss += v * v;
+#pragma unroll
+    for (int q = 0; q < CA_ROWS; ++q) {
+      const int r = threadIdx.x + q * CA_THREADS;
+      if (r > c && r < N) acc[q] -= Lb[r * n + c] * v;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) Lb[N * n + N] = sqrtf(k_ii - ss);
 }
 
 // obs_info (B,n,d): new row N = (k_id - sum_i L[N,i] obs_info[i,:]) / L[N,N];  var -= row^2
@@ -370,7 +395,8 @@ extern "C" int como_b200_chol_append(float* L, float* obs_info, float* var, cons
   COMO_REQUIRE(L && obs_info && var && k_ni && k_id, "get_new_chol_obs_info: null pointer argument");
   COMO_REQUIRE(N >= 0 && N < n, "get_new_chol_obs_info: row %d out of range for n=%d", N, n);
   cudaStream_t st = (cudaStream_t)stream;
-  chol_append_kernel<<<B, 32, 0, st>>>(L, k_ni, k_ii, n, N);
+  COMO_REQUIRE(N <= CA_THREADS * CA_ROWS, "get_new_chol_obs_info: at most %d rows", CA_THREADS * CA_ROWS);
+  chol_append_kernel<<<B, CA_THREADS, 0, st>>>(L, k_ni, k_ii, n, N);
   obs_info_kernel<<<dim3((d + 255) / 256, B), 256, 0, st>>>(L, obs_info, var, k_id, n, d, N);
   return check_launch("get_new_chol_obs_info");
 }
