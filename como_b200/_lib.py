@@ -51,6 +51,7 @@ def _sig(name, restype, argtypes):
 
 abi_version = _sig("como_b200_abi_version", C.c_int, [])
 last_error = _sig("como_b200_last_error", C.c_char_p, [])
+se3_exp = _sig("como_b200_se3_exp", None, [C.POINTER(C.c_double), C.POINTER(C.c_double)])
 track_workspace_bytes = _sig("como_b200_track_workspace_bytes", C.c_size_t, [C.c_int32, C.c_int32])
 track_pack_bytes = _sig("como_b200_track_pack_bytes", C.c_size_t, [C.c_int32])
 track_pack = _sig("como_b200_track_pack", C.c_int, [C.POINTER(TrackLevel), C.c_void_p])
@@ -125,7 +126,7 @@ reproj_depth = _sig("como_b200_reproj_depth", C.c_int, [VP, I32, VP, C.POINTER(F
 
 # every symbol include/como_b200.h declares (checked by tests/test_abi.py without a GPU)
 DECLARED_SYMBOLS = [
-    "como_b200_abi_version", "como_b200_last_error", "como_b200_track_workspace_bytes", "como_b200_track_pack_bytes", "como_b200_track_pack", "como_b200_track_pyr",
+    "como_b200_abi_version", "como_b200_last_error", "como_b200_se3_exp", "como_b200_track_workspace_bytes", "como_b200_track_pack_bytes", "como_b200_track_pack", "como_b200_track_pyr",
     "como_b200_track_debug_candidate_cap",
     "como_b200_precalc_jacobians", "como_b200_median_workspace_bytes", "como_b200_median_f64", "como_b200_median_f32",
     "como_b200_subselect_pixels", "como_b200_ba_scaffold", "como_b200_predictor_apply", "como_b200_predictor_stream_ctas", "como_b200_predictor_colsum",

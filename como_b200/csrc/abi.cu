@@ -39,3 +39,9 @@ int sm_count() {
 
 extern "C" int como_b200_abi_version(void) { return 3; }
 extern "C" const char* como_b200_last_error(void) { return como::g_err; }
+
+// Host evaluation of the SAME se3_exp_tau_phi the kernels call (common.cuh, __host__ __device__): lets a CPU-only test
+// pin the restatement of lietorch's SE(3) exponential to the matrix exponential without a GPU.
+extern "C" void como_b200_se3_exp(const double* tau_phi, double* T16) {
+  como::se3_exp_tau_phi(tau_phi, tau_phi + 3, T16);
+}

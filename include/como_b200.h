@@ -30,6 +30,10 @@ extern "C" {
 int como_b200_abi_version(void);
 /* Human readable description of the last error on this host thread ("" if none). */
 const char* como_b200_last_error(void);
+/* SE(3) exponential of a twist [tau (3), phi (3)] (translation first, lietorch's order; the reference swaps its
+ * [omega, v] into it at como/geometry/lie_algebra.py:45-49) -> row-major 4x4, evaluated on the HOST by the same
+ * function the tracking / SfM / BA update kernels call.  Test hook: no GPU needed. */
+void como_b200_se3_exp(const double* tau_phi, double* T16);
 
 /* ------------------------------------------------------------------------------------------
  * Tracking: frame-to-keyframe inverse-compositional photometric GN (fp32, C = 1 channel).

@@ -35,3 +35,25 @@ def test_argument_errors_do_not_need_a_gpu():
     assert st == -1
     assert b"null" in _lib.last_error()
     assert _lib.track_workspace_bytes(1000, 1) > 1000 * 4
+
+
+def test_se3_exp_of_the_library_is_the_matrix_exponential():
+    """The kernels' own se3_exp_tau_phi (common.cuh), evaluated on the host through the C ABI, against scipy's expm of
+    the twist matrix: pins the restatement of the un-vendored lietorch exponential without a GPU."""
+    import ctypes as C
+
+    import numpy as np
+    from scipy.linalg import expm
+
+    from como_b200 import _lib
+
+    rng = np.random.default_rng(0)
+    for s in (1e-9, 1e-7, 1e-3, 0.3, 1.0, 3.0):
+        x = rng.standard_normal(6) * s
+        A = np.zeros((4, 4))
+        A[:3, :3] = [[0, -x[5], x[4]], [x[5], 0, -x[3]], [-x[4], x[3], 0]]
+        A[:3, 3] = x[:3]
+        xin = (C.c_double * 6)(*x.tolist())
+        out = (C.c_double * 16)()
+        _lib.se3_exp(xin, out)
+        np.testing.assert_allclose(np.array(out[:]).reshape(4, 4), expm(A), rtol=0, atol=1e-13)

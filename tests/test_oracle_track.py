@@ -77,3 +77,30 @@ def test_precalc_jacobians_matches_reference(golden_dir):
         vals = torch.from_numpy(g[f"vals_{l}"]).reshape(-1)
         J = TO.precalc_jacobians(grads, P, vals, torch.from_numpy(g[f"K_{l}"]))
         np.testing.assert_allclose(J.numpy(), g[f"dI_dT_{l}"].reshape(-1, 8), rtol=2e-5, atol=1e-6)
+
+
+def test_se3_exp_is_the_matrix_exponential():
+    """lietorch is not vendored in the reference, so its SE(3) exponential (tangent [tau, phi], translation first) is
+    restated in three places (oracle, import shim, common.cuh).  This pins the restatements to the definition they
+    restate -- the matrix exponential of the twist [[phi^, tau], [0, 0]] -- over random twists, tiny angles (series
+    branch) and angles near pi, and checks the reference's own use of it: se3_exp swaps COMO's [omega, v] into that
+    order (como/geometry/lie_algebra.py:45-49), and SO3_logmap of the rotation block returns omega (:127-144)."""
+    import sys
+    from scipy.linalg import expm
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "shims"))
+    import lietorch
+
+    g = torch.Generator().manual_seed(0)
+    twists = [torch.randn(6, generator=g, dtype=torch.float64) * s for s in (1e-9, 1e-7, 1e-3, 0.3, 1.0, 2.0)]
+    near_pi = torch.randn(6, generator=g, dtype=torch.float64)
+    near_pi[3:] *= (np.pi - 1e-6) / near_pi[3:].norm()
+    twists.append(near_pi)
+    for x in twists:
+        tau, phi = x[:3], x[3:]
+        A = np.zeros((4, 4))
+        A[:3, :3] = [[0, -phi[2], phi[1]], [phi[2], 0, -phi[0]], [-phi[1], phi[0], 0]]
+        A[:3, 3] = tau.numpy()
+        ref = expm(A)
+        np.testing.assert_allclose(TO.se3_exp_tau_phi(tau, phi).numpy(), ref, rtol=0, atol=1e-13)
+        np.testing.assert_allclose(lietorch.SE3.exp(x[None]).matrix()[0].numpy(), ref, rtol=0, atol=1e-13)
