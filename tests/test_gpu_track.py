@@ -347,6 +347,29 @@ def test_all_points_masked_or_invalid_does_not_hang():
     assert torch.isnan(T).any() or torch.isfinite(T).all()
 
 
+def test_empty_level_and_ragged_tile_counts():
+    """A pyramid whose coarsest level holds no points at all (n = 0: skipped, no iteration recorded) and whose other
+    levels have point counts that are not multiples of the 512-pixel tile (padding slots carry NaN points); the rest of
+    the run still replays against the oracle."""
+    from como_b200 import synth
+
+    case = synth.make_tracking_case(120, 160, 3, seed=4, cell=8)
+    keep = {1: 4801 - 512 - 7, 2: 19200 - 1}        # ragged: 4282 = 8 tiles + 186, 19199 = 37 tiles + 255
+    for l in range(3):
+        n = 0 if l == 0 else keep[l]
+        case["vals"][l] = case["vals"][l][:, :n].contiguous()
+        case["P"][l] = case["P"][l][:, :n].contiguous()
+        case["dI_dT"][l] = case["dI_dT"][l][:, :n].contiguous()
+        case["mask"][l] = case["mask"][l][:, :n].contiguous()
+    T, aff, stats = cuda_track(case, case["T_init"], case["aff_init"], TERM)
+    torch.cuda.synchronize()
+    assert stats.shape[0] >= 2 and int(stats[:, 0].min()) == 1          # level 0 took no iteration
+    sub = {k: (v[1:] if isinstance(v, list) else v) for k, v in case.items()}
+    st = stats.clone()
+    st[:, 0] -= 1                                                       # level indices of the two-level sub-problem
+    replay_check(sub, st, T[0].cpu().numpy(), aff.cpu().numpy().ravel(), strict=False)
+
+
 def test_config1_shape_320x240_one_iteration_vs_oracle():
     """BASELINE config 1: 2-frame 320x240 photometric tracking, 3 levels, 1 GN iteration per level."""
     from como_b200 import synth
