@@ -25,7 +25,7 @@ lib = C.CDLL(LIB_PATH)
 class TrackLevel(C.Structure):
     _fields_ = [
         ("vals", C.c_void_p), ("P", C.c_void_p), ("J", C.c_void_p), ("mask", C.c_void_p), ("img", C.c_void_p),
-        ("pack", C.c_void_p), ("n", C.c_int32), ("w", C.c_int32), ("h", C.c_int32), ("K", C.c_float * 9),
+        ("pack", C.c_void_p), ("n", C.c_int32), ("w", C.c_int32), ("h", C.c_int32), ("c", C.c_int32), ("K", C.c_float * 9),
     ]
 
 
@@ -53,7 +53,7 @@ abi_version = _sig("como_b200_abi_version", C.c_int, [])
 last_error = _sig("como_b200_last_error", C.c_char_p, [])
 se3_exp = _sig("como_b200_se3_exp", None, [C.POINTER(C.c_double), C.POINTER(C.c_double)])
 track_workspace_bytes = _sig("como_b200_track_workspace_bytes", C.c_size_t, [C.c_int32, C.c_int32])
-track_pack_bytes = _sig("como_b200_track_pack_bytes", C.c_size_t, [C.c_int32])
+track_pack_bytes = _sig("como_b200_track_pack_bytes", C.c_size_t, [C.c_int32, C.c_int32])
 track_pack = _sig("como_b200_track_pack", C.c_int, [C.POINTER(TrackLevel), C.c_void_p])
 track_pyr = _sig(
     "como_b200_track_pyr", C.c_int,
@@ -62,7 +62,7 @@ track_pyr = _sig(
 track_debug_candidate_cap = _sig("como_b200_track_debug_candidate_cap", None, [C.c_int32])
 precalc_jacobians = _sig(
     "como_b200_precalc_jacobians", C.c_int,
-    [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.c_void_p, C.c_void_p])
+    [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p])
 
 VP, I32, I64, F64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
 median_workspace_bytes = _sig("como_b200_median_workspace_bytes", C.c_size_t, [I32, I32])

@@ -42,9 +42,6 @@ namespace como {
 #ifndef TRK_MAX_OCC
 #define TRK_MAX_OCC 4
 #endif
-#ifndef TRK_P1_DEPTH
-#define TRK_P1_DEPTH 1
-#endif
 #ifndef TRK_STAGES1
 #define TRK_STAGES1 4
 #endif
@@ -261,6 +258,11 @@ __device__ __forceinline__ SliceInfo slice_of(int N, int G, int c) {
   return s;
 }
 
+// entries of a level as the kernel streams them: c channels x whole tiles of its n pixels
+__host__ __device__ __forceinline__ int level_entries(const como_b200_track_level_t& lv) {
+  return (lv.c > 1 ? lv.c : 1) * ((lv.n + TILE - 1) / TILE) * TILE;
+}
+
 // ------------------------------------------------------------------------------------------------
 // producer (one elected lane): wait for the stage to be released, one arrive.expect_tx + one bulk copy.
 // Operands are streamed once per pass: evict-first in L2.
@@ -341,7 +343,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
     for (int l = 0; l < num_levels; ++l) {
       const como_b200_track_level_t lv = levels[l];
       if (lv.n <= 0) continue;
-      const SliceInfo sl = slice_of(lv.n, G, c);
+      const SliceInfo sl = slice_of(level_entries(lv), G, c);
       if (c >= sl.active) continue;   // this CTA sits the level out (its consumers skip it too)
       const uint8_t* pack = reinterpret_cast<const uint8_t*>(lv.pack) + (size_t)(sl.begin / TILE) * PK_TILE_BYTES;
       const int ntiles = (sl.len + TILE - 1) / TILE;
@@ -382,8 +384,10 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
 
   for (int l = 0; l < num_levels; ++l) {
     const como_b200_track_level_t lv = levels[l];
-    const int N = lv.n;
-    if (N <= 0) continue;
+    if (lv.n <= 0) continue;
+    const int N = level_entries(lv);     // (pixel, channel) entries incl. tile padding
+    const int nch = lv.c > 1 ? lv.c : 1;
+    const int tiles_per_channel = (lv.n + TILE - 1) / TILE;
     const int w = lv.w, h = lv.h;
     const SliceInfo sl = slice_of(N, G, c);
     const int Ga = sl.active;            // group size of this level
@@ -419,18 +423,18 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
       consumer_sync();
       const float ea = s_ea, bb = s_aff[1];
 
-      // ---- pass 1: warp, gather, residual, first histogram.  Four pixels per thread and tile, software pipelined
-      // over two tiles: the 16 bilinear taps of tile t+1 are issued before the residuals of tile t are formed, so a
-      // warp always has a tile's worth of gathers in flight.
+      // ---- pass 1: warp, gather, residual, first histogram.  Four pixels per thread and tile.
       constexpr int PB = TILE / CONS_THREADS;
       const float2 wh2 = make_float2((float)w, (float)h);
       const float2 A1 = make_float2(1.0f / wh2.x, 1.0f / wh2.y);
-      const float* __restrict__ img = lv.img;
+      // the tiles of channel 0 come first, then channel 1, ...: one image plane per run of tiles (set below, once per
+      // run; a gray level is a single run)
+      const int tile0 = sl.begin / TILE;   // first tile of this CTA's slice within the level
       struct P1 {
         float fxs[PB], fys[PB], vref[PB], v00[PB], v01[PB], v10[PB], v11[PB];   // vref = NaN marks an invalid pixel
       };
       // stage A: operands -> warped coordinates -> taps in flight
-      auto gather = [&](P1& st) {
+      auto gather = [&](const float* __restrict__ img, P1& st) {
         const unsigned s = n1 % S1;
         const uint8_t* stage = ring + s * P1_BYTES;
         mbar_wait(&full1[s], (n1 / S1) & 1u);
@@ -524,26 +528,20 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         }
       };
       {
-#if TRK_P1_DEPTH == 2
-        // two tiles in flight per warp (a third one costs more in register spills than it hides: measured)
-        P1 sa, sb;
-        if (ntiles > 0) gather(sa);
-        for (int t = 0; t < ntiles; t += 2) {
-          const bool more1 = t + 1 < ntiles;
-          if (more1) gather(sb);
-          finish(t, sa);
-          if (more1) {
-            if (t + 2 < ntiles) gather(sa);
-            finish(t + 1, sb);
+        // one tile at a time per warp: gather, then finish.  (Two tiles in flight -- the taps of tile t+1 issued before
+        // the residuals of tile t are formed -- cost 36 spilled values per tile pair in this kernel and measured 0.65
+        // against 0.71 of the roofline; 12-16 resident warps per SM hide the tap latency instead.)
+        P1 sa;
+        for (int t = 0; t < ntiles;) {
+          const int ch = (tile0 + t) / tiles_per_channel;
+          const int t_end = min(ntiles, (ch + 1) * tiles_per_channel - tile0);
+          const float* img = lv.img + (size_t)ch * (size_t)(w * h);
+          asm volatile("" : "+l"(img));   // opaque: keeps the plane pointer in registers (ptxas otherwise rebuilds it per tap)
+          for (; t < t_end; ++t) {
+            gather(img, sa);
+            finish(t, sa);
           }
         }
-#else
-        P1 sa;
-        for (int t = 0; t < ntiles; ++t) {
-          gather(sa);
-          finish(t, sa);
-        }
-#endif
       }
       // the residual slots are read back by the TMA unit in pass 2 (async proxy): fence, then signal the producer
       asm volatile("fence.proxy.async;" ::: "memory");
@@ -767,7 +765,9 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         if (lane < 8) s_delta[lane] = di;
         __syncwarp();
         if (lane == 0) {
-          const double mse = s_acc[44] / (double)nvalid;
+          // the histogram counted (pixel, channel) entries; the reference divides by valid PIXELS (photo_tracking.py:85-86)
+          const unsigned nvalid_px = nvalid / (unsigned)nch;
+          const double mse = s_acc[44] / (double)nvalid_px;
           const double dn = sqrt(dn2), gnorm = sqrt(gn2);
           const double rel = fabs((mse_prev - mse) / mse_prev);  // NaN on the first iteration -> false
           const bool done = (it + 1 >= term.max_iter) || (dn < (double)term.delta_norm) ||
@@ -779,7 +779,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
             st[2] = (float)gnorm;
             st[3] = (float)dn;
             st[4] = sigma;
-            st[5] = (float)nvalid;
+            st[5] = (float)nvalid_px;
             st[6] = done ? 1.0f : 0.0f;
             st[7] = 0.0f;
 #pragma unroll
@@ -904,11 +904,13 @@ static int g_track_cand_cap = CAND_CAP;
 // keyframe-side re-layout: (vals, P, J, mask) -> 512-pixel tiles [P | I_ref | J 0..3 | J 4..5 | residual]
 // ---------------------------------------------------------------------------------------------
 __global__ void track_pack_kernel(const float* __restrict__ vals, const float* __restrict__ P, const float* __restrict__ J,
-                                  const uint8_t* __restrict__ mask, int n, uint8_t* __restrict__ pack) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // slot index over whole tiles
-  const int ntiles = (n + TILE - 1) / TILE;
-  if (i >= ntiles * TILE) return;
-  const int t = i / TILE, j = i % TILE;
+                                  const uint8_t* __restrict__ mask, int n, int nch, uint8_t* __restrict__ pack) {
+  const int ntiles = (n + TILE - 1) / TILE;            // tiles per channel
+  const int slots = ntiles * TILE;
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // slot index over channels x whole tiles
+  if (s >= (long long)nch * slots) return;
+  const int ch = (int)(s / slots), i = (int)(s % slots);
+  const int t = ch * ntiles + i / TILE, j = i % TILE;
   uint8_t* tile = pack + (size_t)t * PK_TILE_BYTES;
   const float qn = __int_as_float(0x7fc00000);
   const bool use = (i < n) && (mask == nullptr || mask[i] != 0);
@@ -916,12 +918,13 @@ __global__ void track_pack_kernel(const float* __restrict__ vals, const float* _
   float4 ja = make_float4(0.f, 0.f, 0.f, 0.f);
   float2 jb = make_float2(0.f, 0.f);
   if (use) {
+    const size_t e = (size_t)i * nch + ch;             // (pixel, channel) entry of vals (n,c) and J (n,c,8)
     X = P[3 * (size_t)i];
     Y = P[3 * (size_t)i + 1];
     Z = P[3 * (size_t)i + 2];
-    I = vals[i];
-    ja = *reinterpret_cast<const float4*>(J + 8 * (size_t)i);
-    jb = *reinterpret_cast<const float2*>(J + 8 * (size_t)i + 4);
+    I = vals[e];
+    ja = *reinterpret_cast<const float4*>(J + 8 * e);
+    jb = *reinterpret_cast<const float2*>(J + 8 * e + 4);
   }
   float* tp = reinterpret_cast<float*>(tile + PK_P_OFF) + 3 * j;
   tp[0] = X;
@@ -934,14 +937,15 @@ __global__ void track_pack_kernel(const float* __restrict__ vals, const float* _
 }
 
 // ---------------------------------------------------------------------------------------------
-// precalc_jacobians: dI/dxi = gradI * dpi/dP * [-P^ | I]; cols 6,7 = [I_ref, 1].
+// precalc_jacobians: dI/dxi = gradI * dpi/dP * [-P^ | I]; cols 6,7 = [I_ref, 1].  One thread per (pixel, channel).
 // ---------------------------------------------------------------------------------------------
 __global__ void precalc_jac_kernel(const float* __restrict__ grads, const float* __restrict__ P,
-                                   const float* __restrict__ vals, float fx, float fy, int64_t n,
+                                   const float* __restrict__ vals, float fx, float fy, int64_t entries, int nch,
                                    float* __restrict__ J) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float gx = grads[2 * i], gy = grads[2 * i + 1];
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= entries) return;
+  const int64_t i = e / nch;
+  const float gx = grads[2 * e], gy = grads[2 * e + 1];
   const float X = P[3 * i], Y = P[3 * i + 1], Z = P[3 * i + 2];
   // rows of dpi/dP: [fx, 0, -fx X/Z]/Z and [0, fy, -fy Y/Z]/Z  (camera.py:20-37)
   const float t1 = fx * X / Z, t2 = fy * Y / Z;
@@ -956,10 +960,10 @@ __global__ void precalc_jac_kernel(const float* __restrict__ grads, const float*
   o0.w = gx * d00;
   o1.x = gy * d11;
   o1.y = gx * d02 + gy * d12;
-  o1.z = vals[i];
+  o1.z = vals[e];
   o1.w = 1.0f;
-  *reinterpret_cast<float4*>(J + 8 * i) = o0;
-  *reinterpret_cast<float4*>(J + 8 * i + 4) = o1;
+  *reinterpret_cast<float4*>(J + 8 * e) = o0;
+  *reinterpret_cast<float4*>(J + 8 * e + 4) = o1;
 }
 
 }  // namespace como
@@ -972,9 +976,9 @@ extern "C" size_t como_b200_track_workspace_bytes(int32_t max_n, int32_t num_pro
   return L.total;
 }
 
-extern "C" size_t como_b200_track_pack_bytes(int32_t n) {
+extern "C" size_t como_b200_track_pack_bytes(int32_t n, int32_t c) {
   if (n <= 0) return 0;
-  return (size_t)((n + TILE - 1) / TILE) * PK_TILE_BYTES;
+  return (size_t)(c > 1 ? c : 1) * (size_t)((n + TILE - 1) / TILE) * PK_TILE_BYTES;
 }
 
 extern "C" int como_b200_track_pack(const como_b200_track_level_t* lv, void* stream_) {
@@ -984,9 +988,11 @@ extern "C" int como_b200_track_pack(const como_b200_track_level_t* lv, void* str
   COMO_REQUIRE(lv->vals && lv->P && lv->J && lv->pack, "track_pack: null pointer (vals, P, J and pack are required)");
   COMO_REQUIRE(((uintptr_t)lv->J & 15) == 0 && ((uintptr_t)lv->pack & 127) == 0,
                "track_pack: J must be 16-byte and pack 128-byte aligned");
-  const int slots = (lv->n + TILE - 1) / TILE * TILE;
-  track_pack_kernel<<<(slots + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(lv->vals, lv->P, lv->J, lv->mask, lv->n,
-                                                                           (uint8_t*)lv->pack);
+  COMO_REQUIRE(lv->c >= 0 && lv->c <= 16, "track_pack: %d channels", lv->c);
+  const int nch = lv->c > 1 ? lv->c : 1;
+  const long long slots = (long long)nch * ((lv->n + TILE - 1) / TILE * TILE);
+  track_pack_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(lv->vals, lv->P, lv->J, lv->mask, lv->n,
+                                                                                         nch, (uint8_t*)lv->pack);
   return check_launch("track_pack");
 }
 
@@ -1011,7 +1017,8 @@ extern "C" int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_
       COMO_REQUIRE(lv.n >= 0 && lv.w >= 3 && lv.h >= 3, "track_pyr: bad level shape n=%d w=%d h=%d", lv.n, lv.w, lv.h);
       COMO_REQUIRE(lv.n == 0 || (lv.pack && lv.img), "track_pyr: null level pointer (pack and img are required)");
       COMO_REQUIRE(((uintptr_t)lv.pack & 127) == 0, "track_pyr: pack must be 128-byte aligned");
-      if (lv.n > max_n) max_n = lv.n;
+      COMO_REQUIRE(lv.c >= 0 && lv.c <= 16, "track_pyr: %d channels", lv.c);
+      if (lv.n > 0 && level_entries(lv) > max_n) max_n = level_entries(lv);
     }
   TrackLaunchCfg cfg;
   const int G = track_config(num_problems, max_n, &cfg);
@@ -1094,13 +1101,14 @@ extern "C" int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_
 }
 
 extern "C" int como_b200_precalc_jacobians(const float* grads, const float* P, const float* vals,
-                                           const float* K, int64_t n, float* J, void* stream_) {
+                                           const float* K, int64_t n, int32_t c, float* J, void* stream_) {
   COMO_REQUIRE(grads && P && vals && K && J, "precalc_jacobians: null pointer argument");
-  COMO_REQUIRE(n >= 0, "precalc_jacobians: negative n");
+  COMO_REQUIRE(n >= 0 && c >= 1, "precalc_jacobians: bad sizes n=%lld c=%d", (long long)n, c);
   COMO_REQUIRE(((uintptr_t)J & 15) == 0, "precalc_jacobians: J must be 16-byte aligned");
   if (n == 0) return COMO_B200_OK;
   const int threads = 256;
-  const int64_t blocks = (n + threads - 1) / threads;
-  precalc_jac_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream_>>>(grads, P, vals, K[0], K[4], n, J);
+  const int64_t entries = n * c;
+  const int64_t blocks = (entries + threads - 1) / threads;
+  precalc_jac_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream_>>>(grads, P, vals, K[0], K[4], entries, c, J);
   return check_launch("precalc_jacobians");
 }

@@ -60,18 +60,17 @@ def _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, keep, used=None)
     max_n = 0
     for l in range(num_levels):
         v0, P0, J0, m0 = vals_i[l], Pi[l], dI_dT[l], masks[l]
-        if v0.shape[-1] != 1:
-            raise NotImplementedError("como_b200 tracking supports tracking.color: gray (C=1) only")
+        nch = int(v0.shape[-1])                       # image channels: 1 (gray) or 3 (rgb)
         img = img_j[l]
-        if img.shape[0] != 1 or img.shape[1] != 1:
-            raise NotImplementedError("como_b200 tracking expects img_j[l] of shape (1,1,h,w)")
+        if img.shape[0] != 1 or img.shape[1] != nch:
+            raise RuntimeError(f"como_b200 tracking expects img_j[l] of shape (1,{nch},h,w), got {tuple(img.shape)}")
         img = img.contiguous().float()
         Kl = _k9_list(intrinsics[l])
-        n = v0.numel()
-        max_n = max(max_n, n)
+        n = v0.numel() // max(nch, 1)
         a = arr[l]
         a.img = img.data_ptr()
-        a.n, a.w, a.h = n, img.shape[-1], img.shape[-2]
+        a.n, a.w, a.h, a.c = n, img.shape[-1], img.shape[-2], nch
+        max_n = max(max_n, n * nch)
         for k in range(9):
             a.K[k] = Kl[k]
         dev = v0.device
@@ -81,14 +80,14 @@ def _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, keep, used=None)
                 ent[1] == tuple(t._version for t in (v0, P0, J0, m0)):
             pack = ent[2]
         else:
-            v = v0.reshape(-1).float().contiguous()
+            v = v0.reshape(-1).float().contiguous()                 # (n, c) entries
             P = P0.reshape(-1, 3).float().contiguous()
-            J = _aligned(J0.reshape(-1, 8).float())
+            J = _aligned(J0.reshape(-1, 8).float())                 # (n, c, 8) -> one row per entry
             m = m0.reshape(-1).contiguous()
             if m.dtype != torch.uint8:
                 m = m.view(torch.uint8) if m.dtype == torch.bool else m.to(torch.uint8)
             a.vals, a.P, a.J, a.mask = v.data_ptr(), P.data_ptr(), J.data_ptr(), m.data_ptr()
-            pack = torch.empty(max(int(_lib.track_pack_bytes(n)), 128), dtype=torch.uint8, device=dev)
+            pack = torch.empty(max(int(_lib.track_pack_bytes(n, nch)), 128), dtype=torch.uint8, device=dev)
             a.pack = pack.data_ptr()
             if n > 0:
                 _lib.check(_lib.track_pack(C.byref(a), _lib.stream_ptr(dev)), "como_b200_track_pack")
@@ -109,7 +108,8 @@ def _level_structs(vals_i, Pi, dI_dT, masks, intrinsics, img_j, keep, used=None)
 
 def photo_tracking_pyr(Tji_init, aff_init, vals_i, Pi, dI_dT, masks, intrinsics, img_j, photo_sigma,
                        term_criteria, return_stats=False):
-    """Coarse-to-fine inverse-compositional tracking; inputs are per-level lists (coarsest first).
+    """Coarse-to-fine inverse-compositional tracking; inputs are per-level lists (coarsest first); vals (1,N,C),
+    dI_dT (1,N,C,8), img_j (1,C,h,w) with C = 1 (tracking.color: gray) or 3 (rgb).
 
     Like the reference, `photo_sigma` is accepted and ignored (the scale is 1.4826 * median |r|,
     photo_tracking.py:132-138).  Returns (Tji (1,4,4), aff (1,2,1)) [, stats (iters, 32): see COMO_B200_TRACK_STAT_STRIDE].
@@ -213,17 +213,16 @@ class TrackBatchPlan:
 
 
 def precalc_jacobians(dI_dw, P, vals, intrinsics):
-    """dI_dw (B,N,C,2), P (B,N,3), vals (B,N,C), intrinsics (3,3) -> (B,N,C,8); C must be 1."""
+    """dI_dw (B,N,C,2), P (B,N,3), vals (B,N,C), intrinsics (3,3) -> (B,N,C,8); C = 1 (gray) or 3 (rgb)."""
     dev = _lib.require_cuda(dI_dw, P, vals)
-    if vals.shape[2] != 1:
-        raise NotImplementedError("como_b200 precalc_jacobians supports C=1 only")
+    c = int(vals.shape[2])
     b, n, _ = P.shape
     g = dI_dw.reshape(-1, 2).contiguous().float()
     Pf = P.reshape(-1, 3).contiguous().float()
     v = vals.reshape(-1).contiguous().float()
-    J = torch.empty(b * n, 8, dtype=torch.float32, device=dev)
+    J = torch.empty(b * n * c, 8, dtype=torch.float32, device=dev)
     K = (C.c_float * 9)(*_k9_list(intrinsics))
     with torch.cuda.device(dev):
-        st = _lib.precalc_jacobians(_lib.ptr(g), _lib.ptr(Pf), _lib.ptr(v), K, b * n, _lib.ptr(J), _lib.stream_ptr(dev))
+        st = _lib.precalc_jacobians(_lib.ptr(g), _lib.ptr(Pf), _lib.ptr(v), K, b * n, c, _lib.ptr(J), _lib.stream_ptr(dev))
     _lib.check(st, "como_b200_precalc_jacobians")
-    return J.reshape(b, n, 1, 8).to(dI_dw.dtype)
+    return J.reshape(b, n, c, 8).to(dI_dw.dtype)

@@ -23,7 +23,8 @@ consumers copy on the way out (get_kf_viz_data clones; get_kf_ref_data goes thro
 the queue, and como_b200's TupleTensorQueue.pop returns tensors that own their memory), so nothing in the reference's
 flow observes the difference; code that keeps raw slices across iterate() calls must clone them.
 Everything else (UNet, orchestration) keeps running the reference's own Python on the
-same device.  Requires tracking.dtype float / mapping.dtype double, color gray.
+same device.  Requires tracking.dtype float / mapping.dtype double, color gray (the tracking operators themselves also
+take rgb; the Tracking class front-end and the mapper do not).
 """
 import sys
 

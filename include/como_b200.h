@@ -36,7 +36,7 @@ const char* como_b200_last_error(void);
 void como_b200_se3_exp(const double* tau_phi, double* T16);
 
 /* ------------------------------------------------------------------------------------------
- * Tracking: frame-to-keyframe inverse-compositional photometric GN (fp32, C = 1 channel).
+ * Tracking: frame-to-keyframe inverse-compositional photometric GN (fp32, gray or rgb).
  * Replaces como/odom/frontend/photo_tracking.py:10-42 (photo_tracking_pyr), :147-185
  * (photo_level_tracking), :117-143 (tracking_iter), :77-114 (robustify/solve/update) and the
  * torch ops under them (geometry/camera.py:57-68, frontend/photo_utils.py:9-31, lietorch SE3.exp).
@@ -45,17 +45,21 @@ void como_b200_se3_exp(const double* tau_phi, double* T16);
 /* A level as the reference passes it (vals, P, J, mask) plus `pack`: the same operands re-laid out ONCE per keyframe
  * by como_b200_track_pack into 512-pixel tiles [P | I_ref | J cols 0..3 | J cols 4..5 | residual scratch] (masked and
  * padding pixels carry NaN points), so that each GN pass streams one contiguous run per tile with the TMA unit and the
- * residual travels inside the Jacobian tile instead of through a second array.  como_b200_track_pyr reads only
- * pack, img, n, w, h, K; it WRITES the residual slots of `pack` (one launch at a time per pack). */
+ * residual travels inside the Jacobian tile instead of through a second array.  With c > 1 image channels
+ * (tracking.color: rgb, como/odom/Tracking.py:57-60) the tiles of channel 0 come first, then those of channel 1, ...:
+ * every (pixel, channel) pair is one entry with its own I_ref and Jacobian row and a copy of the point.
+ * como_b200_track_pyr reads only pack, img, n, w, h, c, K; it WRITES the residual slots of `pack` (one launch at a
+ * time per pack). */
 typedef struct {
-  const float* vals;   /* (n)     reference intensities I_i            [photo_tracking.py:24 vals_i]  */
+  const float* vals;   /* (n,c)   reference intensities I_i            [photo_tracking.py:24 vals_i]  */
   const float* P;      /* (n,3)   reference points in the KF frame     [Pi]                           */
-  const float* J;      /* (n,8)   dI/d[xi,a,b] as precalc_jacobians lays it out; cols 6 (rewritten every iteration by the
-                        *          reference, photo_tracking.py:125) and 7 (ones) are not read         [dI_dT] */
+  const float* J;      /* (n,c,8) dI/d[xi,a,b] as precalc_jacobians lays it out; cols 6 (rewritten every iteration by
+                        *          the reference, photo_tracking.py:125) and 7 (ones) are not read     [dI_dT] */
   const uint8_t* mask; /* (n) 0/1 or NULL: which points take part      [masks]                        */
-  const float* img;    /* (h,w)   target image of this level           [img_j]                        */
-  void* pack;          /* como_b200_track_pack_bytes(n) bytes, 128-byte aligned, filled by como_b200_track_pack */
+  const float* img;    /* (c,h,w) target image of this level           [img_j]                        */
+  void* pack;          /* como_b200_track_pack_bytes(n, c) bytes, 128-byte aligned, filled by como_b200_track_pack */
   int32_t n, w, h;
+  int32_t c;           /* image channels: 1 (gray; 0 is read as 1) or 3 (rgb)                         */
   float K[9];          /* row-major 3x3 intrinsics of this level       [intrinsics]                   */
 } como_b200_track_level_t;
 
@@ -75,7 +79,7 @@ typedef struct {
 size_t como_b200_track_workspace_bytes(int32_t max_n, int32_t num_problems);
 /* Keyframe-side re-layout (once per keyframe and level; the reference's update_kf_reference, Tracking.py:243-379,
  * is where vals / P / J / mask are produced).  Reads level->vals, P, J (cols 0..5), mask, n; writes level->pack. */
-size_t como_b200_track_pack_bytes(int32_t n);
+size_t como_b200_track_pack_bytes(int32_t n, int32_t c);
 int como_b200_track_pack(const como_b200_track_level_t* level, void* stream);
 
 /* levels: HOST array [num_problems][num_levels] (coarsest first, as the reference stores pyramids).
@@ -88,10 +92,10 @@ int como_b200_track_pyr(const como_b200_track_level_t* levels, int32_t num_level
  * 0 forces the histogram-narrowing path for every iteration.  Both paths return the same exact order statistic. */
 void como_b200_track_debug_candidate_cap(int32_t cap);
 
-/* Replaces precalc_jacobians (como/odom/frontend/photo_tracking.py:46-74), C = 1.
- * grads (n,2) [gx,gy]; P (n,3); vals (n); K 9 floats (host); out J (n,8). */
+/* Replaces precalc_jacobians (como/odom/frontend/photo_tracking.py:46-74).
+ * grads (n,c,2) [gx,gy]; P (n,3); vals (n,c); K 9 floats (host); c channels; out J (n,c,8). */
 int como_b200_precalc_jacobians(const float* grads, const float* P, const float* vals, const float* K,
-                                int64_t n, float* J, void* stream);
+                                int64_t n, int32_t c, float* J, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Exact segmented lower median (torch.median semantics) of non-negative values; NaN entries are

@@ -29,13 +29,14 @@ def ref_cfg():
     return yaml.safe_load(open(os.path.join(ref_harness.REF, "config", "como.yml")))
 
 
-def make_tracker(H, W, end_level, max_iter=50):
+def make_tracker(H, W, end_level, max_iter=50, color="gray"):
     ref_harness.load_reference()
     import como.odom.Tracking as TR
 
     TR.init_gpu = lambda d: None
     cfg = copy.deepcopy(ref_cfg()["tracking"])
     cfg["device"] = "cpu"
+    cfg["color"] = color
     cfg["pyr"]["end_level"] = end_level
     cfg["term_criteria"]["max_iter"] = max_iter
     K = synth.make_intrinsics(H, W)
@@ -44,13 +45,13 @@ def make_tracker(H, W, end_level, max_iter=50):
     return tr, cfg
 
 
-def gen_track(name, H, W, end_level, max_iter, cell):
+def gen_track(name, H, W, end_level, max_iter, cell, color="gray"):
     """photo_tracking_pyr inputs/outputs + per-iteration trace + handle_frame decisions."""
     ref_harness.load_reference()
     import como.odom.frontend.photo_tracking as PT
 
     torch.manual_seed(0)
-    tr, cfg = make_tracker(H, W, end_level, max_iter)
+    tr, cfg = make_tracker(H, W, end_level, max_iter, color)
     rgb = synth.make_rgb(H, W, seed=0, cell=cell)
     depth = synth.make_depth(H, W)
     pose = torch.eye(4)[None]
@@ -630,6 +631,7 @@ def main():
     if what in ("track", "all"):
         gen_track("track_80x60_l3", 60, 80, 3, 50, 4)
         gen_track("track_80x60_l3_it1", 60, 80, 3, 1, 4)  # BASELINE config 1 shape (max_iter 1), shrunk
+        gen_track("track_80x60_l3_rgb", 60, 80, 3, 50, 4, color="rgb")  # tracking.color: rgb (C = 3)
         gen_track("track_160x120_l4", 120, 160, 4, 50, 8)
     if what in ("cov", "all"):
         gen_cov("depthcov")

@@ -31,7 +31,7 @@ def golden_levels(g):
                 K=[t(f"K_{l}") for l in range(nl)], img=[t(f"img_{l}") for l in range(nl)])
 
 
-@pytest.mark.parametrize("name", ["track_80x60_l3", "track_80x60_l3_it1", "track_160x120_l4"])
+@pytest.mark.parametrize("name", ["track_80x60_l3", "track_80x60_l3_it1", "track_160x120_l4", "track_80x60_l3_rgb"])
 def test_track_pyr_vs_reference_golden(golden_dir, name):
     g = load(golden_dir, name)
     term = dict(TERM, max_iter=int(g["max_iter"]))
@@ -41,9 +41,10 @@ def test_track_pyr_vs_reference_golden(golden_dir, name):
     np.testing.assert_allclose(aff.cpu().numpy().ravel(), g["aff_final"].ravel(), atol=1e-4)
 
 
-@pytest.mark.parametrize("name", ["track_80x60_l3", "track_160x120_l4"])
+@pytest.mark.parametrize("name", ["track_80x60_l3", "track_160x120_l4", "track_80x60_l3_rgb"])
 def test_tracking_iter_same_inputs_vs_golden(golden_dir, name):
-    """Replay each recorded reference iteration from its own (T, aff): one level, max_iter 1."""
+    """Replay each recorded reference iteration from its own (T, aff): one level, max_iter 1.  The rgb golden
+    (tracking.color: rgb, C = 3) exercises the channel-stacked tiles: valid counts are pixels, sums run over channels."""
     g = load(golden_dir, name)
     lv = golden_levels(g)
     counts = [int(torch.from_numpy(g[f"mask_{l}"]).sum()) for l in range(int(g["num_levels"]))]
@@ -56,7 +57,8 @@ def test_tracking_iter_same_inputs_vs_golden(golden_dir, name):
         nvalid = int(g["trace_nvalid"][i])
         assert abs(st[5] - nvalid) <= 2
         assert abs(st[1] - g["trace_mse"][i]) <= (1e-4 + 2.0 / nvalid) * g["trace_mse"][i]
-        assert abs(st[2] - g["trace_gnorm"][i]) <= 2e-3 * max(g["trace_gnorm"][i], 1.0)
+        # |g| is what is left of sum w J r after cancellation; three channels leave three times the rounding noise
+        assert abs(st[2] - g["trace_gnorm"][i]) <= (2e-3 if "rgb" not in name else 6e-3) * max(g["trace_gnorm"][i], 1.0)
         assert se3_log_err(T[0].cpu().numpy(), g["trace_T_out"][i, 0]) < 1e-5
         np.testing.assert_allclose(aff.cpu().numpy().ravel(), g["trace_aff_out"][i].ravel(), atol=1e-5)
 
@@ -327,10 +329,36 @@ def test_golden_inputs_replay(golden_dir, name):
     replay_check(lv, stats, T[0].cpu().numpy(), aff.cpu().numpy().ravel(), strict=False)
 
 
-def test_precalc_jacobians_vs_golden(golden_dir):
+def test_rgb_every_iteration_vs_oracle(golden_dir):
+    """C = 3: every iteration the kernel ran, replayed by the channel-aware oracle from the kernel's own iterate:
+    valid pixels +-2, sigma (median over all valid (pixel, channel) residuals) and the robust error 1e-4 relative,
+    update within 1e-4."""
+    g = load(golden_dir, "track_80x60_l3_rgb")
+    lv = golden_levels(g)
+    T, aff, stats = cuda_track(lv, torch.from_numpy(g["T_init"]), torch.from_numpy(g["aff_init"]),
+                               dict(TERM, max_iter=int(g["max_iter"])))
+    st = stats.cpu().numpy()
+    assert st.shape[0] == len(g["trace_mse"])
+    for i in range(st.shape[0]):
+        l = int(st[i, 0])
+        m = lv["mask"][l].reshape(-1)
+        out = TO.tracking_iter_multi(torch.from_numpy(st[i, 8:24].reshape(4, 4).copy()), torch.from_numpy(st[i, 24:26].copy()),
+                                     lv["vals"][l].reshape(-1, 3)[m], lv["P"][l].reshape(-1, 3)[m],
+                                     lv["dI_dT"][l].reshape(-1, 3, 8)[m], lv["K"][l], lv["img"][l][0])
+        Tn, affn, delta, mse, gn, H, gr, sigma, nvalid = out
+        assert abs(st[i, 5] - nvalid) <= 2
+        q = 2.0 / max(3 * nvalid, 1)
+        assert abs(st[i, 4] - sigma) <= 2e-6 + (1e-5 + q) * sigma
+        assert abs(st[i, 1] - mse) <= (2e-4 + 4 * q) * mse
+        T_next = st[i + 1, 8:24].reshape(4, 4) if i + 1 < st.shape[0] else T[0].cpu().numpy()
+        assert se3_log_err(T_next, Tn.numpy()) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["track_80x60_l3", "track_80x60_l3_rgb"])
+def test_precalc_jacobians_vs_golden(golden_dir, name):
     from como_b200.odom.frontend.photo_tracking import precalc_jacobians
 
-    g = load(golden_dir, "track_80x60_l3")
+    g = load(golden_dir, name)
     for l in range(int(g["num_levels"])):
         c = lambda k: torch.from_numpy(g[k]).cuda()
         J = precalc_jacobians(c(f"grads_{l}"), c(f"P_{l}"), c(f"vals_{l}"), torch.from_numpy(g[f"K_{l}"]))

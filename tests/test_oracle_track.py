@@ -21,7 +21,7 @@ def se3_log_err(Ta, Tb):
     return np.linalg.norm(w) + np.linalg.norm(D[:3, 3])
 
 
-@pytest.mark.parametrize("name", ["track_80x60_l3", "track_80x60_l3_it1", "track_160x120_l4"])
+@pytest.mark.parametrize("name", ["track_80x60_l3", "track_80x60_l3_it1", "track_160x120_l4", "track_80x60_l3_rgb"])
 def test_track_pyr_matches_reference(golden_dir, name):
     g = load(golden_dir, name)
     nl = int(g["num_levels"])
@@ -104,3 +104,31 @@ def test_se3_exp_is_the_matrix_exponential():
         ref = expm(A)
         np.testing.assert_allclose(TO.se3_exp_tau_phi(tau, phi).numpy(), ref, rtol=0, atol=1e-13)
         np.testing.assert_allclose(lietorch.SE3.exp(x[None]).matrix()[0].numpy(), ref, rtol=0, atol=1e-13)
+
+
+def level_inputs_multi(g, n):
+    """Masked per-level operands (C channels) for the level whose point count is n."""
+    for l in range(int(g["num_levels"])):
+        if g[f"P_{l}"].shape[1] == n:
+            m = torch.from_numpy(g[f"mask_{l}"]).reshape(-1)
+            C = g[f"vals_{l}"].shape[-1]
+            return (torch.from_numpy(g[f"vals_{l}"]).reshape(-1, C)[m], torch.from_numpy(g[f"P_{l}"]).reshape(-1, 3)[m],
+                    torch.from_numpy(g[f"dI_dT_{l}"]).reshape(-1, C, 8)[m], torch.from_numpy(g[f"K_{l}"]),
+                    torch.from_numpy(g[f"img_{l}"])[0])
+    raise AssertionError("level not found")
+
+
+def test_tracking_iter_rgb_same_inputs(golden_dir):
+    """tracking.color: rgb (C = 3): every recorded reference iteration replayed from the reference's own inputs."""
+    g = load(golden_dir, "track_80x60_l3_rgb")
+    assert g["vals_0"].shape[-1] == 3
+    for i in range(len(g["trace_mse"])):
+        vals, P, J, K, img = level_inputs_multi(g, int(g["trace_n"][i]))
+        T_in = torch.from_numpy(g["trace_T_in"][i, 0])
+        aff_in = torch.from_numpy(g["trace_aff_in"][i]).reshape(2)
+        Tn, affn, delta, mse, gn, H, gr, sigma, nvalid = TO.tracking_iter_multi(T_in, aff_in, vals, P, J, K, img)
+        assert abs(nvalid - int(g["trace_nvalid"][i])) <= 2
+        assert abs(mse - g["trace_mse"][i]) <= (1e-4 + 2.0 / nvalid) * g["trace_mse"][i]
+        assert abs(gn - g["trace_gnorm"][i]) <= 2e-3 * max(g["trace_gnorm"][i], 1.0)
+        np.testing.assert_allclose(delta.numpy(), g["trace_delta"][i].ravel(), atol=2e-5)
+        assert se3_log_err(Tn.numpy(), g["trace_T_out"][i, 0]) < 1e-5
