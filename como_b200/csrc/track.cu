@@ -6,8 +6,9 @@
 //   como/odom/frontend/photo_utils.py:9-31, como/odom/backend/robust_loss.py:9-16.
 //
 // Layout of the launch: grid (G, B) -- G co-resident CTAs share one of B independent problems.  A CTA is
-// 4 consumer warps + 1 producer warp, up to 3 CTAs per SM.  The keyframe-side operands are re-laid out once per
-// keyframe (como_b200_track_pack) into 512-pixel tiles
+// 4 consumer warps + 1 producer warp, 1 to 4 CTAs per SM (two builds of the kernel: 128 registers for up to 3,
+// 96 registers for 4).  The keyframe-side operands are re-laid out once per keyframe (como_b200_track_pack) into
+// 512-pixel tiles (with c > 1 image channels: the tiles of channel 0, then channel 1, ... -- one entry per (pixel, channel))
 //   [ P 12 B/px | I_ref 4 | J cols 0..3 16 | J cols 4..5 8 | residual 4 ]      (masked / padding pixels: NaN points)
 // so that the producer warp streams ONE contiguous run per tile and pass with the TMA unit (cp.async.bulk + mbarrier,
 // SASS UBLKCP), always as far ahead as the ring allows:
@@ -386,8 +387,6 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
     const como_b200_track_level_t lv = levels[l];
     if (lv.n <= 0) continue;
     const int N = level_entries(lv);     // (pixel, channel) entries incl. tile padding
-    const int nch = lv.c > 1 ? lv.c : 1;
-    const int tiles_per_channel = (lv.n + TILE - 1) / TILE;
     const int w = lv.w, h = lv.h;
     const SliceInfo sl = slice_of(N, G, c);
     const int Ga = sl.active;            // group size of this level
@@ -532,6 +531,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         // the residuals of tile t are formed -- cost 36 spilled values per tile pair in this kernel and measured 0.65
         // against 0.71 of the roofline; 12-16 resident warps per SM hide the tap latency instead.)
         P1 sa;
+        const int tiles_per_channel = (lv.n + TILE - 1) / TILE;
         for (int t = 0; t < ntiles;) {
           const int ch = (tile0 + t) / tiles_per_channel;
           const int t_end = min(ntiles, (ch + 1) * tiles_per_channel - tile0);
@@ -649,19 +649,24 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         const float4* sJA = reinterpret_cast<const float4*>(stage + ST2_JA) + tid;
         const float2* sJB = reinterpret_cast<const float2*>(stage + ST2_JB) + tid;
         const float* sR = (t * TILE < r_cap ? (s_r + t * TILE) : reinterpret_cast<const float*>(stage + ST2_R)) + tid;
-        float rr[PB], iref[PB];
-        float4 ja[PB];
-        float2 jb[PB];
+        // the 96-register build loads the tile's four pixels per thread in two batches: 16 instead of 32 operand
+        // registers next to the 49 accumulators
+        constexpr int PH = (OCC_BOUND >= 4) ? PB / 2 : PB;
 #pragma unroll
-        for (int k = 0; k < PB; ++k) {  // padding and masked pixels: pass 1 left NaN
-          rr[k] = sR[k * CONS_THREADS];
-          iref[k] = sI[k * CONS_THREADS];
-          ja[k] = sJA[k * CONS_THREADS];
-          jb[k] = sJB[k * CONS_THREADS];
+        for (int k0 = 0; k0 < PB; k0 += PH) {
+        float rr[PH], iref[PH];
+        float4 ja[PH];
+        float2 jb[PH];
+#pragma unroll
+        for (int k = 0; k < PH; ++k) {  // padding and masked pixels: pass 1 left NaN
+          rr[k] = sR[(k0 + k) * CONS_THREADS];
+          iref[k] = sI[(k0 + k) * CONS_THREADS];
+          ja[k] = sJA[(k0 + k) * CONS_THREADS];
+          jb[k] = sJB[(k0 + k) * CONS_THREADS];
         }
-        stage_release(&empty2[s]);
+        if (k0 + PH >= PB) stage_release(&empty2[s]);
 #pragma unroll
-        for (int k = 0; k < PB; ++k) {
+        for (int k = 0; k < PH; ++k) {
           const float r = rr[k];
           if (r == r) {
             // this iteration's column 6 is -e^{-a} I_j = (b - r) - I_ref (photo_tracking.py:124-127)
@@ -685,6 +690,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
               for (int m = 2 * a2; m < 8; ++m, ++q) A2[q] = __ffma2_rn(W[a2], D[m], A2[q]);
             }
           }
+        }
         }
       }
       // unpack the row pairs into the packed upper triangle
@@ -766,7 +772,7 @@ track_pyr_kernel(const como_b200_track_level_t* __restrict__ levels_all, int num
         __syncwarp();
         if (lane == 0) {
           // the histogram counted (pixel, channel) entries; the reference divides by valid PIXELS (photo_tracking.py:85-86)
-          const unsigned nvalid_px = nvalid / (unsigned)nch;
+          const unsigned nvalid_px = nvalid / (unsigned)(lv.c > 1 ? lv.c : 1);
           const double mse = s_acc[44] / (double)nvalid_px;
           const double dn = sqrt(dn2), gnorm = sqrt(gn2);
           const double rel = fabs((mse_prev - mse) / mse_prev);  // NaN on the first iteration -> false
