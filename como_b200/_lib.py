@@ -103,6 +103,7 @@ kmat_kmm = _sig("como_b200_kmat_kmm", C.c_int, [VP, I32, I32, I32, VP, I32, F64,
 kmat_predictor = _sig("como_b200_kmat_predictor", C.c_int, [VP, I32, I32, I32, VP, VP, VP, I32, F64, VP, VP])
 chol_solve_workspace_bytes = _sig("como_b200_chol_solve_workspace_bytes", C.c_size_t, [I32])
 chol_ctas = _sig("como_b200_chol_ctas", None, [I32])
+chol_schedule = _sig("como_b200_chol_schedule", None, [C.c_int32])
 chol_solve = _sig("como_b200_chol_solve", C.c_int, [VP, VP, I32, VP, VP, C.c_size_t, VP])
 kmat_rows = _sig("como_b200_kmat_rows", C.c_int, [VP, I32, I32, I32, VP, VP, VP, I32, F64, VP, VP, I64, VP, VP, VP, VP])
 weighted_gram = _sig("como_b200_weighted_gram", C.c_int, [VP, VP, VP, VP, I64, I32, F64, F64, VP, VP, VP, VP])
@@ -136,7 +137,7 @@ DECLARED_SYMBOLS = [
     "como_b200_median_dist_compact_f64", "como_b200_median_dist_finish_f64",
     "como_b200_ba_priors", "como_b200_ba_update", "como_b200_cross_covariance", "como_b200_chol_append",
     "como_b200_sampler_workspace_bytes", "como_b200_sampler_greedy", "como_b200_kmat_kmm", "como_b200_kmat_predictor",
-    "como_b200_chol_solve_workspace_bytes", "como_b200_chol_solve", "como_b200_chol_ctas",
+    "como_b200_chol_solve_workspace_bytes", "como_b200_chol_solve", "como_b200_chol_ctas", "como_b200_chol_schedule",
     "como_b200_kmat_rows", "como_b200_weighted_gram", "como_b200_rows_residual",
     "como_b200_reproject_dense", "como_b200_sample_depth_gradmag", "como_b200_sfm_linearize", "como_b200_sfm_accumulate",
     "como_b200_handoff_pack", "como_b200_gray_pyramid", "como_b200_image_pyramid_fused", "como_b200_image_gradients", "como_b200_img_and_grads_f64", "como_b200_kf_reference_level", "como_b200_reproj_depth",

@@ -289,10 +289,10 @@ __device__ void inverse64(CholSmem& S, long long* clk = nullptr) {
 // ---- panel solve  X L^T = T  in place (T: S.T, L: lower factor in S.X, 8 x 8 inverses in S.L8inv), blocked
 // substitution on the tensor path.  Warp w owns rows 8w..8w+7 and never needs another warp's rows: no block barrier.
 //   X[:, cb] = (T[:, cb] - sum_{mb<cb} X[:, mb] L[cb, mb]^T) L8inv_cb^T
-__device__ void trsm64(CholSmem& S) {
+__device__ void trsm64(CholSmem& S, double* Tbuf = nullptr) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g4 = lane >> 2, l4 = lane & 3;
-  double* Tw = S.T + (8 * warp) * CPITCH;
+  double* Tw = (Tbuf ? Tbuf : S.T) + (8 * warp) * CPITCH;
   const double* L = S.X;
   for (int cb = 0; cb < 8; ++cb) {
     double c0 = 0.0, c1 = 0.0;
@@ -467,6 +467,272 @@ chol_factor_kernel(CholView v, const int2* __restrict__ table, int ntiles) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Second schedule of the same factorisation: ONE CTA walks the critical path.
+// In the schedule above the chain  diag(k) -> L(k+1,k) -> diag(k+1)  crosses two CTAs per column: flag, fence and a
+// 32 KB tile through L2 each time, ~20 us per column.  Here CTA 0 owns every diagonal tile AND the tile below it and
+// keeps the operands of the chain in shared memory:
+//     T = P_D(k) - L(k,k-1) L(k,k-1)^T  ->  potrf  ->  L(k+1,k) = P_S(k+1,k) L(k,k)^-T  ->  next column,
+// where the helpers (all other CTAs) have pre-accumulated everything that does not depend on the previous column:
+//     P_D(k)     = A(k,k)   - sum_{j <= k-2} L(k,j)   L(k,j)^T        (kind TK_PRE_DIAG, written in place)
+//     P_S(k+1,k) = A(k+1,k) - sum_{j <= k-1} L(k+1,j) L(k,j)^T        (kind TK_PRE_SUB,  written in place)
+// and do the rest of the panel (rows >= k+2, incl. the right-hand-side row) and the 64 x 64 inverses for the backward
+// substitution (TK_INV) as before.  Helper tiles are listed column-major and dealt round-robin; every dependency of a
+// helper tile is an earlier helper tile or a result of CTA 0 for a column <= its own, and CTA 0 waits only for helper
+// tiles of the column it is in: no cycle, all CTAs resident (cooperative launch).
+// ------------------------------------------------------------------------------------------------------------------
+enum { TK_PANEL = 0, TK_PRE_DIAG = 1, TK_PRE_SUB = 2, TK_INV = 3 };
+
+__device__ __forceinline__ int helper_tiles_in_column(int nb, int k) {
+  return (k >= 2 ? 1 : 0) + (k >= 1 ? 1 : 0) + 1 + (nb - k - 1 > 0 ? nb - k - 1 : 0);
+}
+
+__global__ void chol_table2_kernel(int nb, int4* __restrict__ table) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nb) return;
+  int off = 0;
+  for (int c = 0; c < k; ++c) off += helper_tiles_in_column(nb, c);
+  if (k >= 2) table[off++] = make_int4(k, k, TK_PRE_DIAG, 0);
+  if (k >= 1) table[off++] = make_int4(k + 1, k, TK_PRE_SUB, 0);
+  for (int i = k + 2; i <= nb; ++i) table[off++] = make_int4(i, k, TK_PANEL, 0);
+  table[off++] = make_int4(k, k, TK_INV, 0);
+}
+
+__device__ __forceinline__ void wait_flag(const int* f) {
+  while (ld_acquire_i32(f) == 0) {
+  }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1)
+chol_factor2_kernel(CholView v, const int4* __restrict__ table, int ntiles, int* __restrict__ pflags) {
+  extern __shared__ __align__(16) unsigned char craw[];
+  CholSmem& S = *reinterpret_cast<CholSmem*>(craw);
+  __shared__ double s_invdiag[CT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g4 = lane >> 2, l4 = lane & 3;
+  const int nb = v.nb;
+
+  // ------------------------------------------------------------------------------------------ CTA 0: the chain
+  if (blockIdx.x == 0) {
+    double* Lprev = S.B[1];   // L(k, k-1), left here by the previous column
+    double* Sub = S.A[0];     // the tile below the diagonal: P_S(k+1,k) in, L(k+1,k) out
+    double* Dnext = S.A[1];   // P_D(k+1), prefetched while the solve runs
+    __shared__ int s_have_next;
+    if (tid == 0) s_have_next = 0;
+    __syncthreads();
+    for (int k = 0; k < nb; ++k) {
+      unsigned long long* tl = g_chol_timeline ? g_chol_timeline + 8 * (size_t)k : nullptr;   // debug stamps
+      if (tl && tid == 0) tl[0] = gtime();
+      int pitch;
+      double* gt = tile_ptr(v, k, k, pitch);
+      // T = P_D(k) - L(k,k-1) L(k,k-1)^T, lower 8 x 8 tiles only (the factorisation never reads the others): the 36
+      // tiles are dealt to the 8 warps round-robin -- 4.5 tiles per warp instead of the 8 of a full product, on an
+      // SM whose fp64 rate makes a 64^3 product cost 2 us
+      const bool have = (s_have_next != 0);   // uniform: written before the last barrier of the previous column
+      if (!have && k >= 2) {
+        if (tid == 0) wait_flag(pflags + k * nb + k);
+        __syncthreads();
+      }
+      {
+        int rbs[5], cbs[5];
+        double c0[5], c1[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const int tt = min(warp + 8 * q, 35);   // the fifth slot of warps 4..7 repeats tile 35 (result discarded)
+          int rb = 0;
+          while ((rb + 1) * (rb + 2) / 2 <= tt) ++rb;
+          rbs[q] = rb;
+          cbs[q] = tt - rb * (rb + 1) / 2;
+          c0[q] = c1[q] = 0.0;
+        }
+        if (k >= 1) {
+#pragma unroll 2
+          for (int ks = 0; ks < CT / 4; ++ks) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q)   // five independent accumulator pairs in flight
+              dmma884c(c0[q], c1[q], Lprev[(8 * rbs[q] + g4) * CPITCH + l4 + 4 * ks], Lprev[(8 * cbs[q] + g4) * CPITCH + l4 + 4 * ks]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          if (warp + 8 * q < 36) {
+            const int r = 8 * rbs[q] + g4, col = 8 * cbs[q] + 2 * l4;
+            const double2 own = have ? *reinterpret_cast<const double2*>(Dnext + r * CPITCH + col)
+                                     : __ldcg(reinterpret_cast<const double2*>(gt + (size_t)r * pitch + col));
+            S.T[r * CPITCH + col] = own.x - c0[q];
+            S.T[r * CPITCH + col + 1] = own.y - c1[q];
+          }
+        }
+      }
+      __syncthreads();
+      if (tl && tid == 0) tl[1] = gtime();
+      potrf64(S, s_invdiag);
+      if (tl && tid == 0) tl[2] = gtime();
+      // the tile below the diagonal (row nb = the right-hand side): start fetching it while the factor goes out.
+      // (Polling for it from an idle warp during the factorisation was measured: what the earlier fetch saves, the
+      // polls cost the pivot warps at the block barriers.)
+      const int i = k + 1;
+      int pitch2;
+      double* gt2 = tile_ptr(v, i, k, pitch2);
+      if (k >= 1) {
+        if (tid == 0) wait_flag(pflags + i * nb + k);
+        __syncthreads();
+      }
+      for (int e = tid; e < CT * CT / 2; e += CH_THREADS) {
+        const int r = e >> 5, c = 2 * (e & 31);
+        cp_async16(Sub + r * CPITCH + c, gt2 + (size_t)r * pitch2 + c);
+      }
+      cp_async_commit();
+      if (tl && tid == 0) tl[3] = gtime();
+      for (int e = tid; e < CT * CT; e += CH_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        const double val = (c <= r) ? S.T[r * CPITCH + c] : 0.0;
+        gt[(size_t)r * pitch + c] = val;
+        S.X[r * CPITCH + c] = val;          // the factor, operand of the solve below
+      }
+      for (int e = tid; e < 8 * 64; e += CH_THREADS) v.l8inv[(size_t)k * 512 + e] = S.L8inv[e >> 6][e & 63];
+      // No fence by every thread here: the block barrier orders the other threads' stores before thread 0's release,
+      // and a release is cumulative -- only thread 0 waits for the stores to be performed, the rest moves on.
+      __syncthreads();
+      if (tid == 0) {
+        st_release_i32(v.flags + k * nb + k, 1);
+        // P_D(k+1) is normally long finished: fetch it behind the solve (else the next column loads it the slow way)
+        s_have_next = (k + 1 < nb && (k + 1 < 2 || ld_acquire_i32(pflags + (k + 1) * nb + (k + 1)) != 0)) ? 1 : 0;
+      }
+      cp_async_wait<0>();
+      __syncthreads();
+      if (s_have_next) {
+        int pn;
+        const double* gn = tile_ptr(v, k + 1, k + 1, pn);
+        for (int e = tid; e < CT * CT / 2; e += CH_THREADS) {
+          const int r = e >> 5, c = 2 * (e & 31);
+          cp_async16(Dnext + r * CPITCH + c, gn + (size_t)r * pn + c);
+        }
+        cp_async_commit();
+      }
+      if (tl && tid == 0) tl[4] = gtime();
+      trsm64(S, Sub);
+      __syncthreads();
+      if (tl && tid == 0) tl[5] = gtime();
+      for (int e = tid; e < CT * CT / 2; e += CH_THREADS) {
+        const int r = e >> 5, c = 2 * (e & 31);
+        const double2 val = *reinterpret_cast<const double2*>(Sub + r * CPITCH + c);
+        *reinterpret_cast<double2*>(gt2 + (size_t)r * pitch2 + c) = val;
+        *reinterpret_cast<double2*>(Lprev + r * CPITCH + c) = val;
+      }
+      cp_async_wait<0>();
+      __syncthreads();
+      if (tid == 0) st_release_i32(v.flags + i * nb + k, 1);
+      if (tl && tid == 0) tl[6] = gtime();
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------------------------------ helpers
+  for (int t = blockIdx.x - 1; t < ntiles; t += gridDim.x - 1) {
+    const int4 ent = table[t];
+    const int i = ent.x, k = ent.y, kind = ent.z;
+    if (kind == TK_INV) {
+      // the 64 x 64 inverse of the diagonal block, used by the backward substitution
+      if (tid == 0) wait_flag(v.flags + k * nb + k);
+      __syncthreads();
+      int lp;
+      const double* src = tile_ptr(v, k, k, lp);
+      for (int e = tid; e < CT * CT / 2; e += CH_THREADS) {
+        const int r = e >> 5, c = 2 * (e & 31);
+        cp_async16(S.T + r * CPITCH + c, src + (size_t)r * lp + c);
+      }
+      const double* s8 = v.l8inv + (size_t)k * 512;
+      for (int e = tid; e < 256; e += CH_THREADS) cp_async16(&S.L8inv[0][0] + 2 * e, s8 + 2 * e);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
+      inverse64(S);
+      for (int e = tid; e < CT * CT; e += CH_THREADS) v.linv[(size_t)k * CT * CT + e] = S.X[(e >> 6) * CPITCH + (e & 63)];
+      __syncthreads();
+      continue;
+    }
+    const int jend = (kind == TK_PRE_DIAG) ? k - 1 : k;   // terms j in [0, jend)
+    double acc[8][2];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c][0] = acc[c][1] = 0.0;
+    int pitch;
+    double* gt = tile_ptr(v, i, k, pitch);
+    double2 own[8];   // A_ik: nobody has written it yet
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      own[c] = *reinterpret_cast<const double2*>(gt + (size_t)(8 * warp + g4) * pitch + 8 * c + 2 * l4);
+    auto stage = [&](int j, int buf) {
+      if (tid == 0) {
+        wait_flag(v.flags + i * nb + j);
+        if (i != k) wait_flag(v.flags + k * nb + j);
+      }
+      __syncthreads();
+      load_tile_async(v, i, j, S.A[buf]);
+      if (i != k) load_tile_async(v, k, j, S.B[buf]);
+      cp_async_commit();
+    };
+    if (jend > 0) stage(0, 0);
+    for (int j = 0; j < jend; ++j) {
+      const int buf = j & 1;
+      if (j + 1 < jend) {
+        stage(j + 1, buf ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      tile_gemm(S.A[buf], (i != k) ? S.B[buf] : S.A[buf], acc);
+      __syncthreads();
+    }
+    if (kind != TK_PANEL) {
+      // pre-accumulated tile for CTA 0: A_ik - acc, in place
+      const int r = 8 * warp + g4;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<double2*>(gt + (size_t)r * pitch + 8 * c + 2 * l4) = make_double2(own[c].x - acc[c][0], own[c].y - acc[c][1]);
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release_i32(pflags + i * nb + k, 1);
+      continue;
+    }
+    {
+      const int r = 8 * warp + g4;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int col = 8 * c + 2 * l4;
+        S.T[r * CPITCH + col] = own[c].x - acc[c][0];
+        S.T[r * CPITCH + col + 1] = own[c].y - acc[c][1];
+      }
+    }
+    if (tid == 0) wait_flag(v.flags + k * nb + k);
+    __syncthreads();
+    {
+      int lp;
+      const double* src = tile_ptr(v, k, k, lp);
+      for (int e = tid; e < CT * CT / 2; e += CH_THREADS) {
+        const int r = e >> 5, c = 2 * (e & 31);
+        cp_async16(S.X + r * CPITCH + c, src + (size_t)r * lp + c);
+      }
+      const double* s8 = v.l8inv + (size_t)k * 512;
+      for (int e = tid; e < 256; e += CH_THREADS) cp_async16(&S.L8inv[0][0] + 2 * e, s8 + 2 * e);
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    trsm64(S);
+    __syncthreads();
+    for (int e = tid; e < CT * CT / 2; e += CH_THREADS) {
+      const int r = e >> 5, c = 2 * (e & 31);
+      *reinterpret_cast<double2*>(gt + (size_t)r * pitch + c) = *reinterpret_cast<const double2*>(S.T + r * CPITCH + c);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_i32(v.flags + i * nb + k, 1);
+  }
+}
+
 // Backward substitution L^T x = y.  CTA k owns block column k: s = sum_{i>k} L_ik^T x_i as the x_i arrive,
 // x_k = Linv_k^T (y_k - s).
 __global__ void __launch_bounds__(CH_THREADS)
@@ -541,9 +807,13 @@ extern "C" int como_b200_chol_debug_probe(double* tile, long long* clk) {
 static int g_chol_ctas = 0;
 extern "C" void como_b200_chol_ctas(int32_t ctas) { g_chol_ctas = ctas > 0 ? ctas : 0; }
 
+// 1 (default): CTA 0 walks the critical path (chol_factor2_kernel); 0: every tile is an independent dataflow task
+static int g_chol_schedule = getenv("COMO_B200_CHOL_SCHEDULE") ? atoi(getenv("COMO_B200_CHOL_SCHEDULE")) : 1;
+extern "C" void como_b200_chol_schedule(int32_t mode) { g_chol_schedule = mode; }
+
 extern "C" size_t como_b200_chol_solve_workspace_bytes(int32_t n) {
   const size_t nb = (n + CT - 1) / CT;
-  return align256(sizeof(int) * ((nb + 1) * nb + nb)) + align256(sizeof(int2) * (nb * (nb + 3) / 2 + 8)) +
+  return align256(sizeof(int) * (2 * (nb + 1) * nb + nb)) + align256(sizeof(int4) * (nb * (nb + 3) / 2 + 3 * nb + 8)) +
          align256(sizeof(double) * nb * CT * CT) * 2 + align256(sizeof(double) * nb * 512) +
          align256(sizeof(double) * nb * CT * nb * CT) + 256;
 }
@@ -564,9 +834,10 @@ extern "C" int como_b200_chol_solve(const double* H, const double* g, int32_t n,
   v.nb = nb;
   v.flags = (int*)w;
   int* xflags = v.flags + (nb + 1) * nb;
-  w += align256(sizeof(int) * ((nb + 1) * nb + nb));
+  int* pflags = xflags + nb;
+  w += align256(sizeof(int) * (2 * (nb + 1) * nb + nb));
   int2* table = (int2*)w;
-  w += align256(sizeof(int2) * (nb * (nb + 3) / 2 + 8));
+  w += align256(sizeof(int4) * (nb * (nb + 3) / 2 + 3 * nb + 8));
   v.aug = (double*)w;
   w += align256(sizeof(double) * nb * CT * CT);
   v.linv = (double*)w;
@@ -586,7 +857,26 @@ extern "C" int como_b200_chol_solve(const double* H, const double* g, int32_t n,
   if (grid > ntiles) grid = ntiles;
   // Both kernels spin on flags written by other CTAs of the same grid: launched cooperatively so that the runtime
   // refuses the launch (instead of letting it hang) if the CTAs cannot all be resident.
-  {
+  if (g_chol_schedule == 1 && sm_count() >= 2) {
+    int nh = 0;   // helper tiles
+    for (int k = 0; k < nb; ++k) nh += (k >= 2 ? 1 : 0) + (k >= 1 ? 1 : 0) + 1 + (nb - k - 1 > 0 ? nb - k - 1 : 0);
+    cudaMemsetAsync(pflags, 0, sizeof(int) * (nb + 1) * nb, st);
+    int4* table4 = (int4*)table;
+    chol_table2_kernel<<<(nb + 63) / 64, 64, 0, st>>>(nb, table4);
+    cudaFuncSetAttribute(chol_factor2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CholSmem));
+    int grid2 = sm_count();
+    if (g_chol_ctas > 1 && g_chol_ctas < grid2) grid2 = g_chol_ctas;
+    if (grid2 > nh + 1) grid2 = nh + 1;
+    const int4* tb = table4;
+    int* pf = pflags;
+    void* args[] = {(void*)&v, (void*)&tb, (void*)&nh, (void*)&pf};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)chol_factor2_kernel, dim3(grid2), dim3(CH_THREADS), args,
+                                                sizeof(CholSmem), st);
+    if (e != cudaSuccess) {
+      set_last_error("chol_factor2: cooperative launch failed: %s", cudaGetErrorString(e));
+      return COMO_B200_ELAUNCH;
+    }
+  } else {
     int nt = ntiles;
     const int2* tb = table;
     void* args[] = {(void*)&v, (void*)&tb, (void*)&nt};

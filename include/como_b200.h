@@ -247,6 +247,10 @@ int como_b200_kmat_predictor(const double* cov_img, int32_t B, int32_t H, int32_
 size_t como_b200_chol_solve_workspace_bytes(int32_t n);
 /* Grid size of the factorisation (0 = one CTA per SM, the default). */
 void como_b200_chol_ctas(int32_t ctas);
+/* Schedule of the factorisation: 1 (default) = one CTA walks the critical path (diagonal tile + the tile below it)
+ * with operands kept in shared memory while the others pre-accumulate; 0 = every tile an independent dataflow task.
+ * Same arithmetic per tile; tuning / test hook. */
+void como_b200_chol_schedule(int32_t mode);
 int como_b200_chol_solve(const double* H, const double* g, int32_t n, double* x, void* workspace,
                          size_t workspace_bytes, void* stream);
 
