@@ -305,8 +305,8 @@ class ShardComm:
 
 
 # kernels of one iteration on one GPU, counted in profiles/ (scaffold, predictor stream, 2 medians, residual, accumulation
-# + scatter, priors, solve (3), update + small element-wise ones)
-LAUNCHES_PER_ITERATION = 36
+# + scatter, priors, solve (5: copy, prep, tile table, factorisation, back substitution), update + small ones)
+LAUNCHES_PER_ITERATION = 36   # counted in profiles/r02_launches_bench_all.csv (own kernels per timed step)
 
 
 _IN_PLACE_STATE = ("kf_poses", "kf_aff_params", "recent_poses", "recent_aff_params", "P_m")
