@@ -12,6 +12,6 @@ build() {  # name, flags...
   nvcc -shared -o variants/libcomo_b200_$name.so build/track_v_$name.o $OTHERS -lcudart
   echo "built variants/libcomo_b200_$name.so ($*)"
 }
-build o4 -DTRK_MAX_OCC=4 &
-build d2 -DTRK_P1_DEPTH=2 &
+build s2 -DTRK_STAGES1=2 &
+build o3 -DTRK_MAX_OCC=3 &
 wait
