@@ -177,6 +177,7 @@ struct AccumSmem {
   double refz[2][TP][REF_STRIDE];    // z_n, q_n of a tile (one bulk copy), double buffered, one tile ahead of X
   double Z[2][TG][TP + 1][ZPITCH];   // [J_i | J_j | r] of the unit's own target group (+1 row: fragment overrun)
   double C[2][TP][CPITCH];           // stack coefficients and A = sum alpha^2 per pixel
+  double Cp[TG][TP][11];             // per coefficient warp: partial [D(8) | B | A] of a pixel (odd pitch: no conflicts)
   unsigned long long mbarX[XST], mbarR[2];
 };
 
@@ -381,12 +382,32 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
           S.Z[buf][tt][pl][16] = rs;
         }
       }
-      if (primary && (pa2 != 0.0 || par != 0.0)) {
-        double* dst = &S.C[buf][pl][0];
-        atomicAdd(dst + C_A, pa2);
-        atomicAdd(dst + C_B, par);
+      // The four coefficient warps hold partial sums of the same pixel's D, B, A columns.  They used to add them
+      // into S.C with shared-memory double atomics: 90 % of the kernel's excess shared wavefronts
+      // (profiles/r02_ba_photo_kernels_full.txt) and an order that changed from run to run.  Now each warp leaves its
+      // partials in its own slot and reduce_partials() sums the four in a fixed order.
+      {
+        double* dst = &S.Cp[tt][pl][0];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) atomicAdd(dst + q, pD[q]);
+        for (int q = 0; q < 8; ++q) dst[q] = primary ? pD[q] : 0.0;
+        dst[8] = primary ? par : 0.0;
+        dst[9] = primary ? pa2 : 0.0;
+      }
+    };
+    // thread -> (pixel, column group): D[0..3], D[4..7], B, A of C[buf] = sum over the four warps' partials
+    auto reduce_partials = [&](int buf) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int px = rt & 31, part = rt >> 5;
+      double* dst = &S.C[buf][px][0];
+      if (part < 2) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int col = 4 * part + q;
+          dst[col] = ((S.Cp[0][px][col] + S.Cp[1][px][col]) + S.Cp[2][px][col]) + S.Cp[3][px][col];
+        }
+      } else {
+        const int col = (part == 2) ? 8 : 9;
+        dst[part == 2 ? C_B : C_A] = ((S.Cp[0][px][col] + S.Cp[1][px][col]) + S.Cp[2][px][col]) + S.Cp[3][px][col];
       }
     };
 
@@ -398,27 +419,16 @@ ba_accum_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ coor
       prefetch(0);
       mbar_wait(&S.mbarR[0], 0);
       build(0, 0);
+      reduce_partials(0);
       if (ntiles > 1) prefetch(1);
     }
     __syncthreads();
     for (int tile = 0; tile < ntiles; ++tile) {
       const int buf = tile & 1;
       if (tile + 1 < ntiles) {
-        // the accumulated columns (D, B, A) of C[buf^1] were consumed by the product role during the previous
-        // iteration: thread -> (pixel, column group)
-        {
-          const int px = rt & 31, part = rt >> 5;   // 4 parts: D[0..3], D[4..7], B, A
-          double* dst = &S.C[buf ^ 1][px][0];
-          if (part < 2) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dst[4 * part + q] = 0.0;
-          } else {
-            dst[part == 2 ? C_B : C_A] = 0.0;
-          }
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
         mbar_wait(&S.mbarR[buf ^ 1], ((tile + 1) >> 1) & 1);
         build(tile + 1, buf ^ 1);
+        reduce_partials(buf ^ 1);
         // refz[buf] (tile) is free now for tile + 2; its copy overlaps the next iteration
         if (tile + 2 < ntiles) {
           if (rt == 0) issue_R(tile + 2, buf);   // refz[buf] (tile) was last read during the previous iteration

@@ -346,7 +346,10 @@ def test_full_resolution_k32_headline_window_vs_oracle():
     assert eH < 1e-6 and eg < 1e-6, (eH, eg)
     ep, er, eP = rel(s.kf_poses, sc["kf_poses"]), rel(s.recent_poses, sc["recent_poses"]), rel(s.P_m, sc["P_m"])
     assert ep < 1e-5 and er < 1e-5 and eP < 1e-5, (ep, er, eP)                        # SE(3) log bound is 1e-3
-    assert rel(s.median_depths, sc["median_depths"]) < 1e-7
+    # The median depth of a keyframe is an ORDER STATISTIC of its 307 200 predicted depths, which sit ~1e-7 (relative)
+    # apart around the median: an update that differs from the oracle's in the tenth digit (fp64 atomics in the
+    # scatter land in a different order every run) can move the rank by a position or two.  Bound: a few spacings.
+    assert rel(s.median_depths, sc["median_depths"]) < 2e-6
 
 
 def test_reference_golden_k8_m64_256x192(golden_dir):
