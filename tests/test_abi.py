@@ -57,3 +57,19 @@ def test_se3_exp_of_the_library_is_the_matrix_exponential():
         out = (C.c_double * 16)()
         _lib.se3_exp(xin, out)
         np.testing.assert_allclose(np.array(out[:]).reshape(4, 4), expm(A), rtol=0, atol=1e-13)
+
+
+def test_tracker_pack_and_workspace_sizes_without_a_gpu():
+    """Host-side size functions of the tracker's packed keyframe tiles: 512-pixel tiles of 22 528 bytes
+    ([P 12 | I_ref 4 | J 24 | residual 4] B per pixel), one set of tiles per image channel."""
+    from como_b200 import _lib
+
+    tile = 512 * 44
+    assert _lib.track_pack_bytes(0, 1) == 0
+    assert _lib.track_pack_bytes(1, 1) == tile and _lib.track_pack_bytes(512, 1) == tile
+    assert _lib.track_pack_bytes(513, 1) == 2 * tile
+    assert _lib.track_pack_bytes(513, 3) == 3 * 2 * tile
+    assert _lib.track_pack_bytes(307200, 0) == 600 * tile           # c = 0 reads as one channel
+    # the workspace no longer depends on the number of points (the residuals live in the packed tiles)
+    assert _lib.track_workspace_bytes(1000, 4) == _lib.track_workspace_bytes(307200, 4)
+    assert _lib.track_workspace_bytes(1000, 8) > _lib.track_workspace_bytes(1000, 4)
