@@ -33,6 +33,13 @@ int median_launch(const T*, const long long*, int, long long, T, T*, long long*,
 
 constexpr double HUBER_KD = 1.345;
 
+// 8-byte read-only load with an L2 cache policy (createpolicy): for operands that are streamed once
+__device__ __forceinline__ double ldg_stream(const double* p, unsigned long long policy) {
+  double v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+  return v;
+}
+
 // ================================================================================================ pass A
 constexpr int RA_THREADS = 256;
 
@@ -65,6 +72,11 @@ ba_residual_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ c
   for (int ks = 0; ks < 16; ++ks) bfrag[ks] = (g4 < 7) ? s_vec[g4][4 * ks + l4] : 0.0;
   __shared__ double s_dot[RA_THREADS / 32][32][8];
   const int32_t* crd = coords + 2 * ((size_t)i * d.N);
+  // The 315 MB of gathered predictor rows are read once here: evict-first in L2, so that they do not push out the
+  // target frames' [I, gx, gy] planes, which several pairs (and the neighbouring keyframes' blocks) sample again --
+  // ncu showed every pair re-reading its whole target image from DRAM (813 MB for 416 MB algorithmic).  Measured
+  // effect of the hint alone: 185 -> 181 us; the re-reads are mostly capacity misses across waves.
+  const unsigned long long pol_rows = l2_policy_evict_first();
 #pragma unroll
   for (int rt = 0; rt < 4; ++rt) {
     const int n = n0 + 8 * rt + g4;
@@ -76,7 +88,7 @@ ba_residual_kernel(const double* __restrict__ Knm, const int32_t* __restrict__ c
     }
     double a[16];
 #pragma unroll
-    for (int ks = 0; ks < 16; ++ks) a[ks] = (rowok && 4 * ks + l4 < d.M) ? __ldg(row + 4 * ks + l4) : 0.0;
+    for (int ks = 0; ks < 16; ++ks) a[ks] = (rowok && 4 * ks + l4 < d.M) ? ldg_stream(row + 4 * ks + l4, pol_rows) : 0.0;
     double c0 = 0.0, c1 = 0.0;
 #pragma unroll
     for (int ks = 0; ks < 16; ++ks)
