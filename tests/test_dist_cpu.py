@@ -83,3 +83,20 @@ def test_sharded_ba_host_logic_gloo_world2(golden_dir):
         p.join(timeout=60)
     for r, msg in res:
         assert msg == "ok", f"rank {r}: {msg}"
+
+
+@pytest.mark.parametrize("K,world", [(32, 2), (32, 4), (32, 8), (8, 3), (5, 8), (1, 2)])
+def test_store_vars_keyframe_ranges_partition_the_window(K, world):
+    """ShardComm.kf_range: the contiguous keyframe ranges the ranks stream in store_vars are disjoint, ordered and
+    cover [0, K) -- also when K is not a multiple of the world size or smaller than it (empty ranges at the end)."""
+    from como_b200.odom.mapping_core import ShardComm
+
+    ranges = [ShardComm(world, r, torch.device("cpu")).kf_range(K) for r in range(world)]
+    covered = []
+    for lo, hi in ranges:
+        assert 0 <= lo <= hi <= K
+        covered += list(range(lo, hi))
+    assert covered == list(range(K))
+    sizes = [hi - lo for lo, hi in ranges]
+    assert max(sizes) - min(s for s in sizes if s > 0) <= max(sizes)   # contiguous blocks of ceil(K / world)
+    assert max(sizes) == -(-K // world)

@@ -132,3 +132,17 @@ def test_tracking_iter_rgb_same_inputs(golden_dir):
         assert abs(gn - g["trace_gnorm"][i]) <= 2e-3 * max(g["trace_gnorm"][i], 1.0)
         np.testing.assert_allclose(delta.numpy(), g["trace_delta"][i].ravel(), atol=2e-5)
         assert se3_log_err(Tn.numpy(), g["trace_T_out"][i, 0]) < 1e-5
+
+
+def test_multi_channel_oracle_reduces_to_the_gray_one(golden_dir):
+    """tracking_iter_multi with C = 1 is the same function as tracking_iter (same validity, median, sums)."""
+    g = load(golden_dir, "track_80x60_l3")
+    for i in (0, len(g["trace_mse"]) - 1):
+        vals, P, J, K, img = level_inputs(g, int(g["trace_n"][i]))
+        T_in = torch.from_numpy(g["trace_T_in"][i, 0])
+        aff_in = torch.from_numpy(g["trace_aff_in"][i]).reshape(2)
+        a = TO.tracking_iter(T_in, aff_in, vals, P, J, K, img)
+        b = TO.tracking_iter_multi(T_in, aff_in, vals[:, None], P, J[:, None, :], K, img[None])
+        assert a[8] == b[8] and abs(a[7] - b[7]) <= 1e-7 * a[7]            # nvalid, sigma
+        assert abs(a[3] - b[3]) <= 1e-5 * a[3]                             # mean_sq_err
+        np.testing.assert_allclose(b[2].numpy(), a[2].numpy(), atol=1e-5)  # delta
