@@ -477,15 +477,20 @@ def torch_cuda_reference_ops(K, R, M, N, H, W, P, dim, device, reps=3):
     out = {}
 
     def timed(name, fn):
-        fn()
+        # a LOWER bound: the fastest of `reps` repetitions after a warm-up (a repetition that has to cudaMalloc a
+        # multi-GB result -- the caching allocator's choice, not the operator's cost -- would otherwise inflate it)
+        r = fn()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        best = float("inf")
         for _ in range(reps):
+            r = None
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             r = fn()
-        e1.record()
-        torch.cuda.synchronize()
-        out[name] = e0.elapsed_time(e1) / reps
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out[name] = best
         return r
 
     def store_vars():
